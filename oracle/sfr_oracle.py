@@ -1,0 +1,337 @@
+"""CPU oracle for the SFR target builder (TEST INFRASTRUCTURE, not product).
+
+A NumPy restatement of the reference's non-augmented SFR path.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product path (pixelwiseregression_b200/) never
+does and fails loudly when the CUDA library is missing.
+
+Reference lines followed (relative to the reference tree):
+  datasets.py:208-211   CoM fallback (MSRA)               -> com_from_frame
+  datasets.py:306-309   crop box                          -> crop_box
+  utils.py:167-173      center_crop                       -> center_crop
+  datasets.py:312-319   depth window, centring, int CoM   -> window_and_centre
+  datasets.py:323       cv2.resize -> 128x128             -> resize_bilinear
+  datasets.py:330-332   cv2.resize -> 64x64, mask         -> resize_half / mask
+  datasets.py:350-358   uvd centring + heatmap coords     -> joint_coords
+  utils.py:37-62        generate_heatmap (4-tap splat)    -> splat4
+  utils.py:64-65        cv2.GaussianBlur 7x7 sigma 1.5    -> gaussian_blur7
+  datasets.py:369-383   Dmap + normalisation              -> process_sample
+  datasets.py:385-390   reject gate                       -> process_sample
+  utils.py:332-337      recover_uvd                       -> recover_uvd
+
+Third-party arithmetic that is NOT in the reference tree is restated from its
+published algorithm: OpenCV (env.yml: `opencv`, unpinned; pinned here to the
+container's 4.13.0) `cv2.resize` INTER_LINEAR and `cv2.GaussianBlur`; SciPy
+`center_of_mass`.  Parity pinning: the reference has no tests or golden
+vectors, so this oracle is pinned against outputs of the UNMODIFIED reference
+run in the build container (oracle/make_golden.py -> tests/golden/*.npz) and
+against cv2 directly when it is importable (tests/test_oracle_sfr.py).
+
+Dtype rules (NumPy-2 / NEP-50 promotion, probed on the reference):
+  * NYU/ICVL/HAND17 frames are float32 -> crop, window, resize, label are
+    float32; `crop[crop>0] -= com_z` is evaluated in float64 and rounded back
+    to float32; the window compare is done in float64.
+  * MSRA frames are float64 -> the whole image path is float64 until the final
+    `.float()`.
+  * Joint coordinates, heatmaps and Dmap are float64 until `.float()`.
+"""
+import math
+import numpy as np
+
+IMAGE_SIZE = 128
+LABEL_SIZE = 64
+KSIZE = 7
+SIGMA = 1.5
+
+
+# --------------------------------------------------------------------------- #
+# scalar / index helpers
+# --------------------------------------------------------------------------- #
+def com_from_frame(frame):
+    """datasets.py:208-211.  mean depth of positive pixels and the centre of
+    mass of the binary mask (scipy center_of_mass of `img > 0`)."""
+    pos = frame > 0
+    cnt = int(pos.sum())
+    mean = np.mean(frame[pos])
+    rows, cols = np.nonzero(pos)
+    # scipy: sum(input * grid) / sum(input) with input = bool mask -> exact ints
+    com_row = np.float64(rows.sum()) / np.float64(cnt)
+    com_col = np.float64(cols.sum()) / np.float64(cnt)
+    return np.array([com_col, com_row, np.float64(mean)], dtype=np.float64)
+
+
+def crop_box(com_z, cube, fx, fy):
+    """datasets.py:306-309."""
+    du = np.float64(cube) / np.float64(com_z) * np.float64(fx)
+    dv = np.float64(cube) / np.float64(com_z) * np.float64(fy)
+    return max(int(du + dv), 2)
+
+
+def crop_geometry(com, box, hf, wf):
+    """utils.py:167-173 index arithmetic.  Returns (r0, c0, shift, nrows,
+    ncols): the crop covers frame rows [r0-shift, r0-shift+nrows) and columns
+    [c0-shift, c0-shift+ncols) with zeros outside the frame.  nrows/ncols are
+    2*shift unless the padded-array slice truncates (CoM beyond the frame) and
+    0 when the Python slice is empty (negative CoM)."""
+    r0 = int(com[1])
+    c0 = int(com[0])
+    shift = box // 2
+
+    def extent(start, full):
+        n = full + 2 * shift
+        s = slice(start, start + 2 * shift).indices(n)
+        return max(0, s[1] - s[0]), s[0]
+
+    nrows, rs = extent(r0, hf)
+    ncols, cs = extent(c0, wf)
+    return r0, c0, shift, nrows, ncols, rs, cs
+
+
+def center_crop(frame, com, box):
+    """utils.py:167-173 without materialising the padded frame."""
+    hf, wf = frame.shape
+    r0, c0, shift, nrows, ncols, rs, cs = crop_geometry(com, box, hf, wf)
+    out = np.zeros((nrows, ncols), dtype=frame.dtype)
+    # padded index p maps to frame index p - shift
+    fr0, fc0 = rs - shift, cs - shift
+    ra, rb = max(fr0, 0), min(fr0 + nrows, hf)
+    ca, cb = max(fc0, 0), min(fc0 + ncols, wf)
+    if rb > ra and cb > ca:
+        out[ra - fr0:rb - fr0, ca - fc0:cb - fc0] = frame[ra:rb, ca:cb]
+    return out
+
+
+def window_and_centre(crop, com_z, cube):
+    """datasets.py:312,315.  Strict float64 window, then subtract com_z from
+    positive pixels (float64 arithmetic, rounded to the crop dtype)."""
+    z = np.float64(com_z)
+    lo = z - cube
+    hi = z + cube
+    keep = np.logical_and(crop.astype(np.float64) > lo, crop.astype(np.float64) < hi)
+    crop = crop * keep.astype(crop.dtype)
+    pos = crop > 0
+    crop[pos] = (crop[pos].astype(np.float64) - z).astype(crop.dtype)
+    return crop
+
+
+# --------------------------------------------------------------------------- #
+# OpenCV restatements
+# --------------------------------------------------------------------------- #
+def _linear_taps(dst, src):
+    """cv::resize INTER_LINEAR coefficient table (imgproc/resize.cpp): scale =
+    1/(dst/src) in double, fx = (float)((d+0.5)*scale-0.5), floor, clamp."""
+    inv_scale = np.float64(dst) / np.float64(src)
+    scale = np.float64(1.0) / inv_scale
+    idx = np.empty(dst, dtype=np.int64)
+    a1 = np.empty(dst, dtype=np.float32)
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(math.floor(f))
+        f = np.float32(f - np.float32(s))
+        if s < 0:
+            s, f = 0, np.float32(0)
+        if s >= src - 1:
+            s, f = src - 1, np.float32(0)
+        idx[d] = s
+        a1[d] = f
+    a0 = (np.float32(1.0) - a1).astype(np.float32)
+    return idx, a0, a1
+
+
+def resize_bilinear(src, dh=IMAGE_SIZE, dw=IMAGE_SIZE):
+    """cv2.resize(src, (dw, dh)) INTER_LINEAR for CV_32F / CV_64F: horizontal
+    2-tap pass then vertical 2-tap pass, coefficients held as float, products
+    and sums in the working type (float for CV_32F, double for CV_64F), no
+    antialiasing when shrinking."""
+    sh, sw = src.shape
+    wt = src.dtype.type
+    xi, xa0, xa1 = _linear_taps(dw, sw)
+    yi, ya0, ya1 = _linear_taps(dh, sh)
+    xi1 = np.minimum(xi + 1, sw - 1)
+    yi1 = np.minimum(yi + 1, sh - 1)
+    xa0 = xa0.astype(wt)
+    xa1 = xa1.astype(wt)
+    ya0 = ya0.astype(wt)[:, None]
+    ya1 = ya1.astype(wt)[:, None]
+    top = src[yi][:, xi] * xa0 + src[yi][:, xi1] * xa1
+    bot = src[yi1][:, xi] * xa0 + src[yi1][:, xi1] * xa1
+    return (top * ya0 + bot * ya1).astype(wt)
+
+
+def resize_half(img):
+    """cv2.resize 128->64 INTER_LINEAR: OpenCV reroutes an exact 2x shrink to
+    the INTER_AREA fast path = mean of each 2x2 block."""
+    wt = img.dtype.type
+    s = (img[0::2, 0::2] + img[0::2, 1::2]) + (img[1::2, 0::2] + img[1::2, 1::2])
+    return (s * wt(0.25)).astype(wt)
+
+
+def gaussian_kernel7():
+    """cv::getGaussianKernel(7, 1.5, CV_64F): exp(-x^2/(2 sigma^2)) / sum."""
+    x = np.arange(KSIZE, dtype=np.float64) - (KSIZE - 1) * 0.5
+    scale2x = -0.5 / (SIGMA * SIGMA)
+    k = np.exp(scale2x * x * x)
+    return k / k.sum()
+
+
+def _reflect101(i, n):
+    if i < 0:
+        return -i
+    if i >= n:
+        return 2 * n - 2 - i
+    return i
+
+
+def gaussian_blur7(h):
+    """cv2.GaussianBlur(h, (7,7), 1.5) on a float64 plane: separable, row pass
+    then column pass, BORDER_REFLECT_101."""
+    n = h.shape[0]
+    g = gaussian_kernel7()
+    idx = np.array([[_reflect101(i + k - 3, n) for k in range(KSIZE)] for i in range(n)])
+    rows = np.zeros_like(h)
+    for k in range(KSIZE):
+        rows += g[k] * h[:, idx[:, k]]
+    out = np.zeros_like(h)
+    for k in range(KSIZE):
+        out += g[k] * rows[idx[:, k], :]
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# joints
+# --------------------------------------------------------------------------- #
+def splat4(u, v, size=LABEL_SIZE):
+    """utils.py:37-62.  Centre-of-mass preserving 4-tap splat.  Negative
+    indices wrap NumPy-style; an index >= size raises (the reference turns that
+    into a rejected sample, datasets.py:362-365)."""
+    h = np.zeros((size, size))
+    low_u = int(np.floor(u))
+    low_v = int(np.floor(v))
+    du = u - low_u
+    dv = v - low_v
+    min_d = max(du + dv - 1, 0)
+    max_d = min(du, dv)
+    d = (max_d + min_d) / 2
+    b = du - d
+    c = dv - d
+    a = 1 + d - du - dv
+    h[low_v, low_u] = a
+    h[low_v, low_u + 1] = b
+    h[low_v + 1, low_u] = c
+    h[low_v + 1, low_u + 1] = d
+    return h
+
+
+def joint_coords(uvd, com_int, box):
+    """datasets.py:350-358.  Returns (centred+resized uvd [J,3] float64,
+    heatmap pixel coords [J,2] float64)."""
+    c = uvd.astype(np.float64) - com_int
+    r = c.copy()
+    r[:, :2] = r[:, :2] / (box - 1) * (IMAGE_SIZE - 1)
+    k = r.copy()
+    k[:, :2] = k[:, :2] / (IMAGE_SIZE - 1) * (LABEL_SIZE - 1) + np.array([LABEL_SIZE // 2, LABEL_SIZE // 2])
+    return r, k
+
+
+# --------------------------------------------------------------------------- #
+# one sample, end to end
+# --------------------------------------------------------------------------- #
+def process_sample(frame, uvd, com, cube, fx, fy, test_only=False, backend="numpy"):
+    """Non-augmented branch of HandDataset.process_single_data
+    (datasets.py:301-403).  `frame` float32 (NYU/ICVL/HAND17 semantics) or
+    float64 (MSRA semantics); `com` None -> CoM fallback.  Returns a dict with
+    float32 arrays named like the reference tuple plus `valid` (False where
+    the reference raises)."""
+    if backend == "cv2":
+        import cv2
+        do_resize = lambda s: cv2.resize(s, (IMAGE_SIZE, IMAGE_SIZE))
+        do_half = lambda s: cv2.resize(s, (LABEL_SIZE, LABEL_SIZE))
+        do_blur = lambda s: cv2.GaussianBlur(s, (KSIZE, KSIZE), SIGMA)
+    else:
+        do_resize, do_half, do_blur = resize_bilinear, resize_half, gaussian_blur7
+
+    J = 0 if uvd is None else uvd.shape[0]
+    f32 = np.float32
+    out = dict(valid=False,
+               img=np.zeros((1, IMAGE_SIZE, IMAGE_SIZE), f32),
+               label_img=np.zeros((1, LABEL_SIZE, LABEL_SIZE), f32),
+               mask=np.zeros((1, LABEL_SIZE, LABEL_SIZE), f32),
+               box_size=f32(0), cube_size=f32(cube), com=np.zeros(3, f32),
+               uvd=np.zeros((J, 3), f32),
+               heatmaps=np.zeros((J, LABEL_SIZE, LABEL_SIZE), f32),
+               dmap=np.zeros((J, LABEL_SIZE, LABEL_SIZE), f32))
+    if com is None:
+        com = com_from_frame(frame)
+    com = np.array(com, dtype=np.float64)
+    # integral cube sizes are Python ints in the reference (weak scalars)
+    cube_w = int(cube) if float(cube) == int(cube) else float(cube)
+
+    box = crop_box(com[2], cube_w, fx, fy)
+    crop = center_crop(frame, com, box)
+    if crop.shape[0] == 0 or crop.shape[1] == 0:
+        return out                                  # cv2.resize raises
+    crop = window_and_centre(crop.copy(), com[2], cube_w)
+    com[0] = int(com[0])
+    com[1] = int(com[1])
+    box = crop.shape[0]
+
+    img = do_resize(crop)
+    label = do_half(img)
+    mask = (label != 0).astype(np.float64)
+
+    wt = img.dtype.type
+    out["img"] = (img / wt(cube_w)).astype(f32)[None]
+    out["label_img"] = (label / wt(cube_w)).astype(f32)[None]
+    out["mask"] = mask.astype(f32)[None]
+    out["box_size"] = f32(box)
+    out["com"] = com.astype(f32)
+    bad = bool(np.isnan(out["img"]).any() or np.isnan(out["label_img"]).any())
+    if test_only:
+        # datasets.py:334-348 returns before the reject gate
+        out["valid"] = True
+        return out
+
+    r, k = joint_coords(uvd, com, box)
+    heat = np.zeros((LABEL_SIZE, LABEL_SIZE, J))
+    try:
+        for j in range(J):
+            heat[:, :, j] = do_blur(splat4(k[j, 0], k[j, 1]))
+    except (IndexError, ValueError, OverflowError):
+        return out                                  # "heatmap error"
+    dmap = np.zeros_like(heat)
+    for j in range(J):
+        heatmask = (heat[:, :, j] > 0).astype(np.float64) * mask
+        dmap[:, :, j] = (r[j, 2] - label) * heatmask
+    dmap = dmap / cube_w
+    nuvd = r.copy()
+    nuvd[:, :2] = nuvd[:, :2] / (IMAGE_SIZE - 1)
+    nuvd[:, 2] = nuvd[:, 2] / cube_w
+
+    out["uvd"] = nuvd.astype(f32)
+    out["heatmaps"] = np.ascontiguousarray(heat.transpose(2, 0, 1)).astype(f32)
+    out["dmap"] = np.ascontiguousarray(dmap.transpose(2, 0, 1)).astype(f32)
+    bad = bad or bool(np.isnan(nuvd).any() or np.isnan(heat).any() or np.isnan(dmap).any())
+    out["valid"] = (not bad) and float(mask.sum()) >= 10
+    return out
+
+
+FIELDS = ("img", "label_img", "mask", "box_size", "cube_size", "com", "uvd", "heatmaps", "dmap")
+
+
+def process_batch(frames, uvd, com, cube, fx, fy, test_only=False, backend="numpy"):
+    """Stack process_sample over a batch (the DataLoader's default_collate)."""
+    B = len(frames)
+    outs = [process_sample(frames[b], None if uvd is None else uvd[b],
+                           None if com is None else com[b], cube[b], fx, fy,
+                           test_only=test_only, backend=backend) for b in range(B)]
+    res = {k: np.stack([o[k] for o in outs]) for k in FIELDS}
+    res["valid"] = np.array([o["valid"] for o in outs], dtype=np.uint8)
+    return res
+
+
+def recover_uvd(uvd, box_size, com, cube):
+    """utils.py:332-337 (inverse of the uvd normalisation), float32."""
+    out = uvd.astype(np.float32).copy()
+    out[:, :, :2] = out[:, :, :2] * (box_size.astype(np.float32) - 1).reshape(-1, 1, 1)
+    out[:, :, 2] = out[:, :, 2] * cube.astype(np.float32)[:, None]
+    return out + com.astype(np.float32)[:, None, :]

@@ -1,0 +1,93 @@
+"""Deterministic synthetic depth frames / joints / logits.
+
+No datasets or checkpoints exist on the GPU box, so every test and benchmark
+runs on synthetic inputs shaped like the reference's datasets.  The constants
+are the reference's per-dataset intrinsics and cube sizes:
+NYU  datasets.py:693-696, MSRA datasets.py:406-409, HAND17 datasets.py:862-865,
+ICVL datasets.py:521-524.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class DatasetShape:
+    name: str
+    fx: float
+    fy: float
+    halfu: float
+    halfv: float
+    height: int
+    width: int
+    cube: float
+    joints: int
+    z_range: tuple
+    frame_f64: bool = False      # reference holds the frame as float64 (MSRA)
+    com_from_frame: bool = False  # load_from_text returns com=None (MSRA)
+
+
+NYU = DatasetShape("NYU", 588.037, 587.075, 320, 240, 480, 640, 150, 14, (500.0, 1000.0))
+HAND17 = DatasetShape("HAND17", 475.065948, 475.065857, 315.944855, 245.287079, 480, 640, 150, 21,
+                      (500.0, 1000.0))
+ICVL = DatasetShape("ICVL", 241.42, 241.42, 160, 120, 240, 320, 125, 16, (300.0, 550.0))
+MSRA = DatasetShape("MSRA", 241.42, 241.42, 160, 120, 240, 320, 125, 21, (300.0, 550.0),
+                    frame_f64=True, com_from_frame=True)
+
+SHAPES = {s.name: s for s in (NYU, HAND17, ICVL, MSRA)}
+
+
+def make_frames(shape: DatasetShape, batch: int, seed: int = 0, mixed_cube: bool = True):
+    """Host (NumPy) generator used by the parity tests.
+
+    Returns dict(frames [B,Hf,Wf] float32, com [B,3] float64, cube [B] float64,
+    uvd [B,J,3] float64).  A disc of radius 0.7*cube/z*fx px around the CoM is
+    filled with z + U(-100,100) mm; 5 % of the disc is clutter beyond the cube
+    and 5 % exact zeros, so the depth window and the mask are both exercised.
+    CoMs are non-integer and far enough off-centre that crop boxes straddle the
+    frame edge for part of the batch (zero-padding path)."""
+    rng = np.random.default_rng(seed)
+    hf, wf, J = shape.height, shape.width, shape.joints
+    frames = np.zeros((batch, hf, wf), dtype=np.float32)
+    com = np.empty((batch, 3), dtype=np.float64)
+    com[:, 0] = rng.uniform(0.25, 0.75, batch) * wf
+    com[:, 1] = rng.uniform(0.25, 0.75, batch) * hf
+    com[:, 2] = rng.uniform(shape.z_range[0], shape.z_range[1], batch)
+    cube = np.full(batch, float(shape.cube))
+    if mixed_cube and shape.name == "NYU":
+        # datasets.py:818-819: a second test subject uses int(cube*5/6)
+        cube[rng.uniform(size=batch) < 0.3] = float(int(shape.cube * 5 / 6))
+    uvd = np.empty((batch, J, 3), dtype=np.float64)
+    yy, xx = np.mgrid[0:hf, 0:wf]
+    for b in range(batch):
+        u0, v0, z0 = com[b]
+        rad = 0.7 * cube[b] / z0 * shape.fx
+        disc = (xx - u0) ** 2 + (yy - v0) ** 2 < rad * rad
+        n = int(disc.sum())
+        vals = z0 + rng.uniform(-100.0, 100.0, n)
+        sel = rng.uniform(size=n)
+        vals[sel < 0.05] = z0 + cube[b] + rng.uniform(1.0, 300.0, int((sel < 0.05).sum()))
+        vals[sel > 0.95] = 0.0
+        frames[b][disc] = vals.astype(np.float32)
+        box = max(int(cube[b] / z0 * shape.fx + cube[b] / z0 * shape.fy), 2)
+        shift = box // 2
+        uvd[b, :, 0] = u0 + rng.uniform(-0.6, 0.6, J) * shift
+        uvd[b, :, 1] = v0 + rng.uniform(-0.6, 0.6, J) * shift
+        uvd[b, :, 2] = z0 + rng.uniform(-100.0, 100.0, J)
+    if shape.com_from_frame:
+        # the CoM is recomputed from the frame by the SFR builder; keep the
+        # generator's value only as a hint for joint placement
+        pass
+    return dict(frames=frames, com=com, cube=cube, uvd=uvd)
+
+
+def make_decoder_inputs(batch: int, joints: int, seed: int = 0, hw: int = 64):
+    """Decoder micro-benchmark logits: z, D ~ N(0,1) float32,
+    w ~ U(0.5,1.5), label in [-1,1] with a binary mask."""
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((batch, joints, hw, hw)).astype(np.float32)
+    D = rng.standard_normal((batch, joints, hw, hw)).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, (joints, 1)).astype(np.float32)
+    mask = (rng.uniform(size=(batch, 1, hw, hw)) < 0.4).astype(np.float32)
+    label = (rng.uniform(-1.0, 1.0, (batch, 1, hw, hw)).astype(np.float32)) * mask
+    return dict(z=z, D=D, w=w, label=label, mask=mask)

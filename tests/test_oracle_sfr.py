@@ -1,0 +1,101 @@
+"""CPU: the SFR oracle against the reference-generated golden vectors, against
+OpenCV itself, and (build container only) against the live reference."""
+import numpy as np
+import pytest
+
+from oracle import sfr_oracle as so
+from oracle import ref_shim
+from pixelwiseregression_b200 import synth
+from helpers import SFR_FIELDS, assert_close, assert_sfr_matches, golden_shape, load_golden
+
+GOLDEN_SETS = ["sfr_nyu", "sfr_nyu_test_only", "sfr_hand17", "sfr_msra", "sfr_icvl", "sfr_edge"]
+
+
+def run_oracle_on_golden(g, backend="numpy"):
+    shape = golden_shape(g)
+    frames = g["frames"].astype(np.float64) if shape.frame_f64 else g["frames"]
+    com = None if shape.com_from_frame else g["com"]
+    return so.process_batch(frames, g["uvd"], com, g["cube"], shape.fx, shape.fy,
+                            test_only=bool(g["test_only"]), backend=backend)
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    got = run_oracle_on_golden(g)
+    names = SFR_FIELDS[:6] if bool(g["test_only"]) else SFR_FIELDS
+    ref = {n: g["ref_" + n] for n in names}
+    assert_sfr_matches(got, ref, names, g["ref_valid"], prefix=name + ":")
+
+
+def test_edge_golden_covers_reject_and_accept():
+    g = load_golden("sfr_edge")
+    v = g["ref_valid"]
+    assert v.sum() >= 8 and (v == 0).sum() >= 4
+
+
+def test_resize_restatement_vs_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for n in (28, 128, 150, 176, 234, 353, 880):
+        for dt in (np.float32, np.float64):
+            src = (rng.uniform(-100, 100, (n, n)) * (rng.uniform(size=(n, n)) < 0.7)).astype(dt)
+            ref = cv2.resize(src, (128, 128))
+            got = so.resize_bilinear(src)
+            assert got.dtype == ref.dtype
+            assert_close("resize %d %s" % (n, dt.__name__), got, ref, rtol=2e-7 if dt is np.float32 else 1e-14)
+            assert ((got != 0) == (ref != 0)).all()
+            half = cv2.resize(ref, (64, 64))
+            assert_close("half", so.resize_half(ref), half, rtol=2e-7 if dt is np.float32 else 1e-14)
+            assert ((so.resize_half(ref) != 0) == (half != 0)).all()
+    # non-square source (truncated crop)
+    src = rng.uniform(-50, 50, (200, 131)).astype(np.float32)
+    assert_close("nonsquare", so.resize_bilinear(src), cv2.resize(src, (128, 128)), rtol=2e-7)
+
+
+def test_blur_restatement_vs_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    k = cv2.getGaussianKernel(7, 1.5).ravel()
+    assert np.abs(k - so.gaussian_kernel7()).max() < 1e-16
+    for _ in range(50):
+        u, v = rng.uniform(-1, 62.99, 2)
+        h = so.splat4(u, v)
+        ref = cv2.GaussianBlur(h, (7, 7), 1.5)
+        got = so.gaussian_blur7(h)
+        assert np.abs(got - ref).max() < 1e-15
+        assert ((got > 0) == (ref > 0)).all()
+
+
+def test_splat_is_centre_of_mass_preserving():
+    rng = np.random.default_rng(2)
+    for _ in range(100):
+        u, v = rng.uniform(0, 62.99, 2)
+        h = so.splat4(u, v)
+        yy, xx = np.mgrid[0:64, 0:64]
+        assert abs(h.sum() - 1) < 1e-12
+        assert abs((h * xx).sum() - u) < 1e-10 and abs((h * yy).sum() - v) < 1e-10
+    with pytest.raises(IndexError):
+        so.splat4(63.0, 10.0)
+
+
+def test_recover_uvd_inverts_normalisation():
+    g = load_golden("sfr_nyu")
+    rec = so.recover_uvd(g["ref_uvd"], g["ref_box_size"], g["ref_com"], g["ref_cube_size"])
+    assert np.abs(rec - g["uvd"]).max() < 2e-3  # float32 pixels / millimetres
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("shape_name,batch,seed", [("NYU", 6, 100), ("MSRA", 3, 101), ("HAND17", 3, 102)])
+def test_oracle_matches_live_reference(shape_name, batch, seed):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from make_golden import run_reference_sfr
+    _, _, datasets = ref_shim.load()
+    shape = synth.SHAPES[shape_name]
+    d = synth.make_frames(shape, batch, seed)
+    frames = d["frames"].astype(np.float64) if shape.frame_f64 else d["frames"]
+    ref = run_reference_sfr(datasets, shape, frames, d["uvd"], d["com"], d["cube"])
+    got = so.process_batch(frames, d["uvd"], None if shape.com_from_frame else d["com"], d["cube"],
+                           shape.fx, shape.fy)
+    assert_sfr_matches(got, {n: ref["ref_" + n] for n in SFR_FIELDS}, SFR_FIELDS, ref["ref_valid"])

@@ -1,0 +1,184 @@
+/*
+ * pwr.h — C ABI of libpwr_b200.so: the B200 (sm_100a) hot path of
+ * PixelwiseRegression (SFR target builder, differentiable decoder, decoder
+ * backward fused with the stage loss).
+ *
+ * The reference (/root/reference, pure Python) has no native interface; each
+ * entry point below names the reference lines it replaces.  A reference-side
+ * binding is a ctypes stub.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success; < 0 argument error (PWR_E_*); > 0 a cudaError_t
+ *     reported by the launch (cudaGetLastError right after enqueueing).
+ *   - every pointer is a DEVICE pointer on the current device, contiguous,
+ *     16-byte aligned; the caller owns all buffers; the library never
+ *     allocates, frees, synchronises or keeps state.
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); kernels are
+ *     only enqueued, never waited for.
+ *   - maps are [B, J, 64, 64] float32 row-major ("map" = one 64x64 plane);
+ *     label/mask planes are [B, 1, 64, 64]; images [B, 1, 128, 128].
+ *   - re-entrant and thread-safe (no globals).
+ */
+#ifndef PWR_B200_H
+#define PWR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWR_VERSION 100          /* 0.1.0 */
+
+#define PWR_LABEL_SIZE 64
+#define PWR_IMAGE_SIZE 128
+#define PWR_MAP_ELEMS  4096
+#define PWR_MAX_JOINTS 64
+
+/* argument errors */
+#define PWR_E_NULL      (-1)     /* required pointer is NULL            */
+#define PWR_E_SHAPE     (-2)     /* B/J/frame size out of range         */
+#define PWR_E_ALIGN     (-3)     /* pointer not 16-byte aligned         */
+#define PWR_E_METHOD    (-4)     /* unknown heat-map normalisation      */
+
+/* heat-map normalisation, model.py:81-90 */
+#define PWR_METHOD_SOFTMAX 0     /* softmax(w * z)              :83-85  */
+#define PWR_METHOD_SUM     1     /* (relu(z)+1e-14) / sum       :88-90  */
+#define PWR_METHOD_GIVEN   2     /* z IS the normalised heat map: used when
+                                    DepthRegression.forward is called on its
+                                    own with caller-supplied heat maps :116 */
+
+int pwr_version(void);
+const char* pwr_error_string(int rc);
+
+/* ------------------------------------------------------------------------ *
+ * SFR target builder
+ * ------------------------------------------------------------------------ */
+
+/* Centre of mass fallback, datasets.py:208-211 (MSRA: load_from_text returns
+ * com=None).  com[b] = (mean col, mean row, mean depth) over frame pixels > 0,
+ * float64.  frames [B,Hf,Wf] float32.  A frame without positive pixels yields
+ * NaNs (the reference raises; the builder then flags valid=0). */
+int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com /*[B,3]*/,
+                int B, void* stream);
+
+/* Test-only SFR (the 6-tuple of datasets.py:334-348): crop box :306-309,
+ * center_crop utils.py:167-173, depth window + centring :312-315, int CoM
+ * :317-319, bilinear resize to 128x128 :323, 2x2 mean to 64x64 + mask
+ * :330-332, /cube normalisation :337-338.
+ *   frames [B,Hf,Wf] f32; com [B,3] f64 (u,v,z); cube [B] f64;
+ *   frame_f64 != 0: the reference held the frame as float64 (MSRA), so the
+ *   image path is evaluated in float64 and rounded once at the end.
+ * outputs: img [B,1,128,128], label_img [B,1,64,64], mask [B,1,64,64],
+ *   box_size [B], cube_size [B], com_out [B,3] (int(u), int(v), z) all f32;
+ *   valid [B] u8 = 0 where the reference raises (empty crop). */
+int pwr_sfr_crop(const float* frames, int Hf, int Wf,
+                 const double* com, const double* cube, double fx, double fy,
+                 int frame_f64,
+                 float* img, float* label_img, float* mask,
+                 float* box_size, float* cube_size, float* com_out,
+                 uint8_t* valid, int B, void* stream);
+
+/* Train-mode SFR (the 9-tuple of datasets.py:403): everything pwr_sfr_crop
+ * does plus uvd normalisation :350-353,381-383, heat-map coordinates
+ * :356-358, 4-tap splat utils.py:37-62, 7x7 sigma 1.5 Gaussian
+ * (cv2.GaussianBlur, BORDER_REFLECT_101) utils.py:64-65, Dmap :369-380 and
+ * the reject gate :385-390 / :362-365.
+ *   uvd [B,J,3] f64 joint pixel coordinates + depth.
+ * extra outputs: uvd_norm [B,J,3], heatmaps [B,J,64,64], dmap [B,J,64,64] f32;
+ *   valid [B] u8 = 0 where the reference raises (empty crop, heat-map index
+ *   out of range, NaN, sum(mask) < 10). */
+int pwr_sfr_build(const float* frames, int Hf, int Wf,
+                  const double* com, const double* cube, const double* uvd,
+                  double fx, double fy, int frame_f64,
+                  float* img, float* label_img, float* mask,
+                  float* box_size, float* cube_size, float* com_out,
+                  float* uvd_norm, float* heatmaps, float* dmap,
+                  uint8_t* valid, int B, int J, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Differentiable decoder
+ * ------------------------------------------------------------------------ */
+
+/* Forward: PlaneRegression.forward post-conv model.py:79-97 +
+ * DepthRegression.forward post-conv :123-132 + cat :151.
+ *   z, D [B,J,64,64] conv outputs (logits / depth maps); w [J] (softmax
+ *   temperature, model.py:74; only read for PWR_METHOD_SOFTMAX);
+ *   L, m [B,1,64,64] label image and mask.  D == NULL (then L, m are not
+ *   read) evaluates the plane branch alone and returns d = 0.
+ *   heat_gt, dmap_gt [B,J,64,64], uvd_gt [B,J,3]: only read when
+ *   loss_partial != NULL (an inner stage whose loss VALUE is needed at forward
+ *   time, train.py:197-199).
+ * outputs: H [B,J,64,64] normalised heat maps (NULL = do not store, e.g. the
+ *   last stage at inference); uvd [B,J,3]; stats [B,J,4] = (softmax offset in
+ *   log2 units, 1/sum, masked-heat sum + 1e-14, d) saved for the backward
+ *   (NULL = do not store); loss_partial [B,J,3] per-(b,j) sums of squares
+ *   (heat, dmap, uvd) before lambda/mean scaling (NULL = no loss). */
+int pwr_decoder_fwd(const float* z, const float* w, const float* D,
+                    const float* L, const float* m,
+                    const float* heat_gt, const float* dmap_gt,
+                    const float* uvd_gt,
+                    float* H, float* uvd, float* stats, float* loss_partial,
+                    int B, int J, int method, void* stream);
+
+/* Backward of pwr_decoder_fwd (what autograd derives from model.py:79-132).
+ *   g_uvd [B,J,3] upstream gradient on uvd (NULL = zeros);
+ *   gH_up, gD_up [B,J,64,64] dense upstream gradients on the heat maps and on
+ *   the depth maps (next stage's conv, model.py:208; loss terms computed
+ *   outside); either may be NULL.
+ * outputs: gz, gD [B,J,64,64] (either may be NULL = not wanted); gw_partial
+ *   [B,J] (sum over pixels of dL/d(w z) * z; reduce over B with
+ *   pwr_reduce_partials; NULL unless PWR_METHOD_SOFTMAX). */
+int pwr_decoder_bwd(const float* z, const float* w, const float* D,
+                    const float* L, const float* m, const float* stats,
+                    const float* uvd, const float* g_uvd,
+                    const float* gH_up, const float* gD_up,
+                    float* gz, float* gD, float* gw_partial,
+                    int B, int J, int method, void* stream);
+
+/* Backward fused with the stage loss of train.py:197-205:
+ *   loss = alpha*mean(sum (uvd-uvd_gt)^2) + (1-alpha)*(lambda_h*mean(sum
+ *   (H-heat_gt)^2) + lambda_d*mean(sum (D-dmap_gt)^2)), means over B*J.
+ * Adds d(scale*loss)/d(.), scale = loss_scale * (loss_scale_dev ?
+ * *loss_scale_dev : 1) (a device scalar: the upstream gradient on the loss,
+ * e.g. a GradScaler factor, without a host sync), to the upstream gradients
+ * of pwr_decoder_bwd
+ * and emits loss_partial [B,J,3] = per-(b,j) sums of squares (heat, dmap,
+ * uvd) BEFORE lambda/mean scaling (NULL = not wanted; the target maps are
+ * then only read if their weight (1-alpha)*lambda is non-zero).  `n_mean` is
+ * the B*J of the mean (the global batch under data parallelism; 0 = B*J). */
+int pwr_decoder_bwd_loss(const float* z, const float* w, const float* D,
+                         const float* L, const float* m, const float* stats,
+                         const float* uvd, const float* g_uvd,
+                         const float* gH_up, const float* gD_up,
+                         const float* heat_gt, const float* dmap_gt,
+                         const float* uvd_gt,
+                         float alpha, float lambda_h, float lambda_d,
+                         float loss_scale, const float* loss_scale_dev,
+                         int n_mean,
+                         float* gz, float* gD, float* gw_partial,
+                         float* loss_partial,
+                         int B, int J, int method, void* stream);
+
+/* Deterministic sum over the batch axis: out[j*C + c] = sum_b in[(b*J+j)*C+c]
+ * (gw_partial -> gw: C=1; loss_partial -> per-joint sums: C=3). */
+int pwr_reduce_partials(const float* in, float* out, int B, int J, int C,
+                        void* stream);
+
+/* In-place multiply n floats by *scale_dev (device scalar); used to apply a
+ * non-unit upstream gradient to gradients that were produced eagerly. */
+int pwr_scale_inplace(float* x, const float* scale_dev, long long n,
+                      void* stream);
+
+/* utils.py:332-337 recover_uvd fused with uvd2xyz datasets.py:100-111:
+ *   uvd_px = uvd_norm * (box-1 | box-1 | cube) + com ; xyz = ((u-halfu)/fx*d,
+ *   (v-halfv)/fy*d, d).  uvd_px / xyz may be NULL. */
+int pwr_recover_uvd(const float* uvd_norm, const float* box_size,
+                    const float* cube_size, const float* com,
+                    double fx, double fy, double halfu, double halfv,
+                    float* uvd_px, float* xyz, int B, int J, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWR_B200_H */

@@ -1,0 +1,94 @@
+"""ctypes binding of libpwr_b200.so (include/pwr.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  Loading
+fails loudly when the shared object is missing, and every wrapper refuses
+non-CUDA tensors.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpwr_b200.so")
+
+METHOD_SOFTMAX, METHOD_SUM, METHOD_GIVEN = 0, 1, 2
+METHODS = {"softmax": METHOD_SOFTMAX, "sum": METHOD_SUM, "given": METHOD_GIVEN}
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_D = ctypes.c_double
+_F = ctypes.c_float
+_LL = ctypes.c_longlong
+
+# name -> argtypes, exactly the prototypes of include/pwr.h
+SIGNATURES = {
+    "pwr_version": [],
+    "pwr_error_string": [_I],
+    "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
+    "pwr_sfr_crop": [_P, _I, _I, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "pwr_sfr_build": [_P, _I, _I, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _P],
+    "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _P],
+    "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _P],
+    "pwr_reduce_partials": [_P, _P, _I, _I, _I, _P],
+    "pwr_scale_inplace": [_P, _P, _LL, _P],
+    "pwr_recover_uvd": [_P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _I, _I, _P],
+}
+
+_lib = None
+
+
+class PwrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise PwrError(
+            "libpwr_b200.so not found at %s: build it with `python -m pixelwiseregression_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_char_p if name == "pwr_error_string" else _I
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pwr_error_string(rc)
+        raise PwrError("%s failed: rc=%d (%s)" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PwrError("pixelwiseregression_b200 runs on CUDA tensors only (got a %s tensor); "
+                           "there is no CPU fallback" % t.device.type)
+
+
+def as_f32(t):
+    """Contiguous float32 view/copy on the same device (fp16/bf16 under autocast)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

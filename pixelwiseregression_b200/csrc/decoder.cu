@@ -1,0 +1,492 @@
+// Fused differentiable decoder for sm_100a: forward, backward, backward+loss.
+//
+// Replaces the ~16 ATen launches per stage of the reference
+//   model.py:79-97   PlaneRegression.forward (post-conv): softmax / relu-sum
+//                    normalisation and the soft-argmax sums over U and V
+//   model.py:123-132 DepthRegression.forward (post-conv): masked, heat-map
+//                    weighted depth
+//   model.py:151     cat -> uvd
+//   train.py:197-207 stage loss and everything autograd derives from the above
+// by ONE forward and ONE backward kernel.  Work unit = one (sample, joint)
+// pair = one 64x64 logit map + one 64x64 depth map; one CTA of 256 threads
+// per unit, 16 pixels (four 128-bit accesses) per thread per map, so every
+// map crosses HBM exactly once.  No tensor cores: nothing here is a
+// contraction; the bound is HBM bandwidth.
+//
+// Pixel mapping: chunk c = tid + 256*i (i = 0..3) covers pixels 4c..4c+3,
+// i.e. column x = 4*(tid & 15) + k and row y = (tid >> 4) + 16*i.  The
+// coordinate filter of utils.py:24-35 (U = (x-32)/63, V = (y-32)/63) is
+// synthesised from the indices: sums are taken over the integer offsets
+// (x-32), (y-32) and scaled by 1/63 once.
+#include "common.cuh"
+
+namespace pwr {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kEps = 1e-14f;             // model.py:89,128
+
+struct PixelCoords {
+    float xs;          // (x - 32) of the first of the thread's four columns
+    float ys0;         // (y - 32) of the thread's first row; row i adds 16*i
+};
+__device__ __forceinline__ PixelCoords pixel_coords() {
+    PixelCoords pc;
+    pc.xs = static_cast<float>(static_cast<int>((threadIdx.x & 15) * 4) - 32);
+    pc.ys0 = static_cast<float>(static_cast<int>(threadIdx.x >> 4) - 32);
+    return pc;
+}
+
+__device__ __forceinline__ float comp(const float4& v, int k) {
+    return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void set_comp(float4& v, int k, float x) {
+    if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x;
+}
+
+// Extremum of the logits in the direction of the temperature sign, so that
+// c*(z - ext) <= 0 for every pixel even when a trained w is negative.
+__device__ __forceinline__ float block_extremum(const float4 (&zv)[kVec], bool want_max, float* scratch) {
+    float e = want_max ? -INFINITY : INFINITY;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        if (want_max) e = fmaxf(fmaxf(fmaxf(e, zv[i].x), fmaxf(zv[i].y, zv[i].z)), zv[i].w);
+        else          e = fminf(fminf(fminf(e, zv[i].x), fminf(zv[i].y, zv[i].z)), zv[i].w);
+    }
+    e = want_max ? warp_max(e) : warp_min(e);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = e;
+    __syncthreads();
+    float r = scratch[0];
+#pragma unroll
+    for (int wv = 1; wv < kWarps; ++wv) r = want_max ? fmaxf(r, scratch[wv]) : fminf(r, scratch[wv]);
+    __syncthreads();
+    return r;
+}
+
+// Un-normalised heat value: 2^(c*z - off) for softmax, relu(z)+1e-14 for sum,
+// z itself when the caller hands in an already normalised heat map.
+template <int METHOD>
+__device__ __forceinline__ float heat_raw(float z, float c, float off) {
+    if (METHOD == PWR_METHOD_SOFTMAX) return exp2f(fmaf(z, c, -off));
+    if (METHOD == PWR_METHOD_GIVEN) return z;
+    return fmaxf(z, 0.f) + kEps;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+template <int METHOD, bool LOSS>
+__global__ void __launch_bounds__(kThreads)
+decoder_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ D,
+                   const float* __restrict__ L, const float* __restrict__ m,
+                   const float* __restrict__ heat_gt, const float* __restrict__ dmap_gt,
+                   const float* __restrict__ uvd_gt, float* __restrict__ H,
+                   float* __restrict__ uvd, float* __restrict__ stats, float* __restrict__ loss_partial, int J) {
+    __shared__ float scratch[kWarps * 5];
+    const int bj = blockIdx.x;
+    const int b = bj / J;
+    const int j = bj - b * J;
+    const size_t off = static_cast<size_t>(bj) * kMap + threadIdx.x * 4;
+    const size_t offb = static_cast<size_t>(b) * kMap + threadIdx.x * 4;
+    const bool depth = (D != nullptr);          // PlaneRegression alone: no depth branch
+
+    float4 zv[kVec], dv[kVec], lv[kVec], mv[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) zv[i] = ld_stream(z + off + i * (kThreads * 4));
+    if (depth) {
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) mv[i] = ld_keep(m + offb + i * (kThreads * 4));
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) lv[i] = ld_keep(L + offb + i * (kThreads * 4));
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) dv[i] = ld_stream(D + off + i * (kThreads * 4));
+    } else {
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) mv[i] = lv[i] = dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    float c = 0.f, shift = 0.f;
+    if (METHOD == PWR_METHOD_SOFTMAX) {
+        c = w[j] * kLog2e;
+        shift = block_extremum(zv, c >= 0.f, scratch) * c;
+    }
+
+    const PixelCoords pc = pixel_coords();
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum e, e*(x-32), e*(y-32), e*m, e*m*m*(D+L)
+    float ld2 = 0.f;                            // sum (D - Dgt)^2
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const float ys = pc.ys0 + 16.f * i;
+        float rowsum = 0.f;
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (LOSS) dg = ld_stream(dmap_gt + off + i * (kThreads * 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float e = heat_raw<METHOD>(comp(zv[i], k), c, shift);
+            set_comp(zv[i], k, e);
+            const float mk = comp(mv[i], k);
+            const float em = e * mk;
+            rowsum += e;
+            acc[1] = fmaf(e, pc.xs + static_cast<float>(k), acc[1]);
+            acc[3] += em;
+            acc[4] = fmaf(em, mk * (comp(dv[i], k) + comp(lv[i], k)), acc[4]);
+            if (LOSS) { const float ed = comp(dv[i], k) - comp(dg, k); ld2 = fmaf(ed, ed, ld2); }
+        }
+        acc[0] += rowsum;
+        acc[2] = fmaf(rowsum, ys, acc[2]);
+    }
+    block_sum<5>(acc, scratch);
+
+    const float inv_s = (METHOD == PWR_METHOD_GIVEN) ? 1.f : 1.f / acc[0];
+    float lh2[2] = {0.f, ld2};                  // sum (p - Hgt)^2, sum (D - Dgt)^2
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        float4 h = zv[i];
+        h.x *= inv_s; h.y *= inv_s; h.z *= inv_s; h.w *= inv_s;
+        if (LOSS) {
+            const float4 hg = ld_stream(heat_gt + off + i * (kThreads * 4));
+            const float e0 = h.x - hg.x, e1 = h.y - hg.y, e2 = h.z - hg.z, e3 = h.w - hg.w;
+            lh2[0] += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+        }
+        if (H != nullptr) st_stream(H + off + i * (kThreads * 4), h);
+    }
+    if (LOSS) block_sum<2>(lh2, scratch);
+    if (threadIdx.x == 0) {
+        const float den = fmaf(acc[3], inv_s, kEps);
+        const float d = (acc[4] * inv_s) / den;
+        const float u = acc[1] * inv_s / 63.f, v = acc[2] * inv_s / 63.f;
+        uvd[bj * 3 + 0] = u;
+        uvd[bj * 3 + 1] = v;
+        uvd[bj * 3 + 2] = d;
+        if (stats != nullptr)
+            reinterpret_cast<float4*>(stats)[bj] = make_float4(shift, inv_s, den, d);
+        if (LOSS) {
+            const float eu = u - uvd_gt[bj * 3 + 0], ev = v - uvd_gt[bj * 3 + 1], ed = d - uvd_gt[bj * 3 + 2];
+            loss_partial[bj * 3 + 0] = lh2[0];
+            loss_partial[bj * 3 + 1] = lh2[1];
+            loss_partial[bj * 3 + 2] = eu * eu + ev * ev + ed * ed;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward (optionally fused with the stage loss)
+// ---------------------------------------------------------------------------
+struct LossCoef {
+    float cu;   // loss_scale * 2*alpha / N
+    float ch;   // loss_scale * 2*(1-alpha)*lambda_h / N
+    float cd;   // loss_scale * 2*(1-alpha)*lambda_d / N
+    const float* scale_dev;   // optional device scalar multiplying all three (upstream d/d(loss), e.g. a GradScaler)
+};
+
+// LOSS = false: plain backward.  LOSS = true: adds d(loss)/d(.) of train.py:197-205;
+// the target maps are only read when they matter (non-zero map weights or
+// loss_partial requested), so the default alpha = 1 costs no extra traffic
+// unless the caller wants the logged loss values.
+template <int METHOD, bool LOSS>
+__global__ void __launch_bounds__(kThreads)
+decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ D,
+                   const float* __restrict__ L, const float* __restrict__ m, const float* __restrict__ stats,
+                   const float* __restrict__ uvd, const float* __restrict__ g_uvd,
+                   const float* __restrict__ gH_up, const float* __restrict__ gD_up,
+                   const float* __restrict__ heat_gt, const float* __restrict__ dmap_gt,
+                   const float* __restrict__ uvd_gt, LossCoef coef,
+                   float* __restrict__ gz, float* __restrict__ gD, float* __restrict__ gw_partial,
+                   float* __restrict__ loss_partial, int J) {
+    __shared__ float scratch[kWarps * 3];
+    if (LOSS && coef.scale_dev != nullptr) {
+        const float up = *coef.scale_dev;
+        coef.cu *= up; coef.ch *= up; coef.cd *= up;
+    }
+    const int bj = blockIdx.x;
+    const int b = bj / J;
+    const int j = bj - b * J;
+    const size_t off = static_cast<size_t>(bj) * kMap + threadIdx.x * 4;
+    const size_t offb = static_cast<size_t>(b) * kMap + threadIdx.x * 4;
+    const bool depth = (D != nullptr);
+    const bool map_loss = LOSS && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
+
+    float4 zv[kVec], pv[kVec], gv[kVec];   // logits, heat p, dL/dp
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) zv[i] = ld_stream(z + off + i * (kThreads * 4));
+
+    const float4 st = reinterpret_cast<const float4*>(stats)[bj];   // (shift, 1/sum, den, d)
+    const float wj = (METHOD == PWR_METHOD_SOFTMAX) ? w[j] : 1.f;
+    const float c = wj * kLog2e;
+    float gu = 0.f, gvv = 0.f, gd = 0.f, lu = 0.f;
+    if (g_uvd != nullptr) { gu = g_uvd[bj * 3 + 0]; gvv = g_uvd[bj * 3 + 1]; gd = g_uvd[bj * 3 + 2]; }
+    if (LOSS) {
+        const float eu = uvd[bj * 3 + 0] - uvd_gt[bj * 3 + 0];
+        const float ev = uvd[bj * 3 + 1] - uvd_gt[bj * 3 + 1];
+        const float ed = uvd[bj * 3 + 2] - uvd_gt[bj * 3 + 2];
+        gu = fmaf(coef.cu, eu, gu); gvv = fmaf(coef.cu, ev, gvv); gd = fmaf(coef.cu, ed, gd);
+        lu = eu * eu + ev * ev + ed * ed;
+    }
+    const float gu63 = gu / 63.f, gv63 = gvv / 63.f;
+    const float gdd = depth ? gd / st.z : 0.f;        // g_d / den
+    const float dcoord = st.w;
+    const PixelCoords pc = pixel_coords();
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    float acc[3] = {0.f, 0.f, 0.f};      // sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const size_t o = off + i * (kThreads * 4);
+        const size_t ob = offb + i * (kThreads * 4);
+        float4 d4 = zero4, l4 = zero4, m4 = zero4, hg = zero4, dg = zero4, uh = zero4, ud = zero4;
+        if (depth) { d4 = ld_stream(D + o); l4 = ld_keep(L + ob); m4 = ld_keep(m + ob); }
+        if (map_loss) { hg = ld_stream(heat_gt + o); if (depth) dg = ld_stream(dmap_gt + o); }
+        if (gH_up != nullptr) uh = ld_stream(gH_up + o);
+        if (gD_up != nullptr) ud = ld_stream(gD_up + o);
+        const float gyrow = gv63 * (pc.ys0 + 16.f * i);
+        float4 gd4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float p = heat_raw<METHOD>(comp(zv[i], k), c, st.x) * st.y;
+            const float mk = comp(m4, k), dk = comp(d4, k);
+            const float rec = mk * (dk + comp(l4, k));
+            float gp = fmaf(gu63, pc.xs + static_cast<float>(k), gyrow);
+            gp = fmaf(gdd * mk, rec - dcoord, gp);
+            float gdk = gdd * p * mk * mk;
+            if (LOSS) {
+                const float eh = p - comp(hg, k);
+                const float ed = dk - comp(dg, k);
+                gp = fmaf(coef.ch, eh, gp);
+                gdk = fmaf(coef.cd, ed, gdk);
+                acc[1] = fmaf(eh, eh, acc[1]);
+                acc[2] = fmaf(ed, ed, acc[2]);
+            }
+            gp += comp(uh, k);
+            gdk += comp(ud, k);
+            acc[0] = fmaf(gp, p, acc[0]);
+            set_comp(pv[i], k, p);
+            set_comp(gv[i], k, gp);
+            set_comp(gd4, k, gdk);
+        }
+        if (gD != nullptr) st_stream(gD + o, gd4);
+    }
+    if (METHOD != PWR_METHOD_GIVEN || LOSS) block_sum<3>(acc, scratch);
+
+    const float s1 = acc[0];
+    float s2[1] = {0.f};
+    if (gz != nullptr) {
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            float4 g4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float zk = comp(zv[i], k);
+                float g;
+                if (METHOD == PWR_METHOD_SOFTMAX) {
+                    const float gy = comp(pv[i], k) * (comp(gv[i], k) - s1);   // dL/d(w z)
+                    s2[0] = fmaf(gy, zk, s2[0]);
+                    g = wj * gy;
+                } else if (METHOD == PWR_METHOD_SUM) {
+                    g = zk > 0.f ? (comp(gv[i], k) - s1) * st.y : 0.f;         // through relu and 1/sum
+                } else {
+                    g = comp(gv[i], k);                                        // heat map given: dL/dp itself
+                }
+                set_comp(g4, k, g);
+            }
+            st_stream(gz + off + i * (kThreads * 4), g4);
+        }
+    }
+    if (METHOD == PWR_METHOD_SOFTMAX && gw_partial != nullptr) {
+        block_sum<1>(s2, scratch);
+        if (threadIdx.x == 0) gw_partial[bj] = s2[0];
+    }
+    if (LOSS && loss_partial != nullptr && threadIdx.x == 0) {
+        loss_partial[bj * 3 + 0] = acc[1];
+        loss_partial[bj * 3 + 1] = acc[2];
+        loss_partial[bj * 3 + 2] = lu;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// small helpers: batch reduction of per-(b,j) partials, scaling, recover_uvd
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int J, int C) {
+    __shared__ float scratch[kWarps];
+    const int jc = blockIdx.x;               // j*C + c
+    const int j = jc / C, c = jc - j * C;
+    float v[1] = {0.f};
+    for (int b = threadIdx.x; b < B; b += kThreads) v[0] += in[(static_cast<size_t>(b) * J + j) * C + c];
+    block_sum<1>(v, scratch);
+    if (threadIdx.x == 0) out[jc] = v[0];
+}
+
+__global__ void __launch_bounds__(kThreads)
+scale_inplace_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n4, long long n) {
+    const float s = *scale;
+    if (s == 1.0f) return;
+    const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+    for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < n4; i += stride) {
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) x[n4 * 4 + threadIdx.x] *= s;
+}
+
+// utils.py:332-337 (float32 torch arithmetic) + datasets.py:100-111
+__global__ void recover_uvd_kernel(const float* __restrict__ uvd_norm, const float* __restrict__ box,
+                                   const float* __restrict__ cube, const float* __restrict__ com,
+                                   float fx, float fy, float halfu, float halfv,
+                                   float* __restrict__ uvd_px, float* __restrict__ xyz, int B, int J) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * J) return;
+    const int b = i / J;
+    const float s = __fsub_rn(box[b], 1.f);
+    const float u = __fadd_rn(__fmul_rn(uvd_norm[i * 3 + 0], s), com[b * 3 + 0]);
+    const float v = __fadd_rn(__fmul_rn(uvd_norm[i * 3 + 1], s), com[b * 3 + 1]);
+    const float d = __fadd_rn(__fmul_rn(uvd_norm[i * 3 + 2], cube[b]), com[b * 3 + 2]);
+    if (uvd_px != nullptr) { uvd_px[i * 3 + 0] = u; uvd_px[i * 3 + 1] = v; uvd_px[i * 3 + 2] = d; }
+    if (xyz != nullptr) {
+        xyz[i * 3 + 0] = __fmul_rn(__fdiv_rn(__fsub_rn(u, halfu), fx), d);
+        xyz[i * 3 + 1] = __fmul_rn(__fdiv_rn(__fsub_rn(v, halfv), fy), d);
+        xyz[i * 3 + 2] = d;
+    }
+}
+
+static int check_bj(int B, int J) {
+    if (B < 0 || J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
+    if (static_cast<long long>(B) * J > 0x7fffffffLL / 4) return PWR_E_SHAPE;
+    return 0;
+}
+static bool bad_method(int method) {
+    return method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM && method != PWR_METHOD_GIVEN;
+}
+
+}  // namespace pwr
+
+using namespace pwr;
+
+extern "C" int pwr_decoder_fwd(const float* z, const float* w, const float* D, const float* L, const float* m,
+                               const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
+                               float* H, float* uvd, float* stats, float* loss_partial,
+                               int B, int J, int method, void* stream) {
+    if (bad_method(method)) return PWR_E_METHOD;
+    if (int rc = check_bj(B, J)) return rc;
+    PWR_REQUIRE_PTR(z);
+    if (uvd == nullptr) return PWR_E_NULL;
+    PWR_OPTIONAL_PTR(D); PWR_OPTIONAL_PTR(H); PWR_OPTIONAL_PTR(stats);
+    if (D != nullptr) { PWR_REQUIRE_PTR(L); PWR_REQUIRE_PTR(m); }
+    if (method == PWR_METHOD_SOFTMAX && w == nullptr) return PWR_E_NULL;
+    const bool loss = loss_partial != nullptr;
+    if (loss) {
+        PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt);
+        if (uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
+    }
+    if (B == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define PWR_LAUNCH_FWD(M, LS)                                                                               \
+    decoder_fwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, H, uvd, stats, \
+                                                         loss_partial, J)
+    if (method == PWR_METHOD_SOFTMAX)  { if (loss) PWR_LAUNCH_FWD(PWR_METHOD_SOFTMAX, true); else PWR_LAUNCH_FWD(PWR_METHOD_SOFTMAX, false); }
+    else if (method == PWR_METHOD_SUM) { if (loss) PWR_LAUNCH_FWD(PWR_METHOD_SUM, true);     else PWR_LAUNCH_FWD(PWR_METHOD_SUM, false); }
+    else                               { if (loss) PWR_LAUNCH_FWD(PWR_METHOD_GIVEN, true);   else PWR_LAUNCH_FWD(PWR_METHOD_GIVEN, false); }
+#undef PWR_LAUNCH_FWD
+    return launch_status();
+}
+
+static int launch_bwd(bool loss, const float* z, const float* w, const float* D, const float* L, const float* m,
+                      const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
+                      const float* gD_up, const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
+                      LossCoef coef, float* gz, float* gD, float* gw_partial, float* loss_partial, int B, int J,
+                      int method, void* stream) {
+    if (bad_method(method)) return PWR_E_METHOD;
+    if (int rc = check_bj(B, J)) return rc;
+    PWR_REQUIRE_PTR(z); PWR_REQUIRE_PTR(stats);
+    PWR_OPTIONAL_PTR(D); PWR_OPTIONAL_PTR(gz); PWR_OPTIONAL_PTR(gD); PWR_OPTIONAL_PTR(gH_up); PWR_OPTIONAL_PTR(gD_up);
+    if (D != nullptr) { PWR_REQUIRE_PTR(L); PWR_REQUIRE_PTR(m); }
+    if (D == nullptr && (gD != nullptr || gD_up != nullptr)) return PWR_E_NULL;
+    if (method == PWR_METHOD_SOFTMAX && w == nullptr) return PWR_E_NULL;
+    if (loss) {
+        PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt);
+        if (uvd == nullptr || uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
+    }
+    if (B == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define PWR_LAUNCH_BWD(M, LS)                                                                              \
+    decoder_bwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up,    \
+                                                         heat_gt, dmap_gt, uvd_gt, coef, gz, gD, gw_partial, \
+                                                         loss_partial, J)
+    if (method == PWR_METHOD_SOFTMAX)  { if (loss) PWR_LAUNCH_BWD(PWR_METHOD_SOFTMAX, true); else PWR_LAUNCH_BWD(PWR_METHOD_SOFTMAX, false); }
+    else if (method == PWR_METHOD_SUM) { if (loss) PWR_LAUNCH_BWD(PWR_METHOD_SUM, true);     else PWR_LAUNCH_BWD(PWR_METHOD_SUM, false); }
+    else                               { if (loss) PWR_LAUNCH_BWD(PWR_METHOD_GIVEN, true);   else PWR_LAUNCH_BWD(PWR_METHOD_GIVEN, false); }
+#undef PWR_LAUNCH_BWD
+    return launch_status();
+}
+
+extern "C" int pwr_decoder_bwd(const float* z, const float* w, const float* D, const float* L, const float* m,
+                               const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
+                               const float* gD_up, float* gz, float* gD, float* gw_partial, int B, int J,
+                               int method, void* stream) {
+    LossCoef coef = {0.f, 0.f, 0.f, nullptr};
+    return launch_bwd(false, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, nullptr, nullptr, nullptr, coef, gz,
+                      gD, gw_partial, nullptr, B, J, method, stream);
+}
+
+extern "C" int pwr_decoder_bwd_loss(const float* z, const float* w, const float* D, const float* L, const float* m,
+                                    const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
+                                    const float* gD_up, const float* heat_gt, const float* dmap_gt,
+                                    const float* uvd_gt, float alpha, float lambda_h, float lambda_d,
+                                    float loss_scale, const float* loss_scale_dev, int n_mean, float* gz,
+                                    float* gD, float* gw_partial,
+                                    float* loss_partial, int B, int J, int method, void* stream) {
+    const double n = n_mean > 0 ? static_cast<double>(n_mean) : static_cast<double>(B) * J;
+    LossCoef coef;
+    coef.cu = static_cast<float>(loss_scale * 2.0 * alpha / n);
+    coef.ch = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_h / n);
+    coef.cd = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_d / n);
+    coef.scale_dev = loss_scale_dev;
+    return launch_bwd(true, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, heat_gt, dmap_gt, uvd_gt, coef, gz, gD,
+                      gw_partial, loss_partial, B, J, method, stream);
+}
+
+extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, int C, void* stream) {
+    if (in == nullptr || out == nullptr) return PWR_E_NULL;
+    if (B < 0 || J < 1 || C < 1 || J * C > 65535) return PWR_E_SHAPE;
+    reduce_partials_kernel<<<J * C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, J, C);
+    return launch_status();
+}
+
+extern "C" int pwr_scale_inplace(float* x, const float* scale_dev, long long n, void* stream) {
+    PWR_REQUIRE_PTR(x);
+    if (scale_dev == nullptr) return PWR_E_NULL;
+    if (n < 0) return PWR_E_SHAPE;
+    if (n == 0) return 0;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    scale_inplace_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, scale_dev, n4, n);
+    return launch_status();
+}
+
+extern "C" int pwr_recover_uvd(const float* uvd_norm, const float* box_size, const float* cube_size,
+                               const float* com, double fx, double fy, double halfu, double halfv, float* uvd_px,
+                               float* xyz, int B, int J, void* stream) {
+    if (uvd_norm == nullptr || box_size == nullptr || cube_size == nullptr || com == nullptr) return PWR_E_NULL;
+    if (B < 0 || J < 1) return PWR_E_SHAPE;
+    if (B == 0) return 0;
+    const int n = B * J;
+    recover_uvd_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        uvd_norm, box_size, cube_size, com, static_cast<float>(fx), static_cast<float>(fy),
+        static_cast<float>(halfu), static_cast<float>(halfv), uvd_px, xyz, B, J);
+    return launch_status();
+}
+
+extern "C" int pwr_version(void) { return PWR_VERSION; }
+
+extern "C" const char* pwr_error_string(int rc) {
+    switch (rc) {
+        case 0: return "ok";
+        case PWR_E_NULL: return "required pointer is NULL";
+        case PWR_E_SHAPE: return "shape out of range";
+        case PWR_E_ALIGN: return "pointer not 16-byte aligned";
+        case PWR_E_METHOD: return "unknown heat-map normalisation";
+        default: return rc > 0 ? cudaGetErrorString(static_cast<cudaError_t>(rc)) : "unknown error";
+    }
+}

@@ -1,0 +1,493 @@
+// SFR (Spatial-Form Representation) target builder for sm_100a.
+//
+// One launch turns raw depth frames + joint annotations into the reference's
+// training tuple (datasets.py:301-403): crop / window / centre / resize the
+// depth frame, build the label image and mask, render per-joint Gaussian heat
+// maps and depth maps.  In the reference this is ~40-60 ms of NumPy/OpenCV per
+// sample inside DataLoader workers.
+//
+// Decomposition: a sample is split into kBands horizontal bands of the label
+// image; one CTA per band, the kBands CTAs of a sample form a thread-block
+// cluster.  Each CTA
+//   0. derives the sample geometry (thread 0, float64, reference op order) and
+//      the per-joint splat taps (threads 0..J-1) into shared memory,
+//   1. resamples its 2*R x 128 image rows straight from the frame in HBM
+//      (window + centring applied per tap), writes img, label, mask, and keeps
+//      the un-normalised label band in shared memory,
+//   2. writes its R rows of every joint's heat map and depth map: 128-bit
+//      zero stores outside the <= 8x8 support, float64 evaluation inside.
+// The per-sample reject gate (sum(mask) < 10, NaN; datasets.py:385-390) needs a
+// reduction over the bands: each CTA publishes its count in its own shared
+// memory and rank 0 reads the peers through distributed shared memory.
+//
+// Arithmetic contract (bit-level where the result is discontinuous):
+//   * crop box, int CoM, slice extents: float64 with explicit _rn intrinsics
+//     (no FMA contraction) and Python slice semantics -> bit-exact integers.
+//   * image path in the frame's reference dtype (float32, or float64 for MSRA):
+//     cv::resize INTER_LINEAR coefficient recipe, horizontal then vertical,
+//     un-fused multiplies/adds; 2x2 mean; mask = (label != 0).
+//   * joints, splat taps, Gaussian (cv::getGaussianKernel(7,1.5) constants,
+//     BORDER_REFLECT_101) and Dmap in float64, rounded to float32 at the store.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pwr {
+
+constexpr int kBands = 4;                       // CTAs (= cluster size) per sample
+constexpr int kBandRows = kLabel / kBands;      // label rows per CTA
+constexpr int kLabelIters = kBandRows * kLabel / kThreads;
+
+// cv::getGaussianKernel(7, 1.5, CV_64F), OpenCV 4.13.0 (softdouble, exact bits)
+__constant__ double kGauss7[7] = {0x1.2c18a51a3e5e7p-5, 0x1.c7ce552574441p-4, 0x1.bbe4f897eb627p-3,
+                                  0x1.152db38ecae3ep-2, 0x1.bbe4f897eb627p-3, 0x1.c7ce552574441p-4,
+                                  0x1.2c18a51a3e5e7p-5};
+
+struct SampleGeom {
+    double z, cube;
+    double scale_y, scale_x;   // 1 / (128 / n), as cv::resize computes it
+    float lo_dn, hi_up;        // float-exact equivalents of the float64 window bounds
+    double lo, hi;
+    int ok;                    // crop non-empty and all scalars finite
+    int fr0, fc0;              // frame row / column of crop(0,0) (may be negative)
+    int nrows, ncols;          // crop extent (== 2*shift unless truncated)
+    int r0, c0;                // int(com_v), int(com_u)
+};
+
+struct JointParam {
+    double tap[4];             // a, b, c, d of utils.py:48-58
+    double cd;                 // centred depth  uvd_z - com_z
+    int tx0, tx1, ty0, ty1;    // wrapped heat-map indices of the four taps
+    int ok;
+};
+
+struct TapX { int s0, s1; float a0, a1; };
+
+// Python slice(start, stop).indices(n) for step 1
+__device__ __forceinline__ void py_slice(long long start, long long stop, long long n, int& first, int& count) {
+    if (start < 0) { start += n; if (start < 0) start = 0; } else if (start > n) start = n;
+    if (stop < 0) { stop += n; if (stop < 0) stop = 0; } else if (stop > n) stop = n;
+    first = static_cast<int>(start);
+    count = stop > start ? static_cast<int>(stop - start) : 0;
+}
+
+__device__ void sample_geometry(SampleGeom& g, const double* com, double cube, double fx, double fy, int Hf, int Wf) {
+    const double cu = com[0], cv = com[1], z = com[2];
+    g.z = z; g.cube = cube; g.ok = 0;
+    g.fr0 = g.fc0 = 0; g.nrows = g.ncols = 0; g.r0 = g.c0 = 0;
+    g.scale_x = g.scale_y = 1.0;
+    // datasets.py:306-309
+    const double du = __dmul_rn(__ddiv_rn(cube, z), fx);
+    const double dv = __dmul_rn(__ddiv_rn(cube, z), fy);
+    const double sum = __dadd_rn(du, dv);
+    g.lo = __dsub_rn(z, cube);
+    g.hi = __dadd_rn(z, cube);
+    g.lo_dn = __double2float_rd(g.lo);
+    g.hi_up = __double2float_ru(g.hi);
+    if (!isfinite(sum) || !isfinite(cu) || !isfinite(cv) || !isfinite(z) || !isfinite(cube)) return;  // int(nan) raises
+    if (fabs(sum) > 1.0e6 || fabs(cu) > 1.0e9 || fabs(cv) > 1.0e9) return;
+    int box = static_cast<int>(sum);          // int() truncates toward zero
+    if (box < 2) box = 2;
+    const int shift = box / 2;
+    g.r0 = static_cast<int>(cv);
+    g.c0 = static_cast<int>(cu);
+    // utils.py:167-173: slice of the zero-padded frame
+    int rs, cs;
+    py_slice(g.r0, static_cast<long long>(g.r0) + 2 * shift, static_cast<long long>(Hf) + 2 * shift, rs, g.nrows);
+    py_slice(g.c0, static_cast<long long>(g.c0) + 2 * shift, static_cast<long long>(Wf) + 2 * shift, cs, g.ncols);
+    g.fr0 = rs - shift;
+    g.fc0 = cs - shift;
+    if (g.nrows == 0 || g.ncols == 0) return;  // cv2.resize raises on an empty crop
+    g.scale_y = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(kImage), static_cast<double>(g.nrows)));
+    g.scale_x = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(kImage), static_cast<double>(g.ncols)));
+    g.ok = 1;
+}
+
+// cv::resize INTER_LINEAR tap for destination index d, source extent n
+__device__ __forceinline__ TapX linear_tap(int d, int n, double scale) {
+    float f = __double2float_rn(__dsub_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), 0.5));
+    int s = static_cast<int>(floorf(f));
+    f = __fsub_rn(f, static_cast<float>(s));
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= n - 1) { s = n - 1; f = 0.f; }
+    TapX t;
+    t.s0 = s;
+    t.s1 = min(s + 1, n - 1);
+    t.a1 = f;
+    t.a0 = __fsub_rn(1.f, f);
+    return t;
+}
+
+// utils.py:37-62 + datasets.py:350-358 for one joint
+__device__ void joint_param(JointParam& p, float* uvd_norm_out, const double* uvd, const SampleGeom& g) {
+    const double cu = __dsub_rn(uvd[0], static_cast<double>(g.c0));
+    const double cv = __dsub_rn(uvd[1], static_cast<double>(g.r0));
+    const double cd = __dsub_rn(uvd[2], g.z);
+    const double bm1 = static_cast<double>(g.nrows - 1);          // box_size = crop.shape[0]
+    const double ru = __dmul_rn(__ddiv_rn(cu, bm1), 127.0);
+    const double rv = __dmul_rn(__ddiv_rn(cv, bm1), 127.0);
+    const double ku = __dadd_rn(__dmul_rn(__ddiv_rn(ru, 127.0), 63.0), 32.0);
+    const double kv = __dadd_rn(__dmul_rn(__ddiv_rn(rv, 127.0), 63.0), 32.0);
+    p.cd = cd;
+    p.ok = 0;
+    p.tx0 = p.tx1 = p.ty0 = p.ty1 = 0;
+    p.tap[0] = p.tap[1] = p.tap[2] = p.tap[3] = 0.0;
+    const double nu = __ddiv_rn(ru, 127.0), nv = __ddiv_rn(rv, 127.0), nd = __ddiv_rn(cd, g.cube);
+    if (uvd_norm_out != nullptr) {
+        uvd_norm_out[0] = __double2float_rn(nu);
+        uvd_norm_out[1] = __double2float_rn(nv);
+        uvd_norm_out[2] = __double2float_rn(nd);
+    }
+    if (!isfinite(ku) || !isfinite(kv) || isnan(nd)) return;       // int(floor(nan/inf)) raises / NaN gate
+    const double flu = floor(ku), flv = floor(kv);
+    if (flu < -64.0 || flu > 62.0 || flv < -64.0 || flv > 62.0) return;   // IndexError -> "Out of range"
+    const int lu = static_cast<int>(flu), lv = static_cast<int>(flv);
+    const double du = __dsub_rn(ku, flu), dv = __dsub_rn(kv, flv);
+    const double t = __dsub_rn(__dadd_rn(du, dv), 1.0);
+    const double min_d = (0.0 > t) ? 0.0 : t;                      // max(du + dv - 1, 0)
+    const double max_d = (dv < du) ? dv : du;                      // min(du, dv)
+    const double d = __ddiv_rn(__dadd_rn(max_d, min_d), 2.0);
+    p.tap[1] = __dsub_rn(du, d);
+    p.tap[2] = __dsub_rn(dv, d);
+    p.tap[0] = __dsub_rn(__dsub_rn(__dadd_rn(1.0, d), du), dv);
+    p.tap[3] = d;
+    p.tx0 = lu < 0 ? lu + kLabel : lu;                             // negative indices wrap NumPy-style
+    p.tx1 = lu + 1 < 0 ? lu + 1 + kLabel : lu + 1;
+    p.ty0 = lv < 0 ? lv + kLabel : lv;
+    p.ty1 = lv + 1 < 0 ? lv + 1 + kLabel : lv + 1;
+    p.ok = 1;
+}
+
+// weight with which a unit impulse at index t reaches output index x through the
+// 7-tap Gaussian with BORDER_REFLECT_101 on a 64-long axis
+__device__ __forceinline__ double gauss_reach(int x, int t) {
+    double wgt = 0.0;
+    const int k0 = t - x + 3;                   // direct
+    if (k0 >= 0 && k0 <= 6) wgt += kGauss7[k0];
+    const int k1 = 3 - x - t;                   // reflected at the low border: -(x+k-3) == t
+    if (t >= 1 && k1 >= 0 && k1 <= 6) wgt += kGauss7[k1];
+    const int k2 = 2 * kLabel + 1 - x - t;      // reflected at the high border: 126-(x+k-3) == t
+    if (t <= kLabel - 2 && k2 >= 0 && k2 <= 6) wgt += kGauss7[k2];
+    return wgt;
+}
+
+// ---- working-type arithmetic (float for float32 frames, double for MSRA) ----
+template <typename T> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    // window + centring of one frame pixel, datasets.py:312,315
+    static __device__ __forceinline__ float window(float v, const SampleGeom& g) {
+        const float keep = (v > g.lo_dn && v < g.hi_up) ? 1.f : 0.f;   // == float64 compare, see SampleGeom
+        v = __fmul_rn(v, keep);
+        if (v > 0.f) v = __double2float_rn(__dsub_rn(static_cast<double>(v), g.z));
+        return v;
+    }
+};
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double window(double v, const SampleGeom& g) {
+        const double keep = (v > g.lo && v < g.hi) ? 1.0 : 0.0;
+        v = __dmul_rn(v, keep);
+        if (v > 0.0) v = __dsub_rn(v, g.z);
+        return v;
+    }
+};
+
+struct SfrArgs {
+    const float* frames; int Hf, Wf;
+    const double* com; const double* cube; const double* uvd;
+    double fx, fy;
+    float* img; float* label_img; float* mask;
+    float* box_size; float* cube_size; float* com_out;
+    float* uvd_norm; float* heatmaps; float* dmap;
+    uint8_t* valid;
+    int B, J;
+};
+
+template <typename T, bool TRAIN>
+__global__ void __launch_bounds__(kThreads)
+sfr_build_kernel(SfrArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ SampleGeom geom;
+    __shared__ JointParam joints[TRAIN ? PWR_MAX_JOINTS : 1];
+    __shared__ TapX xtap[kImage];
+    __shared__ TapX ytap[2 * kBandRows];
+    __shared__ T label_s[kBandRows * kLabel];
+    __shared__ int band_flags[2];               // [0] mask count, [1] NaN seen; read by rank 0 through DSMEM
+
+    const int band = static_cast<int>(cluster.block_rank());
+    const int b = blockIdx.x / kBands;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) sample_geometry(geom, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf);
+    __syncthreads();
+    const SampleGeom g = geom;
+
+    int joints_ok = 1;
+    if (TRAIN) {
+        if (tid < a.J) {
+            float* un = (band == 0) ? a.uvd_norm + (static_cast<size_t>(b) * a.J + tid) * 3 : nullptr;
+            if (g.ok) {
+                joint_param(joints[tid], un, a.uvd + (static_cast<size_t>(b) * a.J + tid) * 3, g);
+            } else {
+                joints[tid].ok = 0;
+                if (un != nullptr) { un[0] = 0.f; un[1] = 0.f; un[2] = 0.f; }
+            }
+        }
+    }
+    if (g.ok) {
+        if (tid < kImage) xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);
+        else if (tid < kImage + 2 * kBandRows)
+            ytap[tid - kImage] = linear_tap(band * 2 * kBandRows + (tid - kImage), g.nrows, g.scale_y);
+    }
+    __syncthreads();
+    if (TRAIN) {
+        for (int j = 0; j < a.J; ++j) joints_ok &= joints[j].ok;
+    }
+
+    // ---- phase 1: image band, label band, mask band -------------------------
+    float* img_b = a.img + static_cast<size_t>(b) * kImage * kImage;
+    float* lab_b = a.label_img + static_cast<size_t>(b) * kMap;
+    float* msk_b = a.mask + static_cast<size_t>(b) * kMap;
+    const float* frame = a.frames + static_cast<size_t>(b) * a.Hf * a.Wf;
+    const T cube_t = static_cast<T>(g.cube);
+    int my_count = 0, my_nan = 0;
+#pragma unroll 1
+    for (int it = 0; it < kLabelIters; ++it) {
+        const int lrow = it * (kThreads / kLabel) + (tid >> 6);     // label row inside the band
+        const int lx = tid & (kLabel - 1);
+        const int gly = band * kBandRows + lrow;                   // label row in the sample
+        T lab = T(0);
+        float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+        if (g.ok) {
+            T px[2][2];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const TapX ty = ytap[2 * lrow + dy];
+                const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
+                const bool ra = fr_a >= 0 && fr_a < a.Hf, rb = fr_b >= 0 && fr_b < a.Hf;
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const TapX tx = xtap[2 * lx + dx];
+                    const int fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
+                    const bool ca = fc_a >= 0 && fc_a < a.Wf, cb = fc_b >= 0 && fc_b < a.Wf;
+                    const float v00 = (ra && ca) ? __ldg(frame + static_cast<size_t>(fr_a) * a.Wf + fc_a) : 0.f;
+                    const float v01 = (ra && cb) ? __ldg(frame + static_cast<size_t>(fr_a) * a.Wf + fc_b) : 0.f;
+                    const float v10 = (rb && ca) ? __ldg(frame + static_cast<size_t>(fr_b) * a.Wf + fc_a) : 0.f;
+                    const float v11 = (rb && cb) ? __ldg(frame + static_cast<size_t>(fr_b) * a.Wf + fc_b) : 0.f;
+                    const T w00 = Arith<T>::window(static_cast<T>(v00), g);
+                    const T w01 = Arith<T>::window(static_cast<T>(v01), g);
+                    const T w10 = Arith<T>::window(static_cast<T>(v10), g);
+                    const T w11 = Arith<T>::window(static_cast<T>(v11), g);
+                    const T xa0 = static_cast<T>(tx.a0), xa1 = static_cast<T>(tx.a1);
+                    const T top = Arith<T>::add(Arith<T>::mul(w00, xa0), Arith<T>::mul(w01, xa1));
+                    const T bot = Arith<T>::add(Arith<T>::mul(w10, xa0), Arith<T>::mul(w11, xa1));
+                    px[dy][dx] = Arith<T>::add(Arith<T>::mul(top, static_cast<T>(ty.a0)),
+                                               Arith<T>::mul(bot, static_cast<T>(ty.a1)));
+                }
+            }
+            // 2x2 mean (cv::resize reroutes an exact 2x INTER_LINEAR shrink to the area path)
+            lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
+                                T(0.25));
+            o0 = make_float2(static_cast<float>(Arith<T>::div(px[0][0], cube_t)),
+                             static_cast<float>(Arith<T>::div(px[0][1], cube_t)));
+            o1 = make_float2(static_cast<float>(Arith<T>::div(px[1][0], cube_t)),
+                             static_cast<float>(Arith<T>::div(px[1][1], cube_t)));
+        }
+        const float labn = static_cast<float>(Arith<T>::div(lab, cube_t));
+        const bool hand = g.ok && (lab != T(0));
+        *reinterpret_cast<float2*>(img_b + (2 * gly) * kImage + 2 * lx) = o0;
+        *reinterpret_cast<float2*>(img_b + (2 * gly + 1) * kImage + 2 * lx) = o1;
+        lab_b[gly * kLabel + lx] = g.ok ? labn : 0.f;
+        msk_b[gly * kLabel + lx] = hand ? 1.f : 0.f;
+        label_s[lrow * kLabel + lx] = lab;
+        my_count += hand ? 1 : 0;
+        my_nan |= (isnan(o0.x) || isnan(o0.y) || isnan(o1.x) || isnan(o1.y) || isnan(labn)) ? 1 : 0;
+    }
+    __syncthreads();                                      // label_s complete
+    {
+        // block totals of my_count / my_nan
+        int c = my_count, n = my_nan;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); n |= __shfl_xor_sync(0xffffffffu, n, o); }
+        if (tid == 0) { band_flags[0] = 0; band_flags[1] = 0; }
+        __syncthreads();
+        if ((tid & 31) == 0) { atomicAdd(&band_flags[0], c); atomicOr(&band_flags[1], n); }
+    }
+    cluster.sync();                                       // all bands published their flags
+    if (band == 0 && tid == 0) {
+        int count = 0, nan_seen = 0;
+        for (int r = 0; r < kBands; ++r) {
+            const int* peer = cluster.map_shared_rank(band_flags, r);
+            count += peer[0];
+            nan_seen |= peer[1];
+        }
+        uint8_t v = g.ok ? 1 : 0;
+        if (TRAIN) v = (g.ok && joints_ok && !nan_seen && count >= 10) ? 1 : 0;   // datasets.py:362-365,385-390
+        a.valid[b] = v;
+        a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
+        a.cube_size[b] = static_cast<float>(g.cube);
+        a.com_out[3 * b + 0] = static_cast<float>(g.c0);
+        a.com_out[3 * b + 1] = static_cast<float>(g.r0);
+        a.com_out[3 * b + 2] = static_cast<float>(g.z);
+    }
+    cluster.sync();                                       // peers stay resident until rank 0 has read them
+
+    // ---- phase 2: heat maps and depth maps of this band ----------------------
+    if (TRAIN) {
+        constexpr int kItemsPerJoint = kBandRows * (kLabel / 4);   // float4 items per joint per band
+        const int total = a.J * kItemsPerJoint;
+        for (int item = tid; item < total; item += kThreads) {
+            const int j = item / kItemsPerJoint;
+            const int rem = item - j * kItemsPerJoint;
+            const int lrow = rem >> 4;
+            const int x0 = (rem & 15) * 4;
+            const int gy = band * kBandRows + lrow;
+            const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + gy * kLabel + x0;
+            float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = h4;
+            const JointParam& jp = joints[j];
+            const bool near_y = abs(gy - jp.ty0) <= 3 || abs(gy - jp.ty1) <= 3;
+            const bool near_x = (x0 + 3 >= jp.tx0 - 3 && x0 <= jp.tx0 + 3) || (x0 + 3 >= jp.tx1 - 3 && x0 <= jp.tx1 + 3);
+            if (g.ok && jp.ok && near_y && near_x) {
+                const double wy0 = gauss_reach(gy, jp.ty0), wy1 = gauss_reach(gy, jp.ty1);
+                float hv[4], dv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double wx0 = gauss_reach(x0 + k, jp.tx0), wx1 = gauss_reach(x0 + k, jp.tx1);
+                    // separable order of cv2.GaussianBlur: rows first, then columns
+                    const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
+                    const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
+                    const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
+                    hv[k] = __double2float_rn(h);
+                    const T lab = label_s[lrow * kLabel + x0 + k];
+                    // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
+                    dv[k] = (h > 0.0 && lab != T(0))
+                                ? __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube))
+                                : 0.f;
+                }
+                h4 = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                d4 = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            }
+            st_stream(a.heatmaps + o, h4);
+            st_stream(a.dmap + o, d4);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// centre-of-mass fallback, datasets.py:208-211
+// ---------------------------------------------------------------------------
+constexpr int kComThreads = 512;
+
+__global__ void __launch_bounds__(kComThreads)
+sfr_com_kernel(const float* __restrict__ frames, int Hf, int Wf, double* __restrict__ com) {
+    __shared__ double s_z[kComThreads / 32];
+    __shared__ long long s_r[kComThreads / 32], s_c[kComThreads / 32], s_n[kComThreads / 32];
+    const int b = blockIdx.x;
+    const float* frame = frames + static_cast<size_t>(b) * Hf * Wf;
+    double sz = 0.0;
+    long long sr = 0, sc = 0, sn = 0;
+    const int n = Hf * Wf;
+    for (int i = threadIdx.x; i < n; i += kComThreads) {
+        const float v = __ldg(frame + i);
+        if (v > 0.f) {
+            sz += static_cast<double>(v);
+            sr += i / Wf;
+            sc += i % Wf;
+            sn += 1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_z[warp] = sz; s_r[warp] = sr; s_c[warp] = sc; s_n[warp] = sn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sz = 0.0; sr = sc = sn = 0;
+        for (int wv = 0; wv < kComThreads / 32; ++wv) { sz += s_z[wv]; sr += s_r[wv]; sc += s_c[wv]; sn += s_n[wv]; }
+        const double cnt = static_cast<double>(sn);
+        com[3 * b + 0] = __ddiv_rn(static_cast<double>(sc), cnt);
+        com[3 * b + 1] = __ddiv_rn(static_cast<double>(sr), cnt);
+        com[3 * b + 2] = __ddiv_rn(sz, cnt);
+    }
+}
+
+template <typename T, bool TRAIN>
+static int launch_sfr(const SfrArgs& a, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.B) * kBands, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBands;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, sfr_build_kernel<T, TRAIN>, a);
+    if (err != cudaSuccess) { cudaGetLastError(); return static_cast<int>(err); }
+    return launch_status();
+}
+
+static int check_frames(int Hf, int Wf, int B) {
+    if (B < 0 || Hf < 1 || Wf < 1 || Hf > 16384 || Wf > 16384) return PWR_E_SHAPE;
+    if (static_cast<long long>(B) * kBands > 0x7fffffffLL) return PWR_E_SHAPE;
+    return 0;
+}
+
+}  // namespace pwr
+
+using namespace pwr;
+
+extern "C" int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com, int B, void* stream) {
+    if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (frames == nullptr || com == nullptr) return PWR_E_NULL;
+    if (B == 0) return 0;
+    sfr_com_kernel<<<B, kComThreads, 0, static_cast<cudaStream_t>(stream)>>>(frames, Hf, Wf, com);
+    return launch_status();
+}
+
+extern "C" int pwr_sfr_crop(const float* frames, int Hf, int Wf, const double* com, const double* cube, double fx,
+                            double fy, int frame_f64, float* img, float* label_img, float* mask, float* box_size,
+                            float* cube_size, float* com_out, uint8_t* valid, int B, void* stream) {
+    if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (frames == nullptr || com == nullptr || cube == nullptr || box_size == nullptr || cube_size == nullptr ||
+        com_out == nullptr || valid == nullptr)
+        return PWR_E_NULL;
+    PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
+    if (B == 0) return 0;
+    SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
+                 nullptr, nullptr, nullptr, valid, B, 0};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return frame_f64 ? launch_sfr<double, false>(a, s) : launch_sfr<float, false>(a, s);
+}
+
+extern "C" int pwr_sfr_build(const float* frames, int Hf, int Wf, const double* com, const double* cube,
+                             const double* uvd, double fx, double fy, int frame_f64, float* img, float* label_img,
+                             float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
+                             float* heatmaps, float* dmap, uint8_t* valid, int B, int J, void* stream) {
+    if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
+    if (frames == nullptr || com == nullptr || cube == nullptr || uvd == nullptr || box_size == nullptr ||
+        cube_size == nullptr || com_out == nullptr || uvd_norm == nullptr || valid == nullptr)
+        return PWR_E_NULL;
+    PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
+    PWR_REQUIRE_PTR(heatmaps); PWR_REQUIRE_PTR(dmap);
+    if (B == 0) return 0;
+    SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
+                 uvd_norm, heatmaps, dmap, valid, B, J};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return frame_f64 ? launch_sfr<double, true>(a, s) : launch_sfr<float, true>(a, s);
+}

@@ -1,0 +1,300 @@
+"""Host-side operators over libpwr_b200.so: raw launches and autograd glue.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every
+function below enqueues hand-written sm_100a kernels on the current stream
+through the C ABI of include/pwr.h.  There is no eager / CPU fallback.
+
+Reference lines replaced: model.py:79-97, 123-132, 151 (decoder forward),
+what autograd derives from them plus train.py:197-207 (backward + loss),
+utils.py:332-337 + datasets.py:100-111 (recover_uvd / uvd2xyz).
+"""
+import torch
+
+from . import _lib
+from ._lib import METHODS, as_f32, check, ptr, require_cuda, stream_ptr
+
+HW = 64
+MAP = HW * HW
+
+
+def _check_maps(z, label_img, mask):
+    if z.dim() != 4 or z.shape[2] != HW or z.shape[3] != HW:
+        raise _lib.PwrError("decoder maps must be [B, J, 64, 64], got %s" % (tuple(z.shape),))
+    B = z.shape[0]
+    for name, t in (("label_img", label_img), ("mask", mask)):
+        if t is not None and tuple(t.shape) != (B, 1, HW, HW):
+            raise _lib.PwrError("%s must be [B, 1, 64, 64], got %s" % (name, tuple(t.shape)))
+
+
+def decoder_forward_raw(z, w, D, label_img, mask, method="softmax", store_heat=True, want_stats=True,
+                        targets=None):
+    """One launch of pwr_decoder_fwd.  Returns (H or None, uvd, stats or None,
+    loss_partial or None); all inputs float32 CUDA tensors."""
+    require_cuda(z, w, D, label_img, mask)
+    lib = _lib.load()
+    z = as_f32(z)
+    D = as_f32(D)
+    label_img = as_f32(label_img)
+    mask = as_f32(mask)
+    _check_maps(z, label_img if D is not None else None, mask if D is not None else None)
+    B, J = z.shape[0], z.shape[1]
+    wv = as_f32(w).reshape(-1) if w is not None else None
+    H = torch.empty_like(z) if store_heat else None
+    uvd = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
+    stats = torch.empty(B, J, 4, device=z.device, dtype=torch.float32) if want_stats else None
+    heat_gt = dmap_gt = uvd_gt = loss_partial = None
+    if targets is not None:
+        heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
+        loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        rc = lib.pwr_decoder_fwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
+                                 ptr(uvd_gt), ptr(H), ptr(uvd), ptr(stats), ptr(loss_partial), B, J,
+                                 METHODS[method], stream_ptr(z.device))
+    check(rc, "pwr_decoder_fwd")
+    return H, uvd, stats, loss_partial
+
+
+def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up=None, gD_up=None,
+                         method="softmax", targets=None, alpha=1.0, lambda_h=1.0, lambda_d=0.01,
+                         loss_scale=1.0, loss_scale_dev=None, n_mean=0, want_loss=False, want_gz=True,
+                         want_gD=True):
+    """One launch of pwr_decoder_bwd (targets None) or pwr_decoder_bwd_loss.
+    Returns (gz, gD, gw_partial [B,J] or None, loss_partial [B,J,3] or None)."""
+    require_cuda(z, w, D, label_img, mask, stats, uvd, g_uvd, gH_up, gD_up)
+    lib = _lib.load()
+    z = as_f32(z)
+    D = as_f32(D)
+    B, J = z.shape[0], z.shape[1]
+    wv = as_f32(w).reshape(-1) if w is not None else None
+    gz = torch.empty_like(z) if want_gz else None
+    gD = torch.empty_like(z) if (want_gD and D is not None) else None
+    gw_partial = torch.empty(B, J, device=z.device, dtype=torch.float32) if method == "softmax" else None
+    g_uvd = as_f32(g_uvd)
+    gH_up = as_f32(gH_up)
+    gD_up = as_f32(gD_up)
+    s = stream_ptr(z.device)
+    with torch.cuda.device(z.device):
+        if targets is None:
+            rc = lib.pwr_decoder_bwd(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
+                                     ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(gz), ptr(gD),
+                                     ptr(gw_partial), B, J, METHODS[method], s)
+            check(rc, "pwr_decoder_bwd")
+            return gz, gD, gw_partial, None
+        heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
+        loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32) if want_loss else None
+        rc = lib.pwr_decoder_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
+                                      ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(heat_gt),
+                                      ptr(dmap_gt), ptr(uvd_gt), float(alpha), float(lambda_h), float(lambda_d),
+                                      float(loss_scale), ptr(as_f32(loss_scale_dev)), int(n_mean), ptr(gz),
+                                      ptr(gD), ptr(gw_partial),
+                                      ptr(loss_partial), B, J, METHODS[method], s)
+    check(rc, "pwr_decoder_bwd_loss")
+    return gz, gD, gw_partial, loss_partial
+
+
+def reduce_partials(partial):
+    """[B, J] or [B, J, C] per-(sample, joint) partials -> [J] / [J, C] batch sums
+    (deterministic tree, pwr_reduce_partials)."""
+    require_cuda(partial)
+    B, J = partial.shape[0], partial.shape[1]
+    C = partial.shape[2] if partial.dim() == 3 else 1
+    out = torch.empty((J, C) if partial.dim() == 3 else (J,), device=partial.device, dtype=torch.float32)
+    with torch.cuda.device(partial.device):
+        rc = _lib.load().pwr_reduce_partials(ptr(partial.contiguous()), ptr(out), B, J, C,
+                                             stream_ptr(partial.device))
+    check(rc, "pwr_reduce_partials")
+    return out
+
+
+def scale_inplace_(x, scale):
+    """x *= scale, with `scale` a 0-dim CUDA tensor (no host sync; a no-op launch when scale == 1)."""
+    require_cuda(x, scale)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(as_f32(scale)), x.numel(), stream_ptr(x.device))
+    check(rc, "pwr_scale_inplace")
+    return x
+
+
+def stage_loss_from_partials(loss_partial, lambda_h, lambda_d, n_mean=None):
+    """train.py:197-199 from per-(b,j) sums of squares: returns a [3] tensor
+    (heatmap_loss, depthmap_loss, uvd_loss)."""
+    B, J = loss_partial.shape[0], loss_partial.shape[1]
+    n = float(n_mean if n_mean else B * J)
+    sums = reduce_partials(loss_partial).sum(dim=0)          # [3]
+    scale = torch.tensor([lambda_h / n, lambda_d / n, 1.0 / n], device=sums.device, dtype=torch.float32)
+    return sums * scale
+
+
+class DecoderFunction(torch.autograd.Function):
+    """Differentiable fused decoder: (z, w, D, label_img, mask) -> (heatmaps,
+    depthmaps, uvd), model.py:147-151 without the two conv stacks.  `depthmaps`
+    is D itself (model.py:132 returns the conv output unchanged); routing it
+    through this node lets the backward kernel fold the dense upstream gradient
+    on the depth maps (next stage's conv, loss) into its single pass.
+
+    With `targets` the stage loss of train.py:197-205 rides along: its value
+    comes out of the forward kernel (4th/5th outputs: combined loss, [3] terms)
+    and its gradient is added inside the backward kernel, scaled by the
+    upstream gradient on the combined loss (read on the device)."""
+
+    @staticmethod
+    def forward(ctx, z, w, D, label_img, mask, method, heat_gt=None, dmap_gt=None, uvd_gt=None, alpha=1.0,
+                lambda_h=1.0, lambda_d=0.01):
+        targets = (heat_gt, dmap_gt, uvd_gt) if heat_gt is not None else None
+        H, uvd, stats, loss_partial = decoder_forward_raw(z, w, D, label_img, mask, method, targets=targets)
+        ctx.method = method
+        ctx.in_dtypes = (z.dtype, D.dtype)
+        ctx.loss_cfg = (alpha, lambda_h, lambda_d) if targets is not None else None
+        ctx.save_for_backward(z, w, D, label_img, mask, stats, uvd, heat_gt, dmap_gt, uvd_gt)
+        outs = (H.to(z.dtype), D.view_as(D), uvd.to(z.dtype))
+        if targets is None:
+            return outs
+        terms = stage_loss_from_partials(loss_partial, lambda_h, lambda_d)
+        total = alpha * terms[2] + (1.0 - alpha) * (terms[0] + terms[1])
+        ctx.mark_non_differentiable(terms)
+        return outs + (total, terms)
+
+    @staticmethod
+    def backward(ctx, gH, gD_up, g_uvd, g_total=None, g_terms=None):
+        z, w, D, label_img, mask, stats, uvd, heat_gt, dmap_gt, uvd_gt = ctx.saved_tensors
+        if ctx.loss_cfg is not None and g_total is not None:
+            alpha, lambda_h, lambda_d = ctx.loss_cfg
+            gz, gD, gw_partial, _ = decoder_backward_raw(
+                z, w, D, label_img, mask, stats, uvd, g_uvd, gH, gD_up, ctx.method,
+                targets=(heat_gt, dmap_gt, uvd_gt), alpha=alpha, lambda_h=lambda_h, lambda_d=lambda_d,
+                loss_scale_dev=g_total)
+        else:
+            gz, gD, gw_partial, _ = decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd, gH, gD_up,
+                                                         ctx.method)
+        gw = None
+        if w is not None and ctx.needs_input_grad[1]:
+            gw = reduce_partials(gw_partial).view_as(w).to(w.dtype)
+        return (gz.to(ctx.in_dtypes[0]), gw, gD.to(ctx.in_dtypes[1])) + (None,) * 9
+
+
+def fused_decoder(z, w, D, label_img, mask, method="softmax"):
+    """Autograd-connected fused decoder.  Returns (heatmaps, depthmaps, uvd)."""
+    if torch.is_grad_enabled() and (z.requires_grad or D.requires_grad or (w is not None and w.requires_grad)):
+        return DecoderFunction.apply(z, w, D, label_img, mask, method)
+    H, uvd, _, _ = decoder_forward_raw(z, w, D, label_img, mask, method, want_stats=False)
+    return H.to(z.dtype), D, uvd.to(z.dtype)
+
+
+def fused_decoder_with_loss(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method="softmax", alpha=1.0,
+                            lambda_h=1.0, lambda_d=0.01):
+    """Inner-stage variant: returns (heatmaps, depthmaps, uvd, stage_loss, terms[3])
+    with heatmaps/depthmaps/uvd/stage_loss all differentiable."""
+    return DecoderFunction.apply(z, w, D, label_img, mask, method, heat_gt, dmap_gt, uvd_gt, float(alpha),
+                                 float(lambda_h), float(lambda_d))
+
+
+class PlaneFunction(torch.autograd.Function):
+    """PlaneRegression.forward called on its own (model.py:79-97): no depth branch."""
+
+    @staticmethod
+    def forward(ctx, z, w, method):
+        H, uvd, stats, _ = decoder_forward_raw(z, w, None, None, None, method)
+        ctx.method = method
+        ctx.save_for_backward(z, w, stats, uvd)
+        return H.to(z.dtype), uvd[:, :, :2].contiguous().to(z.dtype)
+
+    @staticmethod
+    def backward(ctx, gH, g_uv):
+        z, w, stats, uvd = ctx.saved_tensors
+        g_uvd = None
+        if g_uv is not None:
+            g_uvd = torch.zeros_like(uvd)
+            g_uvd[:, :, :2] = g_uv
+        gz, _, gw_partial, _ = decoder_backward_raw(z, w, None, None, None, stats, uvd, g_uvd, gH, None, ctx.method)
+        gw = None
+        if w is not None and ctx.needs_input_grad[1]:
+            gw = reduce_partials(gw_partial).view_as(w).to(w.dtype)
+        return gz.to(z.dtype), gw, None
+
+
+class DepthFunction(torch.autograd.Function):
+    """DepthRegression.forward called on its own with caller-supplied heat maps
+    (model.py:123-132): the heat maps take the place of the logits
+    (PWR_METHOD_GIVEN), gradients flow to both the heat maps and D."""
+
+    @staticmethod
+    def forward(ctx, D, heatmaps, label_img, mask):
+        _, uvd, stats, _ = decoder_forward_raw(heatmaps, None, D, label_img, mask, "given", store_heat=False)
+        ctx.save_for_backward(D, heatmaps, label_img, mask, stats, uvd)
+        return uvd[:, :, 2:].contiguous().to(D.dtype)
+
+    @staticmethod
+    def backward(ctx, g_d):
+        D, heatmaps, label_img, mask, stats, uvd = ctx.saved_tensors
+        g_uvd = torch.zeros_like(uvd)
+        g_uvd[:, :, 2:] = g_d
+        gH, gD, _, _ = decoder_backward_raw(heatmaps, None, D, label_img, mask, stats, uvd, g_uvd, None, None,
+                                            "given")
+        return gD.to(D.dtype), gH.to(heatmaps.dtype), None, None
+
+
+class DecoderLossFunction(torch.autograd.Function):
+    """Last-stage decoder fused with the stage loss, train.py:197-207.
+
+    forward runs the forward kernel and then, when gradients are needed, the
+    fused backward+loss kernel straight away (unit upstream): the loss value
+    and the gradients come out of one pass over (z, D, heat_gt, dmap_gt).  The
+    autograd backward only rescales the stored gradients by the upstream scalar
+    (a no-op launch when it is 1, e.g. without a GradScaler).  Only `total` is
+    differentiable; the returned heat maps / uvd / loss terms are detached
+    (use DecoderFunction when later layers consume the maps)."""
+
+    @staticmethod
+    def forward(ctx, z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method, alpha, lambda_h, lambda_d,
+                store_heat):
+        need_grad = any(ctx.needs_input_grad[:3])
+        H, uvd, stats, _ = decoder_forward_raw(z, w, D, label_img, mask, method, store_heat=store_heat)
+        targets = (heat_gt, dmap_gt, uvd_gt)
+        gz, gD, gw_partial, loss_partial = decoder_backward_raw(
+            z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
+            want_loss=True, want_gz=need_grad, want_gD=need_grad)
+        terms = stage_loss_from_partials(loss_partial, lambda_h, lambda_d)
+        total = alpha * terms[2] + (1.0 - alpha) * (terms[0] + terms[1])
+        gw = reduce_partials(gw_partial).view_as(w) if (need_grad and w is not None) else None
+        ctx.has_w = w is not None
+        ctx.grads = (gz, gD, gw)
+        outs = (total, terms, uvd) + ((H,) if store_heat else ())
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        gz, gD, gw = ctx.grads
+        ctx.grads = None
+        if gz is None:
+            raise _lib.PwrError("DecoderLossFunction: forward ran without gradient tracking")
+        scale_inplace_(gz, g_total)
+        scale_inplace_(gD, g_total)
+        if gw is not None:
+            gw = gw * g_total
+        return (gz, gw, gD) + (None,) * 10
+
+
+def fused_decoder_loss(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method="softmax", alpha=1.0,
+                       lambda_h=1.0, lambda_d=0.01, store_heat=True):
+    """Returns (total_loss, loss_terms[3] = (heatmap, depthmap, uvd), uvd[, heatmaps])."""
+    return DecoderLossFunction.apply(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method, float(alpha),
+                                     float(lambda_h), float(lambda_d), bool(store_heat))
+
+
+def recover_uvd(uvd_norm, box_size, com, cube_size, intrinsics=None):
+    """utils.py:332-337 on the GPU (no .cpu() round trip, test.py:106-113).
+    Returns uvd in pixels/mm; with intrinsics=(fx, fy, halfu, halfv) also xyz
+    (datasets.py:100-111)."""
+    require_cuda(uvd_norm, box_size, com, cube_size)
+    B, J = uvd_norm.shape[0], uvd_norm.shape[1]
+    uvd_norm = as_f32(uvd_norm)
+    uvd_px = torch.empty_like(uvd_norm)
+    xyz = torch.empty_like(uvd_norm) if intrinsics is not None else None
+    fx, fy, hu, hv = intrinsics if intrinsics is not None else (1.0, 1.0, 0.0, 0.0)
+    with torch.cuda.device(uvd_norm.device):
+        rc = _lib.load().pwr_recover_uvd(ptr(uvd_norm), ptr(as_f32(box_size)), ptr(as_f32(cube_size)),
+                                         ptr(as_f32(com)), fx, fy, hu, hv, ptr(uvd_px), ptr(xyz), B, J,
+                                         stream_ptr(uvd_norm.device))
+    check(rc, "pwr_recover_uvd")
+    return (uvd_px, xyz) if intrinsics is not None else uvd_px

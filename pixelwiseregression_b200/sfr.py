@@ -1,0 +1,96 @@
+"""Batched SFR target builder on the GPU (pwr_sfr_* of include/pwr.h).
+
+Mirrors HandDataset.process_single_data, non-augmented branch
+(datasets.py:301-403), for a whole batch at once: the returned tensors have
+exactly the shapes and dtypes `default_collate` produces from the reference's
+9-tuple (train) / 6-tuple (test_only), plus `valid [B] uint8`, which replaces
+the reference's exception path (datasets.py:323-327, 362-365, 385-390).
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+
+SFRBatch = namedtuple("SFRBatch", ["img", "label_img", "mask", "box_size", "cube_size", "com", "uvd", "heatmaps",
+                                   "depthmaps", "valid"])
+SFRTestBatch = namedtuple("SFRTestBatch", ["img", "label_img", "mask", "box_size", "cube_size", "com", "valid"])
+
+
+def _f64(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.asarray(x, dtype=np.float64), device=device)
+
+
+def center_of_mass(frames):
+    """datasets.py:208-211 for a batch: [B,Hf,Wf] float32 CUDA -> com [B,3] float64
+    (mean column, mean row, mean depth of the pixels > 0)."""
+    require_cuda(frames)
+    if frames.dtype != torch.float32 or frames.dim() != 3:
+        raise _lib.PwrError("frames must be a [B, Hf, Wf] float32 tensor")
+    frames = frames.contiguous()
+    B, Hf, Wf = frames.shape
+    com = torch.empty(B, 3, device=frames.device, dtype=torch.float64)
+    with torch.cuda.device(frames.device):
+        rc = _lib.load().pwr_sfr_com(ptr(frames), Hf, Wf, ptr(com), B, stream_ptr(frames.device))
+    check(rc, "pwr_sfr_com")
+    return com
+
+
+def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only=False):
+    """frames [B,Hf,Wf] float32 CUDA depth frames (mm); com [B,3] float64 hand
+    centre (u, v, z) or None to use the centre-of-mass fallback; cube [B] (or a
+    scalar) half cube size; uvd [B,J,3] float64 joint annotations (train mode).
+    `frame_f64=True` reproduces datasets whose frames the reference holds as
+    float64 (MSRA, datasets.py:516).
+
+    Returns SFRBatch (train) or SFRTestBatch (test_only), all float32 except
+    `valid` (uint8)."""
+    require_cuda(frames)
+    if frames.dtype != torch.float32 or frames.dim() != 3:
+        raise _lib.PwrError("frames must be a [B, Hf, Wf] float32 tensor")
+    lib = _lib.load()
+    frames = frames.contiguous()
+    dev = frames.device
+    B, Hf, Wf = frames.shape
+    if com is None:
+        com = center_of_mass(frames)
+    com = _f64(com, dev)
+    if not isinstance(cube, torch.Tensor) and np.ndim(cube) == 0:
+        cube = np.full(B, float(cube))
+    cube = _f64(cube, dev)
+    if tuple(com.shape) != (B, 3) or tuple(cube.shape) != (B,):
+        raise _lib.PwrError("com must be [B,3] and cube [B]")
+    f32 = dict(device=dev, dtype=torch.float32)
+    img = torch.empty(B, 1, 128, 128, **f32)
+    label_img = torch.empty(B, 1, 64, 64, **f32)
+    mask = torch.empty(B, 1, 64, 64, **f32)
+    box_size = torch.empty(B, **f32)
+    cube_size = torch.empty(B, **f32)
+    com_out = torch.empty(B, 3, **f32)
+    valid = torch.empty(B, device=dev, dtype=torch.uint8)
+    s = stream_ptr(dev)
+    with torch.cuda.device(dev):
+        if test_only:
+            rc = lib.pwr_sfr_crop(ptr(frames), Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
+                                  ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
+                                  ptr(valid), B, s)
+            check(rc, "pwr_sfr_crop")
+            return SFRTestBatch(img, label_img, mask, box_size, cube_size, com_out, valid)
+        if uvd is None:
+            raise _lib.PwrError("train-mode SFR needs joint annotations (uvd)")
+        uvd = _f64(uvd, dev)
+        if uvd.dim() != 3 or uvd.shape[0] != B or uvd.shape[2] != 3:
+            raise _lib.PwrError("uvd must be [B, J, 3]")
+        J = uvd.shape[1]
+        uvd_norm = torch.empty(B, J, 3, **f32)
+        heatmaps = torch.empty(B, J, 64, 64, **f32)
+        dmap = torch.empty(B, J, 64, 64, **f32)
+        rc = lib.pwr_sfr_build(ptr(frames), Hf, Wf, ptr(com), ptr(cube), ptr(uvd), float(fx), float(fy),
+                               int(frame_f64), ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
+                               ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), B, J, s)
+        check(rc, "pwr_sfr_build")
+    return SFRBatch(img, label_img, mask, box_size, cube_size, com_out, uvd_norm, heatmaps, dmap, valid)

@@ -91,3 +91,44 @@ def make_decoder_inputs(batch: int, joints: int, seed: int = 0, hw: int = 64):
     mask = (rng.uniform(size=(batch, 1, hw, hw)) < 0.4).astype(np.float32)
     label = (rng.uniform(-1.0, 1.0, (batch, 1, hw, hw)).astype(np.float32)) * mask
     return dict(z=z, D=D, w=w, label=label, mask=mask)
+
+
+def make_frames_device(shape: DatasetShape, batch: int, seed: int = 0, device="cuda", chunk: int = 256,
+                       mixed_cube: bool = True):
+    """Device-side generator with the same recipe as make_frames (different random
+    stream), for batches too large to build in NumPy (the B=4096 micro-benchmark
+    holds 5 GB of NYU frames).  Returns CUDA tensors: frames [B,Hf,Wf] float32,
+    com [B,3] float64, cube [B] float64, uvd [B,J,3] float64."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    hf, wf, J = shape.height, shape.width, shape.joints
+    f64 = dict(device=device, dtype=torch.float64)
+    rnd = lambda *s: torch.rand(*s, generator=g, **f64)
+    com = torch.stack([(0.25 + 0.5 * rnd(batch)) * wf, (0.25 + 0.5 * rnd(batch)) * hf,
+                       shape.z_range[0] + (shape.z_range[1] - shape.z_range[0]) * rnd(batch)], dim=1)
+    cube = torch.full((batch,), float(shape.cube), **f64)
+    if mixed_cube and shape.name == "NYU":
+        cube = torch.where(rnd(batch) < 0.3, torch.full_like(cube, float(int(shape.cube * 5 / 6))), cube)
+    box = torch.clamp((cube / com[:, 2] * shape.fx + cube / com[:, 2] * shape.fy).floor(), min=2)
+    shift = (box / 2).floor()
+    uvd = torch.stack([com[:, 0:1] + (rnd(batch, J) * 1.2 - 0.6) * shift[:, None],
+                       com[:, 1:2] + (rnd(batch, J) * 1.2 - 0.6) * shift[:, None],
+                       com[:, 2:3] + (rnd(batch, J) * 200.0 - 100.0)], dim=2)
+    frames = torch.empty(batch, hf, wf, device=device, dtype=torch.float32)
+    yy = torch.arange(hf, device=device, dtype=torch.float32).view(1, hf, 1)
+    xx = torch.arange(wf, device=device, dtype=torch.float32).view(1, 1, wf)
+    for s in range(0, batch, chunk):
+        e = min(s + chunk, batch)
+        c = com[s:e].float()
+        cb = cube[s:e].float()
+        rad = 0.7 * cb / c[:, 2] * shape.fx
+        disc = (xx - c[:, 0].view(-1, 1, 1)) ** 2 + (yy - c[:, 1].view(-1, 1, 1)) ** 2 < (rad * rad).view(-1, 1, 1)
+        val = c[:, 2].view(-1, 1, 1) + (torch.rand(e - s, hf, wf, generator=g, device=device) * 200.0 - 100.0)
+        sel = torch.rand(e - s, hf, wf, generator=g, device=device)
+        clutter = c[:, 2].view(-1, 1, 1) + cb.view(-1, 1, 1) + 1.0 + 299.0 * torch.rand(
+            e - s, hf, wf, generator=g, device=device)
+        val = torch.where(sel < 0.05, clutter, val)
+        val = torch.where(sel > 0.95, torch.zeros_like(val), val)
+        frames[s:e] = torch.where(disc, val, torch.zeros_like(val))
+    return dict(frames=frames, com=com, cube=cube, uvd=uvd)

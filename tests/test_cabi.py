@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/pwr.h
+declares; argument validation happens before any CUDA call."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pixelwiseregression_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pwr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pwr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "libpwr_b200.so does not export %s" % n
+        assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_signature_arity_matches_header():
+    text = open(os.path.join(ROOT, "include", "pwr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, params in re.findall(r"\b(pwr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert len(_lib.SIGNATURES[name]) == n, name
+
+
+def test_version_and_error_strings(lib):
+    assert lib.pwr_version() == 100
+    assert lib.pwr_error_string(0) == b"ok"
+    assert b"NULL" in lib.pwr_error_string(-1)
+    assert b"aligned" in lib.pwr_error_string(-3)
+
+
+def test_argument_errors_without_a_gpu(lib):
+    null = None
+    fake = ctypes.c_void_p(0x1000)          # aligned, never dereferenced: validation fails first
+    odd = ctypes.c_void_p(0x1004)           # misaligned
+    # NULL required pointer
+    assert lib.pwr_decoder_fwd(null, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 0, null) == -1
+    # misaligned map pointer
+    assert lib.pwr_decoder_fwd(odd, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 0, null) == -3
+    # unknown method / bad shapes
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 7, null) == -4
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 0, 0, null) == -2
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, -1, 14, 0, null) == -2
+    assert lib.pwr_sfr_com(null, 480, 640, fake, 1, null) == -1
+    assert lib.pwr_sfr_com(fake, 0, 640, fake, 1, null) == -2
+    assert lib.pwr_reduce_partials(null, fake, 1, 1, 1, null) == -1
+    # B == 0 is a successful no-op
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 0, 14, 0, null) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PwrError, match="no CPU fallback"):
+        _lib.load()

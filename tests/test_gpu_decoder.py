@@ -1,0 +1,264 @@
+"""GPU parity: fused decoder forward / backward / backward+loss (through the C
+ABI) against the reference-generated golden vectors, the float64 oracle on seeded
+inputs, and size-independent properties at B=4096."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_oracle as do
+from pixelwiseregression_b200 import ops, synth
+from helpers import GRAD_RTOL, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_SETS = ["decoder_softmax_a1", "decoder_softmax_a05_up", "decoder_sum_a05_up"]
+DEV = "cuda:0"
+
+
+def cu(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dtype)
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_forward_matches_reference_golden(name):
+    g = load_golden(name)
+    method = str(g["method"])
+    w = cu(g["w"]) if method == "softmax" else None
+    targets = (cu(g["heat_gt"]), cu(g["dmap_gt"]), cu(g["uvd_gt"]))
+    H, uvd, stats, lp = ops.decoder_forward_raw(cu(g["z"]), w, cu(g["D"]), cu(g["label"]), cu(g["mask"]), method,
+                                                targets=targets)
+    assert_close("heat", H.cpu().numpy(), g["ref_heat"])
+    assert_close("uvd", uvd.cpu().numpy(), g["ref_uvd"])
+    terms = ops.stage_loss_from_partials(lp, float(g["lambda_h"]), float(g["lambda_d"])).cpu().numpy()
+    assert_close("loss terms", terms, g["ref_losses"][:3])
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_backward_loss_matches_reference_golden(name):
+    g = load_golden(name)
+    method = str(g["method"])
+    w = cu(g["w"]) if method == "softmax" else None
+    z, D, L, m = cu(g["z"]), cu(g["D"]), cu(g["label"]), cu(g["mask"])
+    targets = (cu(g["heat_gt"]), cu(g["dmap_gt"]), cu(g["uvd_gt"]))
+    up = "gH_up" in g
+    H, uvd, stats, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
+    gz, gD, gwp, lp = ops.decoder_backward_raw(
+        z, w, D, L, m, stats, uvd, cu(g["g_uvd_up"]) if up else None, cu(g["gH_up"]) if up else None,
+        cu(g["gD_up"]) if up else None, method, targets, float(g["alpha"]), float(g["lambda_h"]),
+        float(g["lambda_d"]), want_loss=True)
+    assert_close("gz", gz.cpu().numpy(), g["ref_gz"], GRAD_RTOL)
+    assert_close("gD", gD.cpu().numpy(), g["ref_gD"], GRAD_RTOL)
+    if method == "softmax":
+        assert_close("gw", ops.reduce_partials(gwp).view(-1, 1).cpu().numpy(), g["ref_gw"], GRAD_RTOL)
+    terms = ops.stage_loss_from_partials(lp, float(g["lambda_h"]), float(g["lambda_d"])).cpu().numpy()
+    assert_close("loss terms", terms, g["ref_losses"][:3])
+
+
+def oracle_case(B, J, method, alpha, upstream, seed):
+    rng = np.random.default_rng(seed)
+    d = synth.make_decoder_inputs(B, J, seed)
+    d["z"] = (d["z"] * 3).astype(np.float32)            # sharper softmax than N(0,1)
+    heat_gt = rng.uniform(0, 0.05, (B, J, 64, 64)).astype(np.float32)
+    dmap_gt = (rng.standard_normal((B, J, 64, 64)) * d["mask"]).astype(np.float32)
+    uvd_gt = rng.uniform(-0.5, 0.5, (B, J, 3)).astype(np.float32)
+    ups = None
+    if upstream:
+        ups = ((rng.standard_normal((B, J, 3)) * 1e-2).astype(np.float32),
+               (rng.standard_normal((B, J, 64, 64)) * 1e-3).astype(np.float32),
+               (rng.standard_normal((B, J, 64, 64)) * 1e-3).astype(np.float32))
+    return d, (heat_gt, dmap_gt, uvd_gt), ups
+
+
+@pytest.mark.parametrize("method", ["softmax", "sum"])
+@pytest.mark.parametrize("J", [14, 21])
+@pytest.mark.parametrize("alpha,upstream", [(1.0, False), (0.5, True), (1.0, True)])
+def test_forward_backward_match_fp64_oracle(method, J, alpha, upstream):
+    B = 6
+    d, tg, ups = oracle_case(B, J, method, alpha, upstream, seed=J + int(alpha * 10))
+    dd = torch.float64
+    t64 = lambda a: torch.from_numpy(a).to(dd)
+    w64 = t64(d["w"])
+    p_ref, _, uvd_ref = do.decoder_forward(t64(d["z"]), w64, t64(d["D"]), t64(d["label"]), t64(d["mask"]), method)
+    g_uvd = t64(ups[0]) if ups else torch.zeros(B, J, 3, dtype=dd)
+    gz_ref, gD_ref, gw_ref = do.decoder_backward(
+        t64(d["z"]), w64, t64(d["D"]), t64(d["label"]), t64(d["mask"]), g_uvd, t64(ups[1]) if ups else None,
+        t64(ups[2]) if ups else None, method, targets=tuple(t64(a) for a in tg), alpha=alpha)
+    losses_ref = do.stage_losses(p_ref, t64(d["D"]), uvd_ref, *[t64(a) for a in tg], 1.0, 0.01)
+
+    w = cu(d["w"]) if method == "softmax" else None
+    z, D, L, m = cu(d["z"]), cu(d["D"]), cu(d["label"]), cu(d["mask"])
+    H, uvd, stats, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
+    assert_close("heat", H.cpu().numpy(), p_ref.numpy())
+    assert_close("uvd", uvd.cpu().numpy(), uvd_ref.numpy())
+    gz, gD, gwp, lp = ops.decoder_backward_raw(
+        z, w, D, L, m, stats, uvd, cu(ups[0]) if ups else None, cu(ups[1]) if ups else None,
+        cu(ups[2]) if ups else None, method, tuple(cu(a) for a in tg), alpha, 1.0, 0.01, want_loss=True)
+    assert_close("gz", gz.cpu().numpy(), gz_ref.numpy(), GRAD_RTOL)
+    assert_close("gD", gD.cpu().numpy(), gD_ref.numpy(), GRAD_RTOL)
+    if method == "softmax":
+        assert_close("gw", ops.reduce_partials(gwp).view(-1, 1).cpu().numpy(), gw_ref.numpy(), GRAD_RTOL)
+    terms = ops.stage_loss_from_partials(lp, 1.0, 0.01).cpu().numpy()
+    assert_close("losses", terms, [x.item() for x in losses_ref])
+
+
+def test_autograd_function_matches_oracle_autograd():
+    """DecoderFunction inside an autograd graph (dense upstream on H and D, like
+    the inner stage of the model) == autograd through the float64 oracle."""
+    B, J = 4, 14
+    d, tg, ups = oracle_case(B, J, "softmax", 0.5, True, seed=5)
+    def run(dtype, dev, fused):
+        z = torch.from_numpy(d["z"]).to(dev, dtype).requires_grad_(True)
+        D = torch.from_numpy(d["D"]).to(dev, dtype).requires_grad_(True)
+        w = torch.from_numpy(d["w"]).to(dev, dtype).requires_grad_(True)
+        L, m = torch.from_numpy(d["label"]).to(dev, dtype), torch.from_numpy(d["mask"]).to(dev, dtype)
+        if fused:
+            H, Dm, uvd = ops.fused_decoder(z, w, D, L, m, "softmax")
+        else:
+            H, Dm, uvd = do.decoder_forward(z, w, D, L, m, "softmax")
+        tt = [torch.from_numpy(a).to(dev, dtype) for a in tg]
+        loss = do.combine_losses(do.stage_losses(H, Dm, uvd, *tt, 1.0, 0.01), 0.5)
+        extra = (H * torch.from_numpy(ups[1]).to(dev, dtype)).sum() + (Dm ** 2 * torch.from_numpy(ups[2]).to(dev, dtype)).sum()
+        (loss + extra).backward()
+        return [t.grad.detach().cpu().double().numpy() for t in (z, D, w)] + [loss.item()]
+    ref = run(torch.float64, "cpu", False)
+    got = run(torch.float32, DEV, True)
+    for name, a, b in zip(("gz", "gD", "gw"), got, ref):
+        assert_close(name, a, b, GRAD_RTOL)
+    assert abs(got[3] - ref[3]) <= 1e-5 * abs(ref[3])
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.4])
+def test_eager_loss_function_matches_oracle(alpha):
+    B, J = 4, 14
+    d, tg, _ = oracle_case(B, J, "softmax", alpha, False, seed=9)
+    dd = torch.float64
+    z64 = torch.from_numpy(d["z"]).to(dd).requires_grad_(True)
+    D64 = torch.from_numpy(d["D"]).to(dd).requires_grad_(True)
+    w64 = torch.from_numpy(d["w"]).to(dd).requires_grad_(True)
+    p, Dm, uvd_ref = do.decoder_forward(z64, w64, D64, torch.from_numpy(d["label"]).to(dd),
+                                        torch.from_numpy(d["mask"]).to(dd))
+    terms_ref = do.stage_losses(p, Dm, uvd_ref, *[torch.from_numpy(a).to(dd) for a in tg], 1.0, 0.01)
+    (3.0 * do.combine_losses(terms_ref, alpha)).backward()
+
+    z = cu(d["z"]).requires_grad_(True)
+    D = cu(d["D"]).requires_grad_(True)
+    w = cu(d["w"]).requires_grad_(True)
+    total, terms, uvd, H = ops.fused_decoder_loss(z, w, D, cu(d["label"]), cu(d["mask"]), *[cu(a) for a in tg],
+                                                  method="softmax", alpha=alpha)
+    (3.0 * total).backward()          # non-unit upstream exercises pwr_scale_inplace
+    assert_close("terms", terms.cpu().numpy(), [t.item() for t in terms_ref])
+    assert_close("heat", H.cpu().numpy(), p.detach().numpy())
+    assert_close("gz", z.grad.cpu().numpy(), z64.grad.numpy(), GRAD_RTOL)
+    assert_close("gD", D.grad.cpu().numpy(), D64.grad.numpy(), GRAD_RTOL)
+    assert_close("gw", w.grad.cpu().numpy(), w64.grad.numpy(), GRAD_RTOL)
+
+
+def test_inner_stage_fused_loss_matches_oracle():
+    B, J = 3, 14
+    d, tg, ups = oracle_case(B, J, "softmax", 0.5, True, seed=13)
+    dd = torch.float64
+    z64 = torch.from_numpy(d["z"]).to(dd).requires_grad_(True)
+    D64 = torch.from_numpy(d["D"]).to(dd).requires_grad_(True)
+    w64 = torch.from_numpy(d["w"]).to(dd).requires_grad_(True)
+    p, Dm, uvd_ref = do.decoder_forward(z64, w64, D64, torch.from_numpy(d["label"]).to(dd),
+                                        torch.from_numpy(d["mask"]).to(dd))
+    loss_ref = do.combine_losses(do.stage_losses(p, Dm, uvd_ref, *[torch.from_numpy(a).to(dd) for a in tg], 1.0, 0.01), 0.5)
+    (2.0 * loss_ref + (p * torch.from_numpy(ups[1]).to(dd)).sum() + (Dm * torch.from_numpy(ups[2]).to(dd)).sum()).backward()
+    z = cu(d["z"]).requires_grad_(True)
+    D = cu(d["D"]).requires_grad_(True)
+    w = cu(d["w"]).requires_grad_(True)
+    H, Dout, uvd, stage_loss, terms = ops.fused_decoder_with_loss(z, w, D, cu(d["label"]), cu(d["mask"]),
+                                                                  *[cu(a) for a in tg], alpha=0.5)
+    (2.0 * stage_loss + (H * cu(ups[1])).sum() + (Dout * cu(ups[2])).sum()).backward()
+    assert abs(stage_loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    assert_close("gz", z.grad.cpu().numpy(), z64.grad.numpy(), GRAD_RTOL)
+    assert_close("gD", D.grad.cpu().numpy(), D64.grad.numpy(), GRAD_RTOL)
+    assert_close("gw", w.grad.cpu().numpy(), w64.grad.numpy(), GRAD_RTOL)
+
+
+def test_standalone_plane_and_depth_functions():
+    B, J = 3, 5
+    d, _, _ = oracle_case(B, J, "softmax", 1.0, False, seed=3)
+    dd = torch.float64
+    z64 = torch.from_numpy(d["z"]).to(dd).requires_grad_(True)
+    w64 = torch.from_numpy(d["w"]).to(dd).requires_grad_(True)
+    p, uv = do.plane_decode(z64, w64)
+    hin64 = torch.rand(B, J, 64, 64, dtype=dd).requires_grad_(True)
+    D64 = torch.from_numpy(d["D"]).to(dd).requires_grad_(True)
+    dep = do.depth_decode(D64, hin64, torch.from_numpy(d["label"]).to(dd), torch.from_numpy(d["mask"]).to(dd))
+    ((uv ** 2).sum() + (p ** 2).sum() + (dep ** 2).sum()).backward()
+    z = cu(d["z"]).requires_grad_(True)
+    w = cu(d["w"]).requires_grad_(True)
+    H, uv_g = ops.PlaneFunction.apply(z, w, "softmax")
+    hin = hin64.detach().float().to(DEV).requires_grad_(True)
+    D = cu(d["D"]).requires_grad_(True)
+    dep_g = ops.DepthFunction.apply(D, hin, cu(d["label"]), cu(d["mask"]))
+    ((uv_g ** 2).sum() + (H ** 2).sum() + (dep_g ** 2).sum()).backward()
+    assert_close("uv", uv_g.detach().cpu().numpy(), uv.detach().numpy())
+    assert_close("dep", dep_g.detach().cpu().numpy(), dep.detach().numpy())
+    assert_close("gz", z.grad.cpu().numpy(), z64.grad.numpy(), GRAD_RTOL)
+    assert_close("gw", w.grad.cpu().numpy(), w64.grad.numpy(), GRAD_RTOL)
+    assert_close("gheat", hin.grad.cpu().numpy(), hin64.grad.numpy(), GRAD_RTOL)
+    assert_close("gD", D.grad.cpu().numpy(), D64.grad.numpy(), GRAD_RTOL)
+
+
+def test_edge_inputs():
+    """All-masked sample (den = 1e-14), negative temperature, huge logits, B=0."""
+    B, J = 2, 3
+    z = torch.randn(B, J, 64, 64, device=DEV) * 50
+    D = torch.randn(B, J, 64, 64, device=DEV)
+    w = torch.tensor([[1.0], [-0.7], [2.5]], device=DEV)
+    L = torch.rand(B, 1, 64, 64, device=DEV)
+    m = torch.zeros(B, 1, 64, 64, device=DEV)
+    m[1, :, 10:30, 10:30] = 1
+    H, uvd, stats, _ = ops.decoder_forward_raw(z, w, D, L, m)
+    p_ref, _, uvd_ref = do.decoder_forward(z.double().cpu(), w.double().cpu(), D.double().cpu(), L.double().cpu(),
+                                           m.double().cpu())
+    assert torch.isfinite(H).all() and torch.isfinite(uvd).all()
+    assert float(uvd[0, :, 2].abs().max()) == 0.0
+    assert_close("heat", H.cpu().numpy(), p_ref.numpy())
+    assert_close("uvd", uvd.cpu().numpy(), uvd_ref.numpy())
+    e = torch.empty(0, J, 64, 64, device=DEV)
+    H0, uvd0, _, _ = ops.decoder_forward_raw(e, w, e, torch.empty(0, 1, 64, 64, device=DEV),
+                                             torch.empty(0, 1, 64, 64, device=DEV))
+    assert H0.shape == (0, J, 64, 64) and uvd0.shape == (0, J, 3)
+
+
+def test_full_batch_properties():
+    """B=4096, J=14 (benchmark size): properties that need no oracle."""
+    B, J = 4096, 14
+    g = torch.Generator(device=DEV).manual_seed(0)
+    z = torch.randn(B, J, 64, 64, device=DEV, generator=g)
+    D = torch.randn(B, J, 64, 64, device=DEV, generator=g)
+    w = torch.rand(J, 1, device=DEV, generator=g) + 0.5
+    m = (torch.rand(B, 1, 64, 64, device=DEV, generator=g) < 0.4).float()
+    L = torch.rand(B, 1, 64, 64, device=DEV, generator=g) * m
+    H, uvd, stats, _ = ops.decoder_forward_raw(z, w, D, L, m)
+    assert float((H.sum(dim=(2, 3)) - 1).abs().max()) < 1e-5                 # softmax normalisation
+    assert float(uvd[:, :, :2].abs().max()) <= 0.5 + 1e-6                    # inside the U/V range
+    # shift invariance of the softmax: adding a per-map constant to z changes nothing
+    H2, uvd2, _, _ = ops.decoder_forward_raw(z + 3.0, w, D, L, m)
+    assert float((H2 - H).abs().max()) < 1e-6 * float(H.max()) + 1e-9
+    # d is a convex combination of the masked reconstruction
+    rec = (D + L) * m
+    assert bool((uvd[:, :, 2] <= rec.amax(dim=(2, 3)) + 1e-4).all() and (uvd[:, :, 2] >= rec.amin(dim=(2, 3)) - 1e-4).all())
+    # backward is linear in the upstream gradients
+    g1 = torch.randn(B, J, 3, device=DEV, generator=g)
+    g2 = torch.randn(B, J, 3, device=DEV, generator=g)
+    a = ops.decoder_backward_raw(z, w, D, L, m, stats, uvd, g1)
+    b = ops.decoder_backward_raw(z, w, D, L, m, stats, uvd, g2)
+    c = ops.decoder_backward_raw(z, w, D, L, m, stats, uvd, g1 + g2)
+    for x, y, s in zip(a[:3], b[:3], c[:3]):
+        assert float((x + y - s).abs().max()) <= 1e-5 * float(s.abs().max()) + 1e-9
+    # softmax gradient sums to zero over each map (p sums to one)
+    assert float(a[0].sum(dim=(2, 3)).abs().max()) < 1e-4 * float(a[0].abs().sum(dim=(2, 3)).max())
+    # deterministic
+    a2 = ops.decoder_backward_raw(z, w, D, L, m, stats, uvd, g1)
+    assert torch.equal(a[0], a2[0]) and torch.equal(a[1], a2[1]) and torch.equal(a[2], a2[2])
+
+
+def test_cpu_tensors_are_rejected():
+    from pixelwiseregression_b200._lib import PwrError
+    z = torch.zeros(1, 2, 64, 64)
+    with pytest.raises(PwrError):
+        ops.decoder_forward_raw(z, torch.ones(2, 1), z, torch.zeros(1, 1, 64, 64), torch.zeros(1, 1, 64, 64))

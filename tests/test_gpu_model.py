@@ -1,0 +1,143 @@
+"""GPU: the drop-in model.py — fused decoder inside the full network equals the
+reference's formulas (oracle ops on the same weights), forward and backward, and
+the fused criterion equals the train.py loss lines."""
+import copy
+
+import pytest
+import torch
+
+from oracle import decoder_oracle as do
+from pixelwiseregression_b200 import model as M
+from helpers import GRAD_RTOL, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def reference_forward(net, img, label_img, mask):
+    """PixelwiseRegression.forward with the reference's decoder formulas
+    (model.py:79-97,123-132,151) evaluated by the oracle's plain torch ops."""
+    f = net.conv(img)
+    results = []
+    for stage in net.stages:
+        f, z, d_raw = stage.features_and_logits(f)
+        plane = stage.plane_regression
+        H, D, uvd = do.decoder_forward(z, plane.temperature, d_raw, label_img, mask, plane.method)
+        results.append((H, D, uvd))
+        f = torch.cat([H, D, label_img], dim=1)
+    return results
+
+
+def train_loss(results, uvd, heatmaps, depthmaps, alpha, lambda_h, lambda_d):
+    loss = 0
+    every = []
+    for H, D, u in results:
+        terms = do.stage_losses(H, D, u, heatmaps, depthmaps, uvd, lambda_h, lambda_d)
+        every.append(terms)
+        loss = loss + do.combine_losses(terms, alpha)
+    return loss, every
+
+
+def make(method="softmax", J=14, B=4, seed=0):
+    torch.manual_seed(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    net = M.PixelwiseRegression(J, stage=2, features=32, level=1, norm_method="instance", heatmap_method=method).to(DEV)
+    if method == "softmax":
+        with torch.no_grad():
+            for s in net.stages:
+                s.plane_regression.w.uniform_(0.5, 1.5)
+    img = torch.randn(B, 1, 128, 128, device=DEV) * 0.3
+    mask = (torch.rand(B, 1, 64, 64, device=DEV) < 0.5).float()
+    label = torch.nn.functional.avg_pool2d(img, 2) * mask
+    uvd = torch.rand(B, J, 3, device=DEV) - 0.5
+    heat = torch.rand(B, J, 64, 64, device=DEV) * 0.01
+    dmap = torch.randn(B, J, 64, 64, device=DEV) * mask
+    return net, img, label, mask, uvd, heat, dmap
+
+
+@pytest.mark.parametrize("method", ["softmax", "sum"])
+@pytest.mark.parametrize("alpha", [1.0, 0.5])
+def test_dropin_forward_backward_equals_reference_formulas(method, alpha):
+    net, img, label, mask, uvd, heat, dmap = make(method)
+    ref_net = copy.deepcopy(net)
+    res = net(img, label, mask)                       # fused kernels
+    loss, _ = train_loss(res, uvd, heat, dmap, alpha, 1.0, 0.01)
+    loss.backward()
+    res_ref = reference_forward(ref_net, img, label, mask)
+    loss_ref, _ = train_loss(res_ref, uvd, heat, dmap, alpha, 1.0, 0.01)
+    loss_ref.backward()
+    for (H, D, u), (Hr, Dr, ur) in zip(res, res_ref):
+        assert_close("heat", H.detach().cpu().numpy(), Hr.detach().cpu().numpy())
+        assert_close("dmap", D.detach().cpu().numpy(), Dr.detach().cpu().numpy())
+        assert_close("uvd", u.detach().cpu().numpy(), ur.detach().cpu().numpy())
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    # parameter gradients: global relative error per tensor (conv backward runs in cuDNN for both)
+    checked = 0
+    for (n, p), (_, q) in zip(net.named_parameters(), ref_net.named_parameters()):
+        assert (p.grad is None) == (q.grad is None), n
+        if p.grad is None:
+            continue
+        scale = float(q.grad.abs().max())
+        if scale == 0:
+            assert float(p.grad.abs().max()) == 0
+            continue
+        assert float((p.grad - q.grad).abs().max()) <= 2e-3 * scale, n
+        checked += 1
+    assert checked > 50
+    if method == "softmax":
+        for s, r in zip(net.stages, ref_net.stages):
+            assert_close("gw", s.plane_regression.w.grad.cpu().numpy(), r.plane_regression.w.grad.cpu().numpy(), 1e-3)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.3])
+def test_fused_criterion_equals_train_py_loss(alpha):
+    net, img, label, mask, uvd, heat, dmap = make("softmax", seed=1)
+    ref_net = copy.deepcopy(net)
+    loss, every, uvds = net.forward_loss(img, label, mask, uvd, heat, dmap, alpha, 1.0, 0.01)
+    loss.backward()
+    res_ref = reference_forward(ref_net, img, label, mask)
+    loss_ref, every_ref = train_loss(res_ref, uvd, heat, dmap, alpha, 1.0, 0.01)
+    loss_ref.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    for t, tr in zip(every, every_ref):
+        assert_close("terms", t.cpu().numpy(), [x.item() for x in tr])
+    for u, (_, _, ur) in zip(uvds, res_ref):
+        assert_close("uvd", u.cpu().numpy(), ur.detach().cpu().numpy())
+    for (n, p), (_, q) in zip(net.named_parameters(), ref_net.named_parameters()):
+        scale = float(q.grad.abs().max())
+        if scale > 0:
+            assert float((p.grad - q.grad).abs().max()) <= 2e-3 * scale, n
+
+
+def test_inference_no_grad_and_state_dict_roundtrip():
+    net, img, label, mask, *_ = make("softmax", seed=2)
+    net.eval()
+    with torch.no_grad():
+        res = net(img, label, mask)
+        ref = reference_forward(net, img, label, mask)
+    assert_close("uvd", res[-1][2].cpu().numpy(), ref[-1][2].cpu().numpy())
+    other = M.PixelwiseRegression(14, stage=2, features=32, level=1, norm_method="instance").to(DEV)
+    other.load_state_dict(net.state_dict())
+    with torch.no_grad():
+        res2 = other.eval()(img, label, mask)
+    assert torch.equal(res2[-1][2], res[-1][2])
+
+
+def test_standalone_submodules_keep_reference_signatures():
+    torch.manual_seed(3)
+    plane = M.PlaneRegression(16, 5, 64, norm=torch.nn.InstanceNorm2d).to(DEV)
+    depth = M.DepthRegression(16, 5, norm=torch.nn.InstanceNorm2d).to(DEV)
+    f = torch.randn(2, 16, 64, 64, device=DEV)
+    mask = (torch.rand(2, 1, 64, 64, device=DEV) < 0.5).float()
+    label = torch.rand(2, 1, 64, 64, device=DEV) * mask
+    H, uv = plane(f)
+    D, d = depth(f, H, label, mask)
+    assert H.shape == (2, 5, 64, 64) and uv.shape == (2, 5, 2) and D.shape == (2, 5, 64, 64) and d.shape == (2, 5, 1)
+    Hr, uvr = do.plane_decode(plane.conv(f), plane.w)
+    dr = do.depth_decode(depth.conv(f), Hr, label, mask)
+    assert_close("uv", uv.detach().cpu().numpy(), uvr.detach().cpu().numpy())
+    assert_close("d", d.detach().cpu().numpy(), dr.detach().cpu().numpy())
+    (uv.sum() + d.sum()).backward()
+    assert plane.w.grad is not None and depth.conv[0].weight.grad is not None

@@ -1,0 +1,129 @@
+"""GPU parity: the CUDA SFR builder (through the C ABI) against the reference-
+generated golden vectors, against the NumPy oracle on seeded inputs, and through
+size-independent properties at the benchmark's full batch size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sfr_oracle as so
+from pixelwiseregression_b200 import sfr, synth
+from helpers import SFR_FIELDS, assert_close, assert_sfr_matches, golden_shape, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_SETS = ["sfr_nyu", "sfr_nyu_test_only", "sfr_hand17", "sfr_msra", "sfr_icvl", "sfr_edge"]
+
+
+def run_gpu(frames, uvd, com, cube, shape, test_only=False):
+    dev = torch.device("cuda:0")
+    out = sfr.build_sfr(torch.from_numpy(frames).to(dev), None if com is None else com, cube,
+                        None if test_only else uvd, fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64,
+                        test_only=test_only)
+    torch.cuda.synchronize()
+    d = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    if "depthmaps" in d:
+        d["dmap"] = d.pop("depthmaps")
+    return d
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_gpu_matches_reference_golden(name):
+    g = load_golden(name)
+    shape = golden_shape(g)
+    test_only = bool(g["test_only"])
+    got = run_gpu(g["frames"], g["uvd"], None if shape.com_from_frame else g["com"], g["cube"], shape, test_only)
+    names = SFR_FIELDS[:6] if test_only else SFR_FIELDS
+    ref = {n: g["ref_" + n] for n in names}
+    assert_sfr_matches(got, ref, names, g["ref_valid"], prefix=name + ":")
+
+
+@pytest.mark.parametrize("shape_name,batch,seed", [("NYU", 24, 0), ("HAND17", 8, 1), ("MSRA", 8, 2), ("ICVL", 8, 3)])
+def test_gpu_matches_oracle_seeded(shape_name, batch, seed):
+    shape = synth.SHAPES[shape_name]
+    d = synth.make_frames(shape, batch, seed)
+    frames64 = d["frames"].astype(np.float64) if shape.frame_f64 else d["frames"]
+    com = None if shape.com_from_frame else d["com"]
+    ref = so.process_batch(frames64, d["uvd"], com, d["cube"], shape.fx, shape.fy)
+    got = run_gpu(d["frames"], d["uvd"], com, d["cube"], shape)
+    assert_sfr_matches(got, ref, SFR_FIELDS, ref["valid"], prefix=shape_name + ":")
+    # same operation order as the oracle -> the image path is bit-identical, not just close
+    for n in ("img", "label_img"):
+        assert (got[n] == ref[n]).all(), "%s differs bitwise from the oracle" % n
+    assert ref["valid"].all()
+
+
+def test_gpu_test_only_matches_oracle():
+    shape = synth.NYU
+    d = synth.make_frames(shape, 8, 7)
+    ref = so.process_batch(d["frames"], None, d["com"], d["cube"], shape.fx, shape.fy, test_only=True)
+    got = run_gpu(d["frames"], None, d["com"], d["cube"], shape, test_only=True)
+    assert_sfr_matches(got, ref, SFR_FIELDS[:6], ref["valid"])
+    assert (got["img"] == ref["img"]).all()
+
+
+def test_center_of_mass_kernel_matches_oracle():
+    shape = synth.MSRA
+    d = synth.make_frames(shape, 6, 11)
+    got = sfr.center_of_mass(torch.from_numpy(d["frames"]).cuda()).cpu().numpy()
+    for b in range(6):
+        ref = so.com_from_frame(d["frames"][b].astype(np.float64))
+        assert (got[b, :2] == ref[:2]).all()                      # exact integer sums / count
+        assert abs(got[b, 2] - ref[2]) <= 1e-12 * abs(ref[2])
+
+
+def test_empty_batch_and_bad_inputs():
+    from pixelwiseregression_b200._lib import PwrError
+    shape = synth.NYU
+    out = sfr.build_sfr(torch.zeros(0, 480, 640, device="cuda"), np.zeros((0, 3)), np.zeros(0), np.zeros((0, 14, 3)),
+                        fx=shape.fx, fy=shape.fy)
+    assert out.img.shape == (0, 1, 128, 128) and out.heatmaps.shape == (0, 14, 64, 64)
+    with pytest.raises(PwrError):
+        sfr.build_sfr(torch.zeros(1, 480, 640), np.zeros((1, 3)), 150.0, np.zeros((1, 14, 3)), fx=1.0, fy=1.0)
+    with pytest.raises(PwrError):
+        sfr.build_sfr(torch.zeros(1, 480, 640, device="cuda", dtype=torch.float64), np.zeros((1, 3)), 150.0,
+                      np.zeros((1, 14, 3)), fx=1.0, fy=1.0)
+
+
+def test_nan_and_degenerate_samples_are_flagged_not_fatal():
+    shape = synth.NYU
+    d = synth.make_frames(shape, 4, 21)
+    com = d["com"].copy()
+    com[1, 2] = 0.0            # cube / 0 -> inf -> int() raises in the reference
+    com[2, 0] = np.nan
+    uvd = d["uvd"].copy()
+    uvd[3, 5, 0] = np.nan
+    got = run_gpu(d["frames"], uvd, com, d["cube"], shape)
+    assert got["valid"].tolist() == [1, 0, 0, 0]
+
+
+def test_full_batch_properties():
+    """B=4096 NYU (the benchmark configuration): properties that need no oracle."""
+    shape = synth.NYU
+    B = 4096
+    d = synth.make_frames_device(shape, B, seed=3)
+    out = sfr.build_sfr(d["frames"], d["com"], d["cube"], d["uvd"], fx=shape.fx, fy=shape.fy)
+    torch.cuda.synchronize()
+    assert bool(out.valid.all())
+    # mask == (label != 0), label == 2x2 mean of img up to one rounding
+    assert torch.equal(out.mask, (out.label_img != 0).float())
+    pooled = torch.nn.functional.avg_pool2d(out.img, 2)
+    assert float((pooled - out.label_img).abs().max()) <= 2e-7 * float(out.img.abs().max()) + 1e-9
+    assert float(out.img.abs().max()) < 1.0           # |depth - com_z| < cube
+    # heat maps: unit mass and centre of mass at the joint (all joints are interior by construction)
+    heat = out.heatmaps.double()
+    assert float((heat.sum(dim=(2, 3)) - 1).abs().max()) < 1e-6
+    xs = torch.arange(64, device="cuda", dtype=torch.float64)
+    ku = (heat.sum(dim=2) * xs).sum(dim=2)
+    kv = (heat.sum(dim=3) * xs).sum(dim=2)
+    expect_u = out.uvd[:, :, 0].double() * 63 + 32     # uvd_norm = k-space / 63 shifted by 32
+    expect_v = out.uvd[:, :, 1].double() * 63 + 32
+    assert float((ku - expect_u).abs().max()) < 1e-4 and float((kv - expect_v).abs().max()) < 1e-4
+    # Dmap support = (heat > 0) & mask, values = uvd_d - label
+    supp = (out.heatmaps > 0) & (out.mask > 0)
+    assert torch.equal(out.depthmaps != 0, supp & (out.depthmaps != 0))
+    expect = (out.uvd[:, :, 2].view(B, -1, 1, 1) - out.label_img) * supp
+    assert float((out.depthmaps - expect).abs().max()) < 1e-6
+    # idempotence / determinism: a second launch is bitwise identical
+    again = sfr.build_sfr(d["frames"], d["com"], d["cube"], d["uvd"], fx=shape.fx, fy=shape.fy)
+    for a, b in zip(out, again):
+        assert torch.equal(a, b)

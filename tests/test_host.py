@@ -1,0 +1,63 @@
+"""CPU: host-side logic that needs no GPU — drop-in module layout, synthetic
+generators, refusal of CPU tensors (no silent fallback)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pixelwiseregression_b200 import model, ops, sfr, synth
+from pixelwiseregression_b200._lib import PwrError
+from helpers import GOLDEN
+
+
+def test_state_dict_layout_equals_reference():
+    spec = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    for name, s in spec.items():
+        m = model.PixelwiseRegression(**s["kwargs"])
+        got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        assert got == s["keys"], name
+    assert len(spec["nyu_instance"]["keys"]) == 344
+
+
+def test_constructor_signatures_match_reference():
+    import inspect
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]
+    assert sig(model.PixelwiseRegression) == ["joints", "stage", "label_size", "features", "level", "kernel_size",
+                                              "norm_method", "heatmap_method"]
+    assert sig(model.PredictionBlock) == ["in_dim", "joints", "label_size", "features", "level", "kernel_size", "norm",
+                                          "heatmap_method"]
+    assert sig(model.PlaneRegression) == ["features", "joints", "label_size", "kernel_size", "norm", "inplace",
+                                          "normalization_method"]
+    assert sig(model.DepthRegression) == ["features", "joints", "kernel_size", "norm", "inplace"]
+    assert list(inspect.signature(model.PixelwiseRegression.forward).parameters)[1:] == ["img", "label_img", "mask"]
+    assert list(inspect.signature(model.DepthRegression.forward).parameters)[1:] == ["f", "heatmaps", "label_img", "mask"]
+
+
+def test_com_filter_definition():
+    f = model.com_filter(64, 64)
+    assert f.dtype == torch.float32 and f.shape == (2, 64, 64)
+    assert f[0, 3, 40].item() == np.float32((40 - 32) / 63) and f[1, 3, 40].item() == np.float32((3 - 32) / 63)
+
+
+def test_cpu_tensors_raise_instead_of_falling_back():
+    m = model.PixelwiseRegression(14, stage=1, features=32, level=1, norm_method="instance")
+    with pytest.raises(PwrError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 128, 128), torch.zeros(1, 1, 64, 64), torch.zeros(1, 1, 64, 64))
+    with pytest.raises(PwrError):
+        sfr.build_sfr(torch.zeros(1, 480, 640), np.zeros((1, 3)), 150.0, np.zeros((1, 14, 3)), fx=1.0, fy=1.0)
+    with pytest.raises(PwrError):
+        ops.reduce_partials(torch.zeros(4, 3))
+
+
+def test_synthetic_generators_are_deterministic():
+    a = synth.make_frames(synth.MSRA, 2, 5)
+    b = synth.make_frames(synth.MSRA, 2, 5)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    assert a["frames"].shape == (2, 240, 320) and a["uvd"].shape == (2, 21, 3)
+    d = synth.make_frames_device(synth.NYU, 3, 1, device="cpu")
+    assert d["frames"].shape == (3, 480, 640) and d["uvd"].dtype == torch.float64
+    frac = float((d["frames"] > 0).float().mean())
+    assert 0.01 < frac < 0.5

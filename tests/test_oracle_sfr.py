@@ -57,7 +57,10 @@ def test_blur_restatement_vs_opencv():
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(1)
     k = cv2.getGaussianKernel(7, 1.5).ravel()
-    assert np.abs(k - so.gaussian_kernel7()).max() < 1e-16
+    assert (k == so.gaussian_kernel7()).all()
+    x = np.arange(7) - 3.0
+    closed = np.exp(-x * x / (2 * 1.5 * 1.5))
+    assert np.abs(closed / closed.sum() - k).max() < 1e-16
     for _ in range(50):
         u, v = rng.uniform(-1, 62.99, 2)
         h = so.splat4(u, v)

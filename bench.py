@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — SFR + decoder micro-benchmark (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one pass of the hot path over one batch of synthetic NYU-shaped input
+(B = 4096 samples per GPU, J = 14): SFR target build from raw 480x640 depth
+frames -> fused decoder forward on N(0,1) logits -> fused backward + stage loss
+(+ the batch reduction of dL/dw and the loss sums).  With N > 1 (torchrun) every
+rank owns its own B samples (weak scaling); the only exchange is the all-reduce
+of the [J + 3] vector (dL/dw and the three loss terms) the DDP bucket would carry.
+
+Prints ONE JSON line (rank 0): whole-job samples/s with inputs resident in HBM
+(`value`), the same through host buffers with H2D/D2H inside the timed region
+(`e2e`), the dominant kernel's achieved HBM bandwidth against the measured peak
+(`roofline`), and the oracle port timed on the host cores (`cpu_baseline`).
+
+`--impl reference` times the CPU oracle port (the reference is Python; its path
+cannot travel to the GPU box) on the same workload definition.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SFR+decoder samples/s"
+UNIT = "samples/s"
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    ap.add_argument("--shape", default="NYU")
+    ap.add_argument("--alpha", type=float, default=1.0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--cpu-samples", type=int, default=256, help="samples in the bounded CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(shape, batch):
+    return ("configs[1]: decoder+SFR microbenchmark alone, %s shape (J=%d, %dx%d frames), batch %d per GPU, "
+            "SFR build + decoder fwd + fused bwd/loss" % (shape.name, shape.joints, shape.height, shape.width, batch))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML every few ms
+    while the timed region runs (the recipe's clocks line, in-process)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self.stop_flag = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[0].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                self.stop_flag.wait(self.period)
+        except Exception as exc:  # NVML missing: report it, do not fake numbers
+            self.error = repr(exc)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=5)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable: %s" % self.error]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+# --------------------------------------------------------------------------- #
+# reference arm: the CPU oracle port
+# --------------------------------------------------------------------------- #
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    from pixelwiseregression_b200 import synth
+    shape = synth.SHAPES[args.shape]
+    n = args.cpu_samples
+    cores = os.cpu_count() or 1
+    for _ in range(max(1, min(args.warmup, 1))):           # one warm-up pass (pool start-up, page-in)
+        cpu_baseline.time_path(shape, min(n, 32), seed=1)
+    t0 = time.perf_counter()
+    res = None
+    for i in range(args.steps):
+        res = cpu_baseline.time_path(shape, n, seed=i)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(shape, args.batch),
+                   "note": "each step is a bounded sample of %d samples of that workload on the host CPU" % n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- #
+# B200 arm
+# --------------------------------------------------------------------------- #
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pixelwiseregression_b200 import _lib, ops, roofline, sfr, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    shape = synth.SHAPES[args.shape]
+    B, J = args.batch, shape.joints
+    alpha, lambda_h, lambda_d = args.alpha, 1.0, 0.01
+
+    # ---- synthetic inputs, resident in HBM (seed = rank: every rank owns different samples) ----
+    d = synth.make_frames_device(shape, B, seed=rank, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    z = torch.randn(B, J, 64, 64, device=dev, generator=g).requires_grad_(True)
+    D = torch.randn(B, J, 64, 64, device=dev, generator=g).requires_grad_(True)
+    w = (torch.rand(J, 1, device=dev, generator=g) + 0.5).requires_grad_(True)
+    frames, com, cube, uvd = d["frames"], d["com"], d["cube"], d["uvd"]
+
+    def step(frames_, com_, cube_, uvd_, z_, D_):
+        """The public-API call sequence a training loop makes for this path."""
+        batch = sfr.build_sfr(frames_, com_, cube_, uvd_, fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
+        total, terms, uvd_out, _ = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, batch.heatmaps,
+                                                          batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
+                                                          lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)
+        z_.grad = D_.grad = w.grad = None
+        total.backward()
+        if world > 1:
+            # what the DDP bucket carries for this path: dL/dw [J] and the logged loss terms [3]
+            vec = torch.cat([w.grad.reshape(-1), terms])
+            dist.all_reduce(vec, op=dist.ReduceOp.AVG)
+        return total, terms, uvd_out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(frames, com, cube, uvd, z, D)
+    barrier()
+
+    # ---- timed region: K steps, device-timed, per-kernel events on the launching stream ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    _lib.PROFILE = []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    t_issue = time.perf_counter()
+    for _ in range(args.steps):
+        step(frames, com, cube, uvd, z, D)
+    issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps
+    end.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    launches = _lib.launch_count() - launches0
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    clocks = sampler.summary()
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = B * world * args.steps / (elapsed_ms * 1e-3)
+
+    kernel_ms = {}
+    for name, s, e in prof:
+        kernel_ms.setdefault(name, []).append(s.elapsed_time(e))
+    peak, peak_src = measured_peak()
+    per_launch_bytes = {"pwr_sfr_build": roofline.sfr_build_bytes(J) * B,
+                        "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J) * B,
+                        "pwr_decoder_bwd_loss": roofline.decoder_bwd_bytes(J) * B}
+    kernels = {}
+    for name, ms in kernel_ms.items():
+        avg = sum(ms) / len(ms)
+        gbs = per_launch_bytes[name] / (avg * 1e-3) / 1e9
+        kernels[name] = {"avg_ms": avg, "launches": len(ms), "algorithmic_bytes": per_launch_bytes[name],
+                         "achieved_gbs": gbs, "frac": gbs / peak}
+    dominant = max(kernels, key=lambda k: kernels[k]["avg_ms"])
+    step_kernel_ms = sum(k["avg_ms"] for k in kernels.values())
+
+    # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in
+                dict(frames=frames, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach()).items()}
+        for k, v in dict(frames=frames, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach()).items():
+            host[k].copy_(v)
+        out_host = {"loss": torch.empty(4, pin_memory=True), "uvd": torch.empty(B, J, 3, pin_memory=True)}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+
+        def e2e_step():
+            for k in host:
+                dev_in[k].copy_(host[k], non_blocking=True)
+            z_ = dev_in["z"].requires_grad_(True)
+            D_ = dev_in["D"].requires_grad_(True)
+            total, terms, uvd_out = step(dev_in["frames"], dev_in["com"], dev_in["cube"], dev_in["uvd"], z_, D_)
+            out_host["loss"].copy_(torch.cat([total.detach().reshape(1), terms]), non_blocking=True)
+            out_host["uvd"].copy_(uvd_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dev_in["z"].requires_grad_(False)
+            dev_in["D"].requires_grad_(False)
+
+        n_e2e = args.e2e_steps or min(args.steps, 10)
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e,
+               "note": "per rank and step: frames+com+cube+uvd+z+D copied from pinned host memory, "
+                       "loss[4]+uvd[B,J,3] read back; wall clock with device sync, max over ranks"}
+
+    # ---- CPU baseline: oracle port on the host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        cpu_baseline.time_path(shape, 32, seed=1)                       # warm-up (pool start, page-in)
+        res = cpu_baseline.time_path(shape, args.cpu_samples, seed=0, repeats=2)
+        cpu = {"value": res["samples_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+               "sample": res["sample"] + "; best of 2 passes"}
+
+    if rank == 0:
+        dk = kernels[dominant]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(shape, B), "batch_per_gpu": B, "joints": J,
+                       "alpha": alpha, "lambda_h": lambda_h, "lambda_d": lambda_d,
+                       "l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
+                             % (frames.numel() * 4 / 1e9, z.numel() * 4 / 1e9),
+                       "algorithmic_bytes_per_sample": roofline.step_bytes(J)},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,
+                         "avg_launch_ms": dk["avg_ms"], "algorithmic_bytes_per_launch": dk["algorithmic_bytes"],
+                         "share_of_step": dk["avg_ms"] / step_kernel_ms if step_kernel_ms else None},
+            "kernels": kernels,
+            "step_roofline_frac": (roofline.step_bytes(J) * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
+            "host_issue_ms_per_step": issue_ms,
+            "cpu_baseline": cpu,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    tr = json.load(f)
+                line["roofline"]["traffic"] = tr.get(dominant, {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,10 +61,40 @@ def load():
     return lib
 
 
+LAUNCHES = {}          # entry point -> number of successful launches (one kernel each)
+PROFILE = None         # when a list: (entry point, start event, end event) per launch
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().pwr_error_string(rc)
         raise PwrError("%s failed: rc=%d (%s)" % (what, rc, msg.decode() if msg else "?"))
+    LAUNCHES[what] = LAUNCHES.get(what, 0) + 1
+
+
+def launch_count():
+    return sum(LAUNCHES.values())
+
+
+class timed:
+    """Brackets one launch with CUDA events on the current stream when profiling
+    is switched on (bench.py); free otherwise."""
+
+    def __init__(self, what):
+        self.what = what
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.end.record()
+            PROFILE.append((self.what, self.start, self.end))
+        return False
 
 
 def ptr(t):

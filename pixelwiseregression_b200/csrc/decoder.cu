@@ -367,6 +367,7 @@ extern "C" int pwr_decoder_fwd(const float* z, const float* w, const float* D, c
                                int B, int J, int method, void* stream) {
     if (bad_method(method)) return PWR_E_METHOD;
     if (int rc = check_bj(B, J)) return rc;
+    if (B == 0) return 0;
     PWR_REQUIRE_PTR(z);
     if (uvd == nullptr) return PWR_E_NULL;
     PWR_OPTIONAL_PTR(D); PWR_OPTIONAL_PTR(H); PWR_OPTIONAL_PTR(stats);
@@ -377,7 +378,6 @@ extern "C" int pwr_decoder_fwd(const float* z, const float* w, const float* D, c
         PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt);
         if (uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
-    if (B == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define PWR_LAUNCH_FWD(M, LS)                                                                               \
     decoder_fwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, H, uvd, stats, \
@@ -396,6 +396,7 @@ static int launch_bwd(bool loss, const float* z, const float* w, const float* D,
                       int method, void* stream) {
     if (bad_method(method)) return PWR_E_METHOD;
     if (int rc = check_bj(B, J)) return rc;
+    if (B == 0) return 0;
     PWR_REQUIRE_PTR(z); PWR_REQUIRE_PTR(stats);
     PWR_OPTIONAL_PTR(D); PWR_OPTIONAL_PTR(gz); PWR_OPTIONAL_PTR(gD); PWR_OPTIONAL_PTR(gH_up); PWR_OPTIONAL_PTR(gD_up);
     if (D != nullptr) { PWR_REQUIRE_PTR(L); PWR_REQUIRE_PTR(m); }
@@ -405,7 +406,6 @@ static int launch_bwd(bool loss, const float* z, const float* w, const float* D,
         PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt);
         if (uvd == nullptr || uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
-    if (B == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define PWR_LAUNCH_BWD(M, LS)                                                                              \
     decoder_bwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up,    \
@@ -445,7 +445,7 @@ extern "C" int pwr_decoder_bwd_loss(const float* z, const float* w, const float*
 }
 
 extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, int C, void* stream) {
-    if (in == nullptr || out == nullptr) return PWR_E_NULL;
+    if (out == nullptr || (in == nullptr && B != 0)) return PWR_E_NULL;
     if (B < 0 || J < 1 || C < 1 || J * C > 65535) return PWR_E_SHAPE;
     reduce_partials_kernel<<<J * C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, J, C);
     return launch_status();

@@ -453,8 +453,8 @@ using namespace pwr;
 
 extern "C" int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com, int B, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
-    if (frames == nullptr || com == nullptr) return PWR_E_NULL;
     if (B == 0) return 0;
+    if (frames == nullptr || com == nullptr) return PWR_E_NULL;
     sfr_com_kernel<<<B, kComThreads, 0, static_cast<cudaStream_t>(stream)>>>(frames, Hf, Wf, com);
     return launch_status();
 }
@@ -463,11 +463,11 @@ extern "C" int pwr_sfr_crop(const float* frames, int Hf, int Wf, const double* c
                             double fy, int frame_f64, float* img, float* label_img, float* mask, float* box_size,
                             float* cube_size, float* com_out, uint8_t* valid, int B, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (B == 0) return 0;
     if (frames == nullptr || com == nullptr || cube == nullptr || box_size == nullptr || cube_size == nullptr ||
         com_out == nullptr || valid == nullptr)
         return PWR_E_NULL;
     PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
-    if (B == 0) return 0;
     SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  nullptr, nullptr, nullptr, valid, B, 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -479,13 +479,13 @@ extern "C" int pwr_sfr_build(const float* frames, int Hf, int Wf, const double* 
                              float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
                              float* heatmaps, float* dmap, uint8_t* valid, int B, int J, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (B == 0) return 0;
     if (J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
     if (frames == nullptr || com == nullptr || cube == nullptr || uvd == nullptr || box_size == nullptr ||
         cube_size == nullptr || com_out == nullptr || uvd_norm == nullptr || valid == nullptr)
         return PWR_E_NULL;
     PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
     PWR_REQUIRE_PTR(heatmaps); PWR_REQUIRE_PTR(dmap);
-    if (B == 0) return 0;
     SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  uvd_norm, heatmaps, dmap, valid, B, J};
     cudaStream_t s = static_cast<cudaStream_t>(stream);

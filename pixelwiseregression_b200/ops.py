@@ -46,7 +46,7 @@ def decoder_forward_raw(z, w, D, label_img, mask, method="softmax", store_heat=T
     if targets is not None:
         heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
         loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
-    with torch.cuda.device(z.device):
+    with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd"):
         rc = lib.pwr_decoder_fwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
                                  ptr(uvd_gt), ptr(H), ptr(uvd), ptr(stats), ptr(loss_partial), B, J,
                                  METHODS[method], stream_ptr(z.device))
@@ -73,7 +73,7 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
     gH_up = as_f32(gH_up)
     gD_up = as_f32(gD_up)
     s = stream_ptr(z.device)
-    with torch.cuda.device(z.device):
+    with torch.cuda.device(z.device), _lib.timed("pwr_decoder_bwd" if targets is None else "pwr_decoder_bwd_loss"):
         if targets is None:
             rc = lib.pwr_decoder_bwd(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
                                      ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(gz), ptr(gD),
@@ -115,14 +115,26 @@ def scale_inplace_(x, scale):
     return x
 
 
+_SCALE_CACHE = {}
+
+
+def _loss_scale_tensor(lambda_h, lambda_d, n, device):
+    """[lambda_h/n, lambda_d/n, 1/n] on the device, cached (no per-step H2D copy)."""
+    key = (float(lambda_h), float(lambda_d), float(n), str(device))
+    t = _SCALE_CACHE.get(key)
+    if t is None:
+        t = torch.tensor([lambda_h / n, lambda_d / n, 1.0 / n], dtype=torch.float32).to(device)
+        _SCALE_CACHE[key] = t
+    return t
+
+
 def stage_loss_from_partials(loss_partial, lambda_h, lambda_d, n_mean=None):
     """train.py:197-199 from per-(b,j) sums of squares: returns a [3] tensor
     (heatmap_loss, depthmap_loss, uvd_loss)."""
     B, J = loss_partial.shape[0], loss_partial.shape[1]
     n = float(n_mean if n_mean else B * J)
     sums = reduce_partials(loss_partial).sum(dim=0)          # [3]
-    scale = torch.tensor([lambda_h / n, lambda_d / n, 1.0 / n], device=sums.device, dtype=torch.float32)
-    return sums * scale
+    return sums * _loss_scale_tensor(lambda_h, lambda_d, n, sums.device)
 
 
 class DecoderFunction(torch.autograd.Function):

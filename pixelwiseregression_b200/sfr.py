@@ -73,24 +73,25 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     com_out = torch.empty(B, 3, **f32)
     valid = torch.empty(B, device=dev, dtype=torch.uint8)
     s = stream_ptr(dev)
-    with torch.cuda.device(dev):
-        if test_only:
+    if test_only:
+        with torch.cuda.device(dev), _lib.timed("pwr_sfr_crop"):
             rc = lib.pwr_sfr_crop(ptr(frames), Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
                                   ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
                                   ptr(valid), B, s)
-            check(rc, "pwr_sfr_crop")
-            return SFRTestBatch(img, label_img, mask, box_size, cube_size, com_out, valid)
-        if uvd is None:
-            raise _lib.PwrError("train-mode SFR needs joint annotations (uvd)")
-        uvd = _f64(uvd, dev)
-        if uvd.dim() != 3 or uvd.shape[0] != B or uvd.shape[2] != 3:
-            raise _lib.PwrError("uvd must be [B, J, 3]")
-        J = uvd.shape[1]
-        uvd_norm = torch.empty(B, J, 3, **f32)
-        heatmaps = torch.empty(B, J, 64, 64, **f32)
-        dmap = torch.empty(B, J, 64, 64, **f32)
+        check(rc, "pwr_sfr_crop")
+        return SFRTestBatch(img, label_img, mask, box_size, cube_size, com_out, valid)
+    if uvd is None:
+        raise _lib.PwrError("train-mode SFR needs joint annotations (uvd)")
+    uvd = _f64(uvd, dev)
+    if uvd.dim() != 3 or uvd.shape[0] != B or uvd.shape[2] != 3:
+        raise _lib.PwrError("uvd must be [B, J, 3]")
+    J = uvd.shape[1]
+    uvd_norm = torch.empty(B, J, 3, **f32)
+    heatmaps = torch.empty(B, J, 64, 64, **f32)
+    dmap = torch.empty(B, J, 64, 64, **f32)
+    with torch.cuda.device(dev), _lib.timed("pwr_sfr_build"):
         rc = lib.pwr_sfr_build(ptr(frames), Hf, Wf, ptr(com), ptr(cube), ptr(uvd), float(fx), float(fy),
                                int(frame_f64), ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
                                ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), B, J, s)
-        check(rc, "pwr_sfr_build")
+    check(rc, "pwr_sfr_build")
     return SFRBatch(img, label_img, mask, box_size, cube_size, com_out, uvd_norm, heatmaps, dmap, valid)

@@ -75,14 +75,14 @@ def test_dropin_forward_backward_equals_reference_formulas(method, alpha):
     assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
     # parameter gradients: global relative error per tensor (conv backward runs in cuDNN for both)
     checked = 0
+    # biases feeding an InstanceNorm have an exactly-zero true gradient (pure rounding
+    # noise in both paths), so errors are judged against the network-wide gradient scale too
+    floor = 1e-4 * max(float(q.grad.abs().max()) for q in ref_net.parameters() if q.grad is not None)
     for (n, p), (_, q) in zip(net.named_parameters(), ref_net.named_parameters()):
         assert (p.grad is None) == (q.grad is None), n
         if p.grad is None:
             continue
-        scale = float(q.grad.abs().max())
-        if scale == 0:
-            assert float(p.grad.abs().max()) == 0
-            continue
+        scale = max(float(q.grad.abs().max()), floor)
         assert float((p.grad - q.grad).abs().max()) <= 2e-3 * scale, n
         checked += 1
     assert checked > 50
@@ -105,10 +105,10 @@ def test_fused_criterion_equals_train_py_loss(alpha):
         assert_close("terms", t.cpu().numpy(), [x.item() for x in tr])
     for u, (_, _, ur) in zip(uvds, res_ref):
         assert_close("uvd", u.cpu().numpy(), ur.detach().cpu().numpy())
+    floor = 1e-4 * max(float(q.grad.abs().max()) for q in ref_net.parameters() if q.grad is not None)
     for (n, p), (_, q) in zip(net.named_parameters(), ref_net.named_parameters()):
-        scale = float(q.grad.abs().max())
-        if scale > 0:
-            assert float((p.grad - q.grad).abs().max()) <= 2e-3 * scale, n
+        scale = max(float(q.grad.abs().max()), floor)
+        assert float((p.grad - q.grad).abs().max()) <= 2e-3 * scale, n
 
 
 def test_inference_no_grad_and_state_dict_roundtrip():

@@ -18,6 +18,7 @@
 // coordinate filter of utils.py:24-35 (U = (x-32)/63, V = (y-32)/63) is
 // synthesised from the indices: sums are taken over the integer offsets
 // (x-32), (y-32) and scaled by 1/63 once.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace pwr {
@@ -62,11 +63,19 @@ __device__ __forceinline__ float block_extremum(const float4 (&zv)[kVec], bool w
     return r;
 }
 
+// MUFU.EX2: 2 ulp, results below 2^-126 flush to zero (irrelevant after the
+// 1/sum normalisation: such pixels are < 1e-38 of the map's mass).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Un-normalised heat value: 2^(c*z - off) for softmax, relu(z)+1e-14 for sum,
 // z itself when the caller hands in an already normalised heat map.
 template <int METHOD>
 __device__ __forceinline__ float heat_raw(float z, float c, float off) {
-    if (METHOD == PWR_METHOD_SOFTMAX) return exp2f(fmaf(z, c, -off));
+    if (METHOD == PWR_METHOD_SOFTMAX) return ex2_approx(fmaf(z, c, -off));
     if (METHOD == PWR_METHOD_GIVEN) return z;
     return fmaxf(z, 0.f) + kEps;
 }
@@ -302,6 +311,260 @@ decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, con
 }
 
 // ---------------------------------------------------------------------------
+// backward, persistent + TMA-pipelined variant (the hot configurations)
+// ---------------------------------------------------------------------------
+// The direct-load kernel above keeps three 16-float arrays live across a block
+// reduction (104 registers -> 2 CTAs/SM) and only has a few 128-bit loads in
+// flight per thread, so it is latency- rather than bandwidth-bound (ncu r1:
+// 55 % DRAM, 45 % of stall samples on the first use of a loaded value).  Here
+// one CTA per SM stays resident and walks a contiguous range of (b,j) items;
+// a single elected thread streams the next item's maps into a shared-memory
+// ring with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx) while
+// all 512 threads compute the current item out of shared memory.  Bytes in
+// flight no longer depend on registers or occupancy: a whole 64 KB stage per
+// SM is always outstanding.  L and m are fetched once per sample, not once per
+// (sample, joint).
+//
+// A stage has four 16 KB slots: z, D and two optional maps whose meaning the
+// host picks: (heat_gt, dmap_gt) for the fused loss, or (gH_up, gD_up) for
+// dense upstream gradients.  Configurations that need both pairs at once go
+// through the direct-load kernel.
+constexpr int kPipeThreads = 512;
+constexpr int kPipeWarps = kPipeThreads / 32;
+constexpr int kPipeVec = kMap / 4 / kPipeThreads;     // float4 chunks per thread per map = 2
+constexpr int kPipeStages = 2;
+constexpr int kSlotBytes = kMap * 4;                  // 16 KB
+constexpr int kPipeSmemBytes = kPipeStages * 4 * kSlotBytes + 2 * 2 * kSlotBytes + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk TMA copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void pipe_block_sum(float (&v)[N], float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) scratch[warp * N + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kPipeWarps; ++wv) s += scratch[wv * N + i];
+        v[i] = s;
+    }
+    __syncthreads();
+}
+
+struct PipeArgs {
+    const float* z; const float* w; const float* D; const float* L; const float* m;
+    const float* stats; const float* uvd; const float* g_uvd;
+    const float* slot2; const float* slot3;    // (heat_gt, dmap_gt) or (gH_up, gD_up); either may be NULL
+    const float* uvd_gt;
+    LossCoef coef;
+    float* gz; float* gD; float* gw_partial; float* loss_partial;
+    int J; int items;
+    int slots_are_targets;                     // 1: slot2/3 = heat_gt/dmap_gt, 0: = gH_up/gD_up
+};
+
+template <int METHOD, bool LOSS>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+decoder_bwd_pipe_kernel(PipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_base = reinterpret_cast<float*>(smem_raw);                               // [stages][4][4096]
+    float* lm_base = stage_base + kPipeStages * 4 * kMap;                                 // [2][2][4096]
+    uint64_t* full = reinterpret_cast<uint64_t*>(lm_base + 2 * 2 * kMap);                 // [stages]
+    __shared__ float scratch[kPipeWarps * 3];
+
+    const int tid = threadIdx.x;
+    const long long first = static_cast<long long>(a.items) * blockIdx.x / gridDim.x;
+    const long long last = static_cast<long long>(a.items) * (blockIdx.x + 1) / gridDim.x;
+    if (first >= last) return;
+
+    if (LOSS && a.coef.scale_dev != nullptr) {
+        const float up = *a.coef.scale_dev;
+        a.coef.cu *= up; a.coef.ch *= up; a.coef.cd *= up;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kPipeStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const bool has2 = a.slot2 != nullptr, has3 = a.slot3 != nullptr;
+    const uint32_t stage_tx = (2 + (has2 ? 1 : 0) + (has3 ? 1 : 0)) * kSlotBytes;
+
+    // producer (thread 0): stream item `it` into stage `s`; fetch L, m when the sample changes
+    auto issue = [&](long long it, int s, int prev_b, int lm_buf) {
+        const int b = static_cast<int>(it / a.J);
+        const size_t off = static_cast<size_t>(it) * kMap;
+        float* st = stage_base + s * 4 * kMap;
+        const bool new_lm = (b != prev_b);
+        mbar_expect_tx(&full[s], stage_tx + (new_lm ? 2 * kSlotBytes : 0));
+        bulk_g2s(st, a.z + off, kSlotBytes, &full[s]);
+        bulk_g2s(st + kMap, a.D + off, kSlotBytes, &full[s]);
+        if (has2) bulk_g2s(st + 2 * kMap, a.slot2 + off, kSlotBytes, &full[s]);
+        if (has3) bulk_g2s(st + 3 * kMap, a.slot3 + off, kSlotBytes, &full[s]);
+        if (new_lm) {
+            float* lm = lm_base + lm_buf * 2 * kMap;
+            bulk_g2s(lm, a.L + static_cast<size_t>(b) * kMap, kSlotBytes, &full[s]);
+            bulk_g2s(lm + kMap, a.m + static_cast<size_t>(b) * kMap, kSlotBytes, &full[s]);
+        }
+    };
+
+    // lm_cur: buffer holding the current item's L/m; toggles whenever the sample changes
+    int lm_cur = 0;
+    int b_cur = static_cast<int>(first / a.J);
+    if (tid == 0) issue(first, 0, -1, 0);
+
+    const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
+    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + 32*i
+
+    int k = 0;
+    for (long long it = first; it < last; ++it, ++k) {
+        const int s = k % kPipeStages;
+        const uint32_t parity = (k / kPipeStages) & 1;
+        // prefetch the next item into the other stage (its readers finished before the barrier
+        // that ended the previous iteration)
+        const long long nxt = it + 1;
+        const int b_next = nxt < last ? static_cast<int>(nxt / a.J) : b_cur;
+        const int lm_next = (b_next != b_cur) ? (lm_cur ^ 1) : lm_cur;
+        if (tid == 0 && nxt < last) issue(nxt, (k + 1) % kPipeStages, b_cur, lm_next);
+
+        const int bj = static_cast<int>(it);
+        const int j = bj - b_cur * a.J;
+        const float4 st = reinterpret_cast<const float4*>(a.stats)[bj];   // (shift, 1/sum, den, d)
+        const float wj = (METHOD == PWR_METHOD_SOFTMAX) ? a.w[j] : 1.f;
+        const float c = wj * kLog2e;
+        float gu = 0.f, gvv = 0.f, gd = 0.f, lu = 0.f;
+        if (a.g_uvd != nullptr) { gu = a.g_uvd[bj * 3 + 0]; gvv = a.g_uvd[bj * 3 + 1]; gd = a.g_uvd[bj * 3 + 2]; }
+        if (LOSS) {
+            const float eu = a.uvd[bj * 3 + 0] - a.uvd_gt[bj * 3 + 0];
+            const float ev = a.uvd[bj * 3 + 1] - a.uvd_gt[bj * 3 + 1];
+            const float ed = a.uvd[bj * 3 + 2] - a.uvd_gt[bj * 3 + 2];
+            gu = fmaf(a.coef.cu, eu, gu); gvv = fmaf(a.coef.cu, ev, gvv); gd = fmaf(a.coef.cu, ed, gd);
+            lu = eu * eu + ev * ev + ed * ed;
+        }
+        const float gu63 = gu / 63.f, gv63 = gvv / 63.f;
+        const float gdd = gd / st.z;
+        const float dcoord = st.w;
+
+        const float4* sz = reinterpret_cast<const float4*>(stage_base + s * 4 * kMap);
+        const float4* sD = sz + kMap / 4;
+        const float4* s2 = sz + 2 * (kMap / 4);
+        const float4* s3 = sz + 3 * (kMap / 4);
+        const float4* sL = reinterpret_cast<const float4*>(lm_base + lm_cur * 2 * kMap);
+        const float4* sM = sL + kMap / 4;
+
+        mbar_wait(&full[s], parity);
+
+        const bool tg = a.slots_are_targets != 0;
+        float4 pv[kPipeVec], gv[kPipeVec];
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < kPipeVec; ++i) {
+            const int cidx = tid + i * kPipeThreads;
+            const float4 z4 = sz[cidx], d4 = sD[cidx], l4 = sL[cidx], m4 = sM[cidx];
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 q2 = has2 ? s2[cidx] : zero4;
+            const float4 q3 = has3 ? s3[cidx] : zero4;
+            const float gyrow = gv63 * (ys0 + 32.f * i);
+            float4 gd4;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float p = heat_raw<METHOD>(comp(z4, kk), c, st.x) * st.y;
+                const float mk = comp(m4, kk), dk = comp(d4, kk);
+                const float rec = mk * (dk + comp(l4, kk));
+                float gp = fmaf(gu63, xs + static_cast<float>(kk), gyrow);
+                gp = fmaf(gdd * mk, rec - dcoord, gp);
+                float gdk = gdd * p * mk * mk;
+                if (LOSS && tg) {
+                    const float eh = has2 ? p - comp(q2, kk) : 0.f;
+                    const float ed = has3 ? dk - comp(q3, kk) : 0.f;
+                    gp = fmaf(a.coef.ch, eh, gp);
+                    gdk = fmaf(a.coef.cd, ed, gdk);
+                    acc[1] = fmaf(eh, eh, acc[1]);
+                    acc[2] = fmaf(ed, ed, acc[2]);
+                }
+                if (!tg) { gp += comp(q2, kk); gdk += comp(q3, kk); }
+                acc[0] = fmaf(gp, p, acc[0]);
+                set_comp(pv[i], kk, p);
+                set_comp(gv[i], kk, gp);
+                set_comp(gd4, kk, gdk);
+            }
+            if (a.gD != nullptr) st_stream(a.gD + static_cast<size_t>(bj) * kMap + cidx * 4, gd4);
+        }
+        if (METHOD != PWR_METHOD_GIVEN || LOSS) pipe_block_sum<3>(acc, scratch);
+
+        const float s1 = acc[0];
+        float sw[1] = {0.f};
+        if (a.gz != nullptr) {
+#pragma unroll
+            for (int i = 0; i < kPipeVec; ++i) {
+                const int cidx = tid + i * kPipeThreads;
+                const float4 z4 = sz[cidx];
+                float4 g4;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float zk = comp(z4, kk);
+                    float g;
+                    if (METHOD == PWR_METHOD_SOFTMAX) {
+                        const float gy = comp(pv[i], kk) * (comp(gv[i], kk) - s1);
+                        sw[0] = fmaf(gy, zk, sw[0]);
+                        g = wj * gy;
+                    } else if (METHOD == PWR_METHOD_SUM) {
+                        g = zk > 0.f ? (comp(gv[i], kk) - s1) * st.y : 0.f;
+                    } else {
+                        g = comp(gv[i], kk);
+                    }
+                    set_comp(g4, kk, g);
+                }
+                st_stream(a.gz + static_cast<size_t>(bj) * kMap + cidx * 4, g4);
+            }
+        }
+        if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr) {
+            pipe_block_sum<1>(sw, scratch);
+            if (tid == 0) a.gw_partial[bj] = sw[0];
+        }
+        if (LOSS && a.loss_partial != nullptr && tid == 0) {
+            a.loss_partial[bj * 3 + 0] = acc[1];
+            a.loss_partial[bj * 3 + 1] = acc[2];
+            a.loss_partial[bj * 3 + 2] = lu;
+        }
+        // every thread is done with stage s and (if the sample changes) with the old L/m buffer
+        __syncthreads();
+        b_cur = b_next;
+        lm_cur = lm_next;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // small helpers: batch reduction of per-(b,j) partials, scaling, recover_uvd
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -352,6 +615,11 @@ static int check_bj(int B, int J) {
     if (B < 0 || J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
     if (static_cast<long long>(B) * J > 0x7fffffffLL / 4) return PWR_E_SHAPE;
     return 0;
+}
+// PWR_BWD_DIRECT=1 forces the direct-load backward (A/B measurements, tests of both paths).
+static bool force_direct_bwd() {
+    const char* e = getenv("PWR_BWD_DIRECT");
+    return e != nullptr && e[0] == '1';
 }
 static bool bad_method(int method) {
     return method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM && method != PWR_METHOD_GIVEN;
@@ -407,6 +675,34 @@ static int launch_bwd(bool loss, const float* z, const float* w, const float* D,
         if (uvd == nullptr || uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // Hot configurations -> persistent TMA-pipelined kernel: depth branch present, and at most one
+    // pair of extra maps (targets XOR dense upstream gradients).
+    const bool need_targets = loss && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
+    const bool need_up = gH_up != nullptr || gD_up != nullptr;
+    if (D != nullptr && !(need_targets && need_up) && !force_direct_bwd()) {
+        PipeArgs a;
+        a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.stats = stats; a.uvd = uvd; a.g_uvd = g_uvd;
+        a.slot2 = need_targets ? heat_gt : gH_up;
+        a.slot3 = need_targets ? dmap_gt : gD_up;
+        a.uvd_gt = uvd_gt; a.coef = coef; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial;
+        a.loss_partial = loss_partial; a.J = J; a.items = B * J;
+        a.slots_are_targets = need_targets ? 1 : 0;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = a.items < sms ? a.items : sms;
+#define PWR_LAUNCH_PIPE(M, LS)                                                                             \
+    do {                                                                                                   \
+        cudaFuncSetAttribute(decoder_bwd_pipe_kernel<M, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             kPipeSmemBytes);                                                              \
+        decoder_bwd_pipe_kernel<M, LS><<<grid, kPipeThreads, kPipeSmemBytes, s>>>(a);                      \
+    } while (0)
+        if (method == PWR_METHOD_SOFTMAX)  { if (loss) PWR_LAUNCH_PIPE(PWR_METHOD_SOFTMAX, true); else PWR_LAUNCH_PIPE(PWR_METHOD_SOFTMAX, false); }
+        else if (method == PWR_METHOD_SUM) { if (loss) PWR_LAUNCH_PIPE(PWR_METHOD_SUM, true);     else PWR_LAUNCH_PIPE(PWR_METHOD_SUM, false); }
+        else                               { if (loss) PWR_LAUNCH_PIPE(PWR_METHOD_GIVEN, true);   else PWR_LAUNCH_PIPE(PWR_METHOD_GIVEN, false); }
+#undef PWR_LAUNCH_PIPE
+        return launch_status();
+    }
 #define PWR_LAUNCH_BWD(M, LS)                                                                              \
     decoder_bwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up,    \
                                                          heat_gt, dmap_gt, uvd_gt, coef, gz, gD, gw_partial, \

@@ -178,6 +178,15 @@ template <> struct Arith<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float rcp(float b) { return __frcp_rn(b); }
+    // a / b, correctly rounded, from rb = RN(1/b): q = RN(a*rb) is within 1 ulp, the FMA residual is
+    // exact, and one correction step lands on RN(a/b) (Markstein).  |a| < cube-ish and b = cube, so no
+    // overflow / denormal corner can occur; NaN propagates like the true division.
+    static __device__ __forceinline__ float div_by(float a, float b, float rb) {
+        const float q = __fmul_rn(a, rb);
+        const float r = __fmaf_rn(-q, b, a);
+        return __fmaf_rn(r, rb, q);
+    }
     // window + centring of one frame pixel, datasets.py:312,315
     static __device__ __forceinline__ float window(float v, const SampleGeom& g) {
         const float keep = (v > g.lo_dn && v < g.hi_up) ? 1.f : 0.f;   // == float64 compare, see SampleGeom
@@ -190,6 +199,8 @@ template <> struct Arith<double> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double rcp(double b) { return b; }
+    static __device__ __forceinline__ double div_by(double a, double b, double) { return __ddiv_rn(a, b); }
     static __device__ __forceinline__ double window(double v, const SampleGeom& g) {
         const double keep = (v > g.lo && v < g.hi) ? 1.0 : 0.0;
         v = __dmul_rn(v, keep);
@@ -256,6 +267,7 @@ sfr_build_kernel(SfrArgs a) {
     float* msk_b = a.mask + static_cast<size_t>(b) * kMap;
     const float* frame = a.frames + static_cast<size_t>(b) * a.Hf * a.Wf;
     const T cube_t = static_cast<T>(g.cube);
+    const T cube_r = Arith<T>::rcp(cube_t);
     int my_count = 0, my_nan = 0;
 #pragma unroll 1
     for (int it = 0; it < kLabelIters; ++it) {
@@ -271,15 +283,16 @@ sfr_build_kernel(SfrArgs a) {
                 const TapX ty = ytap[2 * lrow + dy];
                 const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
                 const bool ra = fr_a >= 0 && fr_a < a.Hf, rb = fr_b >= 0 && fr_b < a.Hf;
+                const int row_a = fr_a * a.Wf, row_b = fr_b * a.Wf;      // Hf*Wf < 2^31 (checked on the host)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const TapX tx = xtap[2 * lx + dx];
                     const int fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
                     const bool ca = fc_a >= 0 && fc_a < a.Wf, cb = fc_b >= 0 && fc_b < a.Wf;
-                    const float v00 = (ra && ca) ? __ldg(frame + static_cast<size_t>(fr_a) * a.Wf + fc_a) : 0.f;
-                    const float v01 = (ra && cb) ? __ldg(frame + static_cast<size_t>(fr_a) * a.Wf + fc_b) : 0.f;
-                    const float v10 = (rb && ca) ? __ldg(frame + static_cast<size_t>(fr_b) * a.Wf + fc_a) : 0.f;
-                    const float v11 = (rb && cb) ? __ldg(frame + static_cast<size_t>(fr_b) * a.Wf + fc_b) : 0.f;
+                    const float v00 = (ra && ca) ? __ldg(frame + (row_a + fc_a)) : 0.f;
+                    const float v01 = (ra && cb) ? __ldg(frame + (row_a + fc_b)) : 0.f;
+                    const float v10 = (rb && ca) ? __ldg(frame + (row_b + fc_a)) : 0.f;
+                    const float v11 = (rb && cb) ? __ldg(frame + (row_b + fc_b)) : 0.f;
                     const T w00 = Arith<T>::window(static_cast<T>(v00), g);
                     const T w01 = Arith<T>::window(static_cast<T>(v01), g);
                     const T w10 = Arith<T>::window(static_cast<T>(v10), g);
@@ -294,12 +307,12 @@ sfr_build_kernel(SfrArgs a) {
             // 2x2 mean (cv::resize reroutes an exact 2x INTER_LINEAR shrink to the area path)
             lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
                                 T(0.25));
-            o0 = make_float2(static_cast<float>(Arith<T>::div(px[0][0], cube_t)),
-                             static_cast<float>(Arith<T>::div(px[0][1], cube_t)));
-            o1 = make_float2(static_cast<float>(Arith<T>::div(px[1][0], cube_t)),
-                             static_cast<float>(Arith<T>::div(px[1][1], cube_t)));
+            o0 = make_float2(static_cast<float>(Arith<T>::div_by(px[0][0], cube_t, cube_r)),
+                             static_cast<float>(Arith<T>::div_by(px[0][1], cube_t, cube_r)));
+            o1 = make_float2(static_cast<float>(Arith<T>::div_by(px[1][0], cube_t, cube_r)),
+                             static_cast<float>(Arith<T>::div_by(px[1][1], cube_t, cube_r)));
         }
-        const float labn = static_cast<float>(Arith<T>::div(lab, cube_t));
+        const float labn = static_cast<float>(Arith<T>::div_by(lab, cube_t, cube_r));
         const bool hand = g.ok && (lab != T(0));
         *reinterpret_cast<float2*>(img_b + (2 * gly) * kImage + 2 * lx) = o0;
         *reinterpret_cast<float2*>(img_b + (2 * gly + 1) * kImage + 2 * lx) = o1;
@@ -339,42 +352,50 @@ sfr_build_kernel(SfrArgs a) {
     cluster.sync();                                       // peers stay resident until rank 0 has read them
 
     // ---- phase 2: heat maps and depth maps of this band ----------------------
+    // A heat map is zero outside the <= 8x8 footprint of the blurred 4-tap splat, and so is the
+    // depth map.  Pass A streams zeros over the band of every map with 128-bit stores; pass B
+    // revisits only the footprint (<= 11 candidate rows x 11 candidate columns per joint, most of
+    // them rejected by integer tests) and evaluates it in float64.
     if (TRAIN) {
         constexpr int kItemsPerJoint = kBandRows * (kLabel / 4);   // float4 items per joint per band
-        const int total = a.J * kItemsPerJoint;
-        for (int item = tid; item < total; item += kThreads) {
-            const int j = item / kItemsPerJoint;
-            const int rem = item - j * kItemsPerJoint;
-            const int lrow = rem >> 4;
-            const int x0 = (rem & 15) * 4;
-            const int gy = band * kBandRows + lrow;
-            const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + gy * kLabel + x0;
-            float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = h4;
-            const JointParam& jp = joints[j];
-            const bool near_y = abs(gy - jp.ty0) <= 3 || abs(gy - jp.ty1) <= 3;
-            const bool near_x = (x0 + 3 >= jp.tx0 - 3 && x0 <= jp.tx0 + 3) || (x0 + 3 >= jp.tx1 - 3 && x0 <= jp.tx1 + 3);
-            if (g.ok && jp.ok && near_y && near_x) {
-                const double wy0 = gauss_reach(gy, jp.ty0), wy1 = gauss_reach(gy, jp.ty1);
-                float hv[4], dv[4];
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t band_off = static_cast<size_t>(b) * a.J * kMap + band * kBandRows * kLabel;
+        for (int j = 0; j < a.J; ++j) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double wx0 = gauss_reach(x0 + k, jp.tx0), wx1 = gauss_reach(x0 + k, jp.tx1);
-                    // separable order of cv2.GaussianBlur: rows first, then columns
-                    const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
-                    const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
-                    const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
-                    hv[k] = __double2float_rn(h);
-                    const T lab = label_s[lrow * kLabel + x0 + k];
-                    // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
-                    dv[k] = (h > 0.0 && lab != T(0))
-                                ? __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube))
-                                : 0.f;
-                }
-                h4 = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                d4 = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            for (int item = tid; item < kItemsPerJoint; item += kThreads) {
+                st_stream(a.heatmaps + band_off + static_cast<size_t>(j) * kMap + item * 4, zero4);
+                st_stream(a.dmap + band_off + static_cast<size_t>(j) * kMap + item * 4, zero4);
             }
-            st_stream(a.heatmaps + o, h4);
-            st_stream(a.dmap + o, d4);
+        }
+        __syncthreads();      // CTA-scope order: the zero of a pixel precedes its footprint value
+        if (g.ok) {
+            constexpr int kCand = 11;    // offsets -3..3 around tap 0, then 0..3 around tap 1
+            const int total = a.J * kCand * kCand;
+            const int y_lo = band * kBandRows, y_hi = y_lo + kBandRows;
+            for (int c = tid; c < total; c += kThreads) {
+                const int j = c / (kCand * kCand);
+                const int r = c - j * (kCand * kCand);
+                const int sy = r / kCand, sx = r - sy * kCand;
+                const JointParam& jp = joints[j];
+                if (!jp.ok) continue;
+                const int y = sy < 7 ? jp.ty0 + sy - 3 : jp.ty1 + sy - 7;
+                const int x = sx < 7 ? jp.tx0 + sx - 3 : jp.tx1 + sx - 7;
+                if (y < y_lo || y >= y_hi || x < 0 || x >= kLabel) continue;
+                if (sy >= 7 && abs(y - jp.ty0) <= 3) continue;     // already listed around tap 0
+                if (sx >= 7 && abs(x - jp.tx0) <= 3) continue;
+                const double wy0 = gauss_reach(y, jp.ty0), wy1 = gauss_reach(y, jp.ty1);
+                const double wx0 = gauss_reach(x, jp.tx0), wx1 = gauss_reach(x, jp.tx1);
+                // separable order of cv2.GaussianBlur: rows first, then columns
+                const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
+                const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
+                const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
+                const T lab = label_s[(y - y_lo) * kLabel + x];
+                const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + y * kLabel + x;
+                a.heatmaps[o] = __double2float_rn(h);
+                // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
+                if (h > 0.0 && lab != T(0))
+                    a.dmap[o] = __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube));
+            }
         }
     }
 }

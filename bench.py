@@ -225,6 +225,8 @@ def run_b200(args):
     kernel_ms = {}
     for name, s, e in prof:
         kernel_ms.setdefault(name, []).append(s.elapsed_time(e))
+    # device time between the three big kernels (small kernels, launch gaps), averaged per step
+    gap_ms = sum(prof[i][2].elapsed_time(prof[i + 1][1]) for i in range(len(prof) - 1)) / args.steps
     peak, peak_src = measured_peak()
     per_launch_bytes = {"pwr_sfr_build": roofline.sfr_build_bytes(J) * B,
                         "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J) * B,
@@ -309,6 +311,7 @@ def run_b200(args):
             "kernels": kernels,
             "step_roofline_frac": (roofline.step_bytes(J) * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
             "host_issue_ms_per_step": issue_ms,
+            "between_kernels_ms_per_step": gap_ms,
             "cpu_baseline": cpu,
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")

@@ -165,6 +165,14 @@ int pwr_decoder_bwd_loss(const float* z, const float* w, const float* D,
 int pwr_reduce_partials(const float* in, float* out, int B, int J, int C,
                         void* stream);
 
+/* Stage loss values of train.py:197-205 from loss_partial [B,J,3]:
+ *   out4 = (lambda_h*mean_h, lambda_d*mean_d, mean_u, alpha*mean_u +
+ *   (1-alpha)*(lambda_h*mean_h + lambda_d*mean_d)), means over n_mean (0 =
+ *   B*J) of the per-(b,j) sums of squares.  One launch, fixed summation order. */
+int pwr_stage_loss(const float* loss_partial, int B, int J,
+                   float lambda_h, float lambda_d, float alpha, int n_mean,
+                   float* out4, void* stream);
+
 /* In-place multiply n floats by *scale_dev (device scalar); used to apply a
  * non-unit upstream gradient to gradients that were produced eagerly. */
 int pwr_scale_inplace(float* x, const float* scale_dev, long long n,

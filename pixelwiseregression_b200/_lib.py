@@ -32,6 +32,7 @@ SIGNATURES = {
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _P],
     "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _P],
     "pwr_reduce_partials": [_P, _P, _I, _I, _I, _P],
+    "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P],
     "pwr_scale_inplace": [_P, _P, _LL, _P],
     "pwr_recover_uvd": [_P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _I, _I, _P],
 }

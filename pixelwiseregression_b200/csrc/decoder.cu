@@ -578,6 +578,32 @@ reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out, in
     if (threadIdx.x == 0) out[jc] = v[0];
 }
 
+// train.py:197-205 from the per-(b,j) sums of squares: one CTA, fixed order.
+constexpr int kLossThreads = 1024;
+__global__ void __launch_bounds__(kLossThreads)
+stage_loss_kernel(const float* __restrict__ loss_partial, int n_items, float scale_h, float scale_d, float scale_u,
+                  float alpha, float* __restrict__ out) {
+    __shared__ float scratch[(kLossThreads / 32) * 3];
+    float v[3] = {0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < n_items; i += kLossThreads) {
+        v[0] += loss_partial[i * 3 + 0];
+        v[1] += loss_partial[i * 3 + 1];
+        v[2] += loss_partial[i * 3 + 2];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) { scratch[warp * 3 + 0] = v[0]; scratch[warp * 3 + 1] = v[1]; scratch[warp * 3 + 2] = v[2]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s[3] = {0.f, 0.f, 0.f};
+        for (int wv = 0; wv < kLossThreads / 32; ++wv) { s[0] += scratch[wv * 3]; s[1] += scratch[wv * 3 + 1]; s[2] += scratch[wv * 3 + 2]; }
+        const float lh = s[0] * scale_h, ld = s[1] * scale_d, lu = s[2] * scale_u;
+        out[0] = lh; out[1] = ld; out[2] = lu;
+        out[3] = alpha * lu + (1.f - alpha) * (lh + ld);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 scale_inplace_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n4, long long n) {
     const float s = *scale;
@@ -744,6 +770,17 @@ extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, in
     if (out == nullptr || (in == nullptr && B != 0)) return PWR_E_NULL;
     if (B < 0 || J < 1 || C < 1 || J * C > 65535) return PWR_E_SHAPE;
     reduce_partials_kernel<<<J * C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, J, C);
+    return launch_status();
+}
+
+extern "C" int pwr_stage_loss(const float* loss_partial, int B, int J, float lambda_h, float lambda_d, float alpha,
+                              int n_mean, float* out4, void* stream) {
+    if (int rc = check_bj(B, J)) return rc;
+    if (out4 == nullptr || (loss_partial == nullptr && B != 0)) return PWR_E_NULL;
+    const double n = n_mean > 0 ? static_cast<double>(n_mean) : static_cast<double>(B) * J;
+    stage_loss_kernel<<<1, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        loss_partial, B * J, static_cast<float>(lambda_h / n), static_cast<float>(lambda_d / n),
+        static_cast<float>(1.0 / n), alpha, out4);
     return launch_status();
 }
 

@@ -235,31 +235,44 @@ sfr_build_kernel(SfrArgs a) {
     const int b = blockIdx.x / kBands;
     const int tid = threadIdx.x;
 
-    if (tid == 0) sample_geometry(geom, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf);
-    __syncthreads();
-    const SampleGeom g = geom;
-
-    int joints_ok = 1;
-    if (TRAIN) {
-        if (tid < a.J) {
-            float* un = (band == 0) ? a.uvd_norm + (static_cast<size_t>(b) * a.J + tid) * 3 : nullptr;
-            if (g.ok) {
-                joint_param(joints[tid], un, a.uvd + (static_cast<size_t>(b) * a.J + tid) * 3, g);
-            } else {
-                joints[tid].ok = 0;
-                if (un != nullptr) { un[0] = 0.f; un[1] = 0.f; un[2] = 0.f; }
+    // ---- prologue: warp 0 derives the sample geometry (thread 0) and the joint taps (one lane
+    // per joint) in float64 while warps 1..7 already stream the zeros of phase 2 (pass A): a
+    // heat map is zero outside the <= 8x8 footprint of the blurred 4-tap splat, and so is the
+    // depth map, so every map band is zero-filled with 128-bit stores and patched later.
+    if (tid < 32) {
+        if (tid == 0) sample_geometry(geom, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf);
+        __syncwarp();
+        if (TRAIN) {
+            for (int j = tid; j < a.J; j += 32) {
+                float* un = (band == 0) ? a.uvd_norm + (static_cast<size_t>(b) * a.J + j) * 3 : nullptr;
+                if (geom.ok) {
+                    joint_param(joints[j], un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, geom);
+                } else {
+                    joints[j].ok = 0;
+                    if (un != nullptr) { un[0] = 0.f; un[1] = 0.f; un[2] = 0.f; }
+                }
             }
         }
+    } else if (TRAIN) {
+        constexpr int kBandVec = kBandRows * (kLabel / 4);          // float4 per map band
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t band_off = static_cast<size_t>(b) * a.J * kMap + band * kBandRows * kLabel;
+        const int total = a.J * kBandVec;
+        for (int item = tid - 32; item < total; item += kThreads - 32) {
+            const int j = item / kBandVec;
+            const size_t o = band_off + static_cast<size_t>(j) * kMap + (item - j * kBandVec) * 4;
+            st_stream(a.heatmaps + o, zero4);
+            st_stream(a.dmap + o, zero4);
+        }
     }
+    __syncthreads();
+    const SampleGeom g = geom;
     if (g.ok) {
         if (tid < kImage) xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);
         else if (tid < kImage + 2 * kBandRows)
             ytap[tid - kImage] = linear_tap(band * 2 * kBandRows + (tid - kImage), g.nrows, g.scale_y);
     }
     __syncthreads();
-    if (TRAIN) {
-        for (int j = 0; j < a.J; ++j) joints_ok &= joints[j].ok;
-    }
 
     // ---- phase 1: image band, label band, mask band -------------------------
     float* img_b = a.img + static_cast<size_t>(b) * kImage * kImage;
@@ -269,7 +282,7 @@ sfr_build_kernel(SfrArgs a) {
     const T cube_t = static_cast<T>(g.cube);
     const T cube_r = Arith<T>::rcp(cube_t);
     int my_count = 0, my_nan = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (int it = 0; it < kLabelIters; ++it) {
         const int lrow = it * (kThreads / kLabel) + (tid >> 6);     // label row inside the band
         const int lx = tid & (kLabel - 1);
@@ -332,42 +345,17 @@ sfr_build_kernel(SfrArgs a) {
         __syncthreads();
         if ((tid & 31) == 0) { atomicAdd(&band_flags[0], c); atomicOr(&band_flags[1], n); }
     }
-    cluster.sync();                                       // all bands published their flags
-    if (band == 0 && tid == 0) {
-        int count = 0, nan_seen = 0;
-        for (int r = 0; r < kBands; ++r) {
-            const int* peer = cluster.map_shared_rank(band_flags, r);
-            count += peer[0];
-            nan_seen |= peer[1];
-        }
-        uint8_t v = g.ok ? 1 : 0;
-        if (TRAIN) v = (g.ok && joints_ok && !nan_seen && count >= 10) ? 1 : 0;   // datasets.py:362-365,385-390
-        a.valid[b] = v;
-        a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
-        a.cube_size[b] = static_cast<float>(g.cube);
-        a.com_out[3 * b + 0] = static_cast<float>(g.c0);
-        a.com_out[3 * b + 1] = static_cast<float>(g.r0);
-        a.com_out[3 * b + 2] = static_cast<float>(g.z);
-    }
-    cluster.sync();                                       // peers stay resident until rank 0 has read them
+    // Split cluster barrier: publish, keep working, and only look at the peers' flags (rank 0)
+    // once the footprint pass is done, so no band ever idles in the middle of the kernel.
+    __syncthreads();                                      // band_flags final
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
-    // ---- phase 2: heat maps and depth maps of this band ----------------------
-    // A heat map is zero outside the <= 8x8 footprint of the blurred 4-tap splat, and so is the
-    // depth map.  Pass A streams zeros over the band of every map with 128-bit stores; pass B
-    // revisits only the footprint (<= 11 candidate rows x 11 candidate columns per joint, most of
-    // them rejected by integer tests) and evaluates it in float64.
+    // ---- phase 2, pass B: the <= 8x8 footprint of every joint in this band, float64 ----------
+    // (<= 11 candidate rows x 11 candidate columns per joint, most rejected by integer tests;
+    // pass A zero-filled the maps before the barriers above, so CTA-scope order holds)
+    int joints_ok = 1;
     if (TRAIN) {
-        constexpr int kItemsPerJoint = kBandRows * (kLabel / 4);   // float4 items per joint per band
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const size_t band_off = static_cast<size_t>(b) * a.J * kMap + band * kBandRows * kLabel;
-        for (int j = 0; j < a.J; ++j) {
-#pragma unroll
-            for (int item = tid; item < kItemsPerJoint; item += kThreads) {
-                st_stream(a.heatmaps + band_off + static_cast<size_t>(j) * kMap + item * 4, zero4);
-                st_stream(a.dmap + band_off + static_cast<size_t>(j) * kMap + item * 4, zero4);
-            }
-        }
-        __syncthreads();      // CTA-scope order: the zero of a pixel precedes its footprint value
+        for (int j = 0; j < a.J; ++j) joints_ok &= joints[j].ok;
         if (g.ok) {
             constexpr int kCand = 11;    // offsets -3..3 around tap 0, then 0..3 around tap 1
             const int total = a.J * kCand * kCand;
@@ -398,6 +386,27 @@ sfr_build_kernel(SfrArgs a) {
             }
         }
     }
+
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // all bands published
+    if (band == 0 && tid == 0) {
+        int count = 0, nan_seen = 0;
+        for (int r = 0; r < kBands; ++r) {
+            const int* peer = cluster.map_shared_rank(band_flags, r);
+            count += peer[0];
+            nan_seen |= peer[1];
+        }
+        uint8_t v = g.ok ? 1 : 0;
+        if (TRAIN) v = (g.ok && joints_ok && !nan_seen && count >= 10) ? 1 : 0;   // datasets.py:362-365,385-390
+        a.valid[b] = v;
+        a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
+        a.cube_size[b] = static_cast<float>(g.cube);
+        a.com_out[3 * b + 0] = static_cast<float>(g.c0);
+        a.com_out[3 * b + 1] = static_cast<float>(g.r0);
+        a.com_out[3 * b + 2] = static_cast<float>(g.z);
+    }
+    // peers stay resident until rank 0 has read their shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------

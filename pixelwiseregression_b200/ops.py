@@ -115,26 +115,22 @@ def scale_inplace_(x, scale):
     return x
 
 
-_SCALE_CACHE = {}
-
-
-def _loss_scale_tensor(lambda_h, lambda_d, n, device):
-    """[lambda_h/n, lambda_d/n, 1/n] on the device, cached (no per-step H2D copy)."""
-    key = (float(lambda_h), float(lambda_d), float(n), str(device))
-    t = _SCALE_CACHE.get(key)
-    if t is None:
-        t = torch.tensor([lambda_h / n, lambda_d / n, 1.0 / n], dtype=torch.float32).to(device)
-        _SCALE_CACHE[key] = t
-    return t
-
-
-def stage_loss_from_partials(loss_partial, lambda_h, lambda_d, n_mean=None):
-    """train.py:197-199 from per-(b,j) sums of squares: returns a [3] tensor
-    (heatmap_loss, depthmap_loss, uvd_loss)."""
+def stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean=0):
+    """train.py:197-205 from per-(b,j) sums of squares in one launch (pwr_stage_loss):
+    returns a [4] tensor (heatmap_loss, depthmap_loss, uvd_loss, combined loss)."""
+    require_cuda(loss_partial)
     B, J = loss_partial.shape[0], loss_partial.shape[1]
-    n = float(n_mean if n_mean else B * J)
-    sums = reduce_partials(loss_partial).sum(dim=0)          # [3]
-    return sums * _loss_scale_tensor(lambda_h, lambda_d, n, sums.device)
+    out = torch.empty(4, device=loss_partial.device, dtype=torch.float32)
+    with torch.cuda.device(loss_partial.device):
+        rc = _lib.load().pwr_stage_loss(ptr(loss_partial), B, J, float(lambda_h), float(lambda_d), float(alpha),
+                                        int(n_mean), ptr(out), stream_ptr(loss_partial.device))
+    check(rc, "pwr_stage_loss")
+    return out
+
+
+def stage_loss_from_partials(loss_partial, lambda_h, lambda_d, n_mean=0):
+    """[3] tensor (heatmap_loss, depthmap_loss, uvd_loss), train.py:197-199."""
+    return stage_loss(loss_partial, lambda_h, lambda_d, 1.0, n_mean)[:3]
 
 
 class DecoderFunction(torch.autograd.Function):
@@ -152,6 +148,7 @@ class DecoderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, w, D, label_img, mask, method, heat_gt=None, dmap_gt=None, uvd_gt=None, alpha=1.0,
                 lambda_h=1.0, lambda_d=0.01):
+        ctx.set_materialize_grads(False)
         targets = (heat_gt, dmap_gt, uvd_gt) if heat_gt is not None else None
         H, uvd, stats, loss_partial = decoder_forward_raw(z, w, D, label_img, mask, method, targets=targets)
         ctx.method = method
@@ -161,8 +158,8 @@ class DecoderFunction(torch.autograd.Function):
         outs = (H.to(z.dtype), D.view_as(D), uvd.to(z.dtype))
         if targets is None:
             return outs
-        terms = stage_loss_from_partials(loss_partial, lambda_h, lambda_d)
-        total = alpha * terms[2] + (1.0 - alpha) * (terms[0] + terms[1])
+        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
+        terms, total = out4[:3], out4[3]
         ctx.mark_non_differentiable(terms)
         return outs + (total, terms)
 
@@ -205,6 +202,7 @@ class PlaneFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, w, method):
+        ctx.set_materialize_grads(False)
         H, uvd, stats, _ = decoder_forward_raw(z, w, None, None, None, method)
         ctx.method = method
         ctx.save_for_backward(z, w, stats, uvd)
@@ -231,6 +229,7 @@ class DepthFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, D, heatmaps, label_img, mask):
+        ctx.set_materialize_grads(False)
         _, uvd, stats, _ = decoder_forward_raw(heatmaps, None, D, label_img, mask, "given", store_heat=False)
         ctx.save_for_backward(D, heatmaps, label_img, mask, stats, uvd)
         return uvd[:, :, 2:].contiguous().to(D.dtype)
@@ -239,7 +238,8 @@ class DepthFunction(torch.autograd.Function):
     def backward(ctx, g_d):
         D, heatmaps, label_img, mask, stats, uvd = ctx.saved_tensors
         g_uvd = torch.zeros_like(uvd)
-        g_uvd[:, :, 2:] = g_d
+        if g_d is not None:
+            g_uvd[:, :, 2:] = g_d
         gH, gD, _, _ = decoder_backward_raw(heatmaps, None, D, label_img, mask, stats, uvd, g_uvd, None, None,
                                             "given")
         return gD.to(D.dtype), gH.to(heatmaps.dtype), None, None
@@ -259,14 +259,15 @@ class DecoderLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method, alpha, lambda_h, lambda_d,
                 store_heat):
+        ctx.set_materialize_grads(False)       # no zero-filled gradient tensors for the detached outputs
         need_grad = any(ctx.needs_input_grad[:3])
         H, uvd, stats, _ = decoder_forward_raw(z, w, D, label_img, mask, method, store_heat=store_heat)
         targets = (heat_gt, dmap_gt, uvd_gt)
         gz, gD, gw_partial, loss_partial = decoder_backward_raw(
             z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
             want_loss=True, want_gz=need_grad, want_gD=need_grad)
-        terms = stage_loss_from_partials(loss_partial, lambda_h, lambda_d)
-        total = alpha * terms[2] + (1.0 - alpha) * (terms[0] + terms[1])
+        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
+        terms, total = out4[:3], out4[3]
         gw = reduce_partials(gw_partial).view_as(w) if (need_grad and w is not None) else None
         ctx.has_w = w is not None
         ctx.grads = (gz, gD, gw)
@@ -280,6 +281,8 @@ class DecoderLossFunction(torch.autograd.Function):
         ctx.grads = None
         if gz is None:
             raise _lib.PwrError("DecoderLossFunction: forward ran without gradient tracking")
+        if g_total is None:
+            return (None,) * 13
         scale_inplace_(gz, g_total)
         scale_inplace_(gD, g_total)
         if gw is not None:

@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--shape", default="NYU")
     ap.add_argument("--alpha", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
-    ap.add_argument("--cpu-samples", type=int, default=256, help="samples in the bounded CPU baseline")
+    ap.add_argument("--cpu-samples", type=int, default=512, help="samples in the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -78,6 +78,11 @@ class ClockSampler(threading.Thread):
         self.sm_max = None
         self.stop_flag = threading.Event()
         self.error = None
+        self.marked = 0
+
+    def mark(self):
+        """Start of the timed region: samples taken from here on are `samples_timed`."""
+        self.marked = len(self.sm)
 
     def run(self):
         try:
@@ -108,6 +113,8 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable: %s" % self.error]}
         return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.sm_max,
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "samples_timed": len(self.sm) - self.marked,
+                "sm_mhz_timed": statistics.median(self.sm[self.marked:]) if len(self.sm) > self.marked else None,
                 "power_w_max": max(self.power) if self.power else None}
 
 
@@ -123,13 +130,17 @@ def run_reference(args):
     shape = synth.SHAPES[args.shape]
     n = args.cpu_samples
     cores = os.cpu_count() or 1
-    for _ in range(max(1, min(args.warmup, 1))):           # one warm-up pass (pool start-up, page-in)
-        cpu_baseline.time_path(shape, min(n, 32), seed=1)
+    import torch
+    torch.set_num_threads(cores)
+    d = cpu_baseline.prepare(shape, n, seed=0)                 # inputs are built outside the timed region
+    for _ in range(max(1, args.warmup)):                       # warm-up passes (pool start-up, page-in)
+        cpu_baseline.run_path(shape, d, cores)
     t0 = time.perf_counter()
-    res = None
-    for i in range(args.steps):
-        res = cpu_baseline.time_path(shape, n, seed=i)
+    for _ in range(args.steps):
+        cpu_baseline.run_path(shape, d, cores)
     dt = time.perf_counter() - t0
+    cpu_baseline.shutdown()
+    res = {"sample": cpu_baseline.describe(shape, n, cores)}
     value = n * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -194,13 +205,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the warm-up on (same load as the timed region, which may last
+    # only tens of milliseconds); samples inside the timed region are counted separately
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(frames, com, cube, uvd, z, D)
     barrier()
 
     # ---- timed region: K steps, device-timed, per-kernel events on the launching stream ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     launches0 = _lib.launch_count()
     _lib.PROFILE = []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,7 +299,6 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
-        cpu_baseline.time_path(shape, 32, seed=1)                       # warm-up (pool start, page-in)
         res = cpu_baseline.time_path(shape, args.cpu_samples, seed=0, repeats=2)
         cpu = {"value": res["samples_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
                "sample": res["sample"] + "; best of 2 passes"}

@@ -10,7 +10,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpwr_b200.so")
+# PWR_LIB_PATH selects another build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("PWR_LIB_PATH") or os.path.join(_PKG, "libpwr_b200.so")
 
 METHOD_SOFTMAX, METHOD_SUM, METHOD_GIVEN = 0, 1, 2
 METHODS = {"softmax": METHOD_SOFTMAX, "sum": METHOD_SUM, "given": METHOD_GIVEN}

@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 METRIC = "SFR+decoder samples/s"
 UNIT = "samples/s"
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+OUT = sys.stdout
 
 
 def parse_args():
@@ -152,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # --------------------------------------------------------------------------- #
@@ -335,13 +336,24 @@ def run_b200(args):
                 line["roofline"]["traffic"] = tr.get(dominant, {}).get("dram_bytes_per_launch")
             except Exception:
                 pass
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else a library may print to fd 1
+    (e.g. NCCL's version banner) is routed to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse_args()
+    global OUT
+    OUT = claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -17,8 +17,9 @@
 //   2. writes its R rows of every joint's heat map and depth map: 128-bit
 //      zero stores outside the <= 8x8 support, float64 evaluation inside.
 // The per-sample reject gate (sum(mask) < 10, NaN; datasets.py:385-390) needs a
-// reduction over the bands: each CTA publishes its count in its own shared
-// memory and rank 0 reads the peers through distributed shared memory.
+// reduction over the bands: each CTA pushes its count into rank 0's shared
+// memory (distributed shared memory, red.shared::cluster) and arrives on rank
+// 0's mbarrier; only rank 0's thread 0 ever waits.
 //
 // Arithmetic contract (bit-level where the result is discontinuous):
 //   * crop box, int CoM, slice extents: float64 with explicit _rn intrinsics
@@ -220,6 +221,46 @@ struct SfrArgs {
     int B, J;
 };
 
+// Bilinear taps of one 2x2 image block (one label pixel), gathered from the frame with the
+// depth window + centring applied per tap.  INTERIOR: every source row / column of this band
+// lies inside the frame, so no bounds predicates are needed.
+template <typename T, bool INTERIOR>
+__device__ __forceinline__ void resample_block(T (&px)[2][2], const float* __restrict__ frame, const SampleGeom& g,
+                                               const TapX* ytap2, const TapX* xtap2, int Hf, int Wf) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const TapX ty = ytap2[dy];
+        const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
+        const bool ra = INTERIOR || (fr_a >= 0 && fr_a < Hf), rb = INTERIOR || (fr_b >= 0 && fr_b < Hf);
+        const int row_a = fr_a * Wf, row_b = fr_b * Wf;          // Hf*Wf < 2^31 (checked on the host)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const TapX tx = xtap2[dx];
+            const int fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
+            const bool ca = INTERIOR || (fc_a >= 0 && fc_a < Wf), cb = INTERIOR || (fc_b >= 0 && fc_b < Wf);
+            const float v00 = (ra && ca) ? __ldg(frame + (row_a + fc_a)) : 0.f;
+            const float v01 = (ra && cb) ? __ldg(frame + (row_a + fc_b)) : 0.f;
+            const float v10 = (rb && ca) ? __ldg(frame + (row_b + fc_a)) : 0.f;
+            const float v11 = (rb && cb) ? __ldg(frame + (row_b + fc_b)) : 0.f;
+            const T w00 = Arith<T>::window(static_cast<T>(v00), g);
+            const T w01 = Arith<T>::window(static_cast<T>(v01), g);
+            const T w10 = Arith<T>::window(static_cast<T>(v10), g);
+            const T w11 = Arith<T>::window(static_cast<T>(v11), g);
+            const T xa0 = static_cast<T>(tx.a0), xa1 = static_cast<T>(tx.a1);
+            const T top = Arith<T>::add(Arith<T>::mul(w00, xa0), Arith<T>::mul(w01, xa1));
+            const T bot = Arith<T>::add(Arith<T>::mul(w10, xa0), Arith<T>::mul(w11, xa1));
+            px[dy][dx] = Arith<T>::add(Arith<T>::mul(top, static_cast<T>(ty.a0)), Arith<T>::mul(bot, static_cast<T>(ty.a1)));
+        }
+    }
+}
+
+// remote (cluster) shared-memory helpers for the per-sample reject gate
+__device__ __forceinline__ uint32_t cluster_addr_of_rank(const void* smem_ptr, uint32_t rank) {
+    uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr)), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+
 template <typename T, bool TRAIN>
 __global__ void __launch_bounds__(kThreads)
 sfr_build_kernel(SfrArgs a) {
@@ -229,11 +270,31 @@ sfr_build_kernel(SfrArgs a) {
     __shared__ TapX xtap[kImage];
     __shared__ TapX ytap[2 * kBandRows];
     __shared__ T label_s[kBandRows * kLabel];
-    __shared__ int band_flags[2];               // [0] mask count, [1] NaN seen; read by rank 0 through DSMEM
+    __shared__ int band_list[TRAIN ? PWR_MAX_JOINTS : 1];   // joints whose footprint touches this band
+    __shared__ int band_list_n;
+    __shared__ int joints_bad;                              // some joint is out of range / NaN
+    __shared__ int band_flags[2];                           // [0] mask count, [1] NaN seen (this CTA)
+    // rank 0 only: totals pushed by all bands of the sample + the barrier they arrive on
+    __shared__ int sample_flags[2];
+    __shared__ __align__(8) uint64_t sample_bar;
 
     const int band = static_cast<int>(cluster.block_rank());
     const int b = blockIdx.x / kBands;
     const int tid = threadIdx.x;
+    const int y_lo = band * kBandRows, y_hi = y_lo + kBandRows;
+
+    if (tid == 0) {
+        band_list_n = 0; joints_bad = 0; band_flags[0] = 0; band_flags[1] = 0;
+        if (band == 0) {
+            sample_flags[0] = 0; sample_flags[1] = 0;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
+                             static_cast<uint32_t>(__cvta_generic_to_shared(&sample_bar))), "r"(kBands) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    // phase 0 of the cluster barrier: "rank 0's gate state is initialised"; waited for (by then
+    // long complete) right before a band pushes its totals
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
     // ---- prologue: warp 0 derives the sample geometry (thread 0) and the joint taps (one lane
     // per joint) in float64 while warps 1..7 already stream the zeros of phase 2 (pass A): a
@@ -245,24 +306,32 @@ sfr_build_kernel(SfrArgs a) {
         if (TRAIN) {
             for (int j = tid; j < a.J; j += 32) {
                 float* un = (band == 0) ? a.uvd_norm + (static_cast<size_t>(b) * a.J + j) * 3 : nullptr;
+                JointParam& jp = joints[j];
                 if (geom.ok) {
-                    joint_param(joints[j], un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, geom);
+                    joint_param(jp, un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, geom);
                 } else {
-                    joints[j].ok = 0;
+                    jp.ok = 0;
                     if (un != nullptr) { un[0] = 0.f; un[1] = 0.f; un[2] = 0.f; }
+                }
+                if (!jp.ok) {
+                    joints_bad = 1;
+                } else if ((jp.ty0 + 3 >= y_lo && jp.ty0 - 3 < y_hi) || (jp.ty1 + 3 >= y_lo && jp.ty1 < y_hi)) {
+                    band_list[atomicAdd(&band_list_n, 1)] = j;       // rows ty0-3..ty0+3 or ty1..ty1+3 hit the band
                 }
             }
         }
     } else if (TRAIN) {
-        constexpr int kBandVec = kBandRows * (kLabel / 4);          // float4 per map band
+        // 7 warps x (joints warp-1, warp+6, ...) x 2 maps x 256 float4 of zeros per band
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const size_t band_off = static_cast<size_t>(b) * a.J * kMap + band * kBandRows * kLabel;
-        const int total = a.J * kBandVec;
-        for (int item = tid - 32; item < total; item += kThreads - 32) {
-            const int j = item / kBandVec;
-            const size_t o = band_off + static_cast<size_t>(j) * kMap + (item - j * kBandVec) * 4;
-            st_stream(a.heatmaps + o, zero4);
-            st_stream(a.dmap + o, zero4);
+        const size_t band_off = static_cast<size_t>(b) * a.J * kMap + y_lo * kLabel + (tid & 31) * 4;
+        for (int j = (tid >> 5) - 1; j < a.J; j += kWarps - 1) {
+            float* hp = a.heatmaps + band_off + static_cast<size_t>(j) * kMap;
+            float* dp = a.dmap + band_off + static_cast<size_t>(j) * kMap;
+#pragma unroll
+            for (int i = 0; i < kBandRows * kLabel / 128; ++i) {
+                st_stream(hp + i * 128, zero4);
+                st_stream(dp + i * 128, zero4);
+            }
         }
     }
     __syncthreads();
@@ -281,42 +350,20 @@ sfr_build_kernel(SfrArgs a) {
     const float* frame = a.frames + static_cast<size_t>(b) * a.Hf * a.Wf;
     const T cube_t = static_cast<T>(g.cube);
     const T cube_r = Arith<T>::rcp(cube_t);
+    const bool interior = g.ok && g.fc0 >= 0 && g.fc0 + g.ncols <= a.Wf && g.fr0 + ytap[0].s0 >= 0 &&
+                          g.fr0 + ytap[2 * kBandRows - 1].s1 < a.Hf;
     int my_count = 0, my_nan = 0;
 #pragma unroll 2
     for (int it = 0; it < kLabelIters; ++it) {
         const int lrow = it * (kThreads / kLabel) + (tid >> 6);     // label row inside the band
         const int lx = tid & (kLabel - 1);
-        const int gly = band * kBandRows + lrow;                   // label row in the sample
+        const int gly = y_lo + lrow;                               // label row in the sample
         T lab = T(0);
         float2 o0 = make_float2(0.f, 0.f), o1 = o0;
         if (g.ok) {
             T px[2][2];
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-                const TapX ty = ytap[2 * lrow + dy];
-                const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
-                const bool ra = fr_a >= 0 && fr_a < a.Hf, rb = fr_b >= 0 && fr_b < a.Hf;
-                const int row_a = fr_a * a.Wf, row_b = fr_b * a.Wf;      // Hf*Wf < 2^31 (checked on the host)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const TapX tx = xtap[2 * lx + dx];
-                    const int fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
-                    const bool ca = fc_a >= 0 && fc_a < a.Wf, cb = fc_b >= 0 && fc_b < a.Wf;
-                    const float v00 = (ra && ca) ? __ldg(frame + (row_a + fc_a)) : 0.f;
-                    const float v01 = (ra && cb) ? __ldg(frame + (row_a + fc_b)) : 0.f;
-                    const float v10 = (rb && ca) ? __ldg(frame + (row_b + fc_a)) : 0.f;
-                    const float v11 = (rb && cb) ? __ldg(frame + (row_b + fc_b)) : 0.f;
-                    const T w00 = Arith<T>::window(static_cast<T>(v00), g);
-                    const T w01 = Arith<T>::window(static_cast<T>(v01), g);
-                    const T w10 = Arith<T>::window(static_cast<T>(v10), g);
-                    const T w11 = Arith<T>::window(static_cast<T>(v11), g);
-                    const T xa0 = static_cast<T>(tx.a0), xa1 = static_cast<T>(tx.a1);
-                    const T top = Arith<T>::add(Arith<T>::mul(w00, xa0), Arith<T>::mul(w01, xa1));
-                    const T bot = Arith<T>::add(Arith<T>::mul(w10, xa0), Arith<T>::mul(w11, xa1));
-                    px[dy][dx] = Arith<T>::add(Arith<T>::mul(top, static_cast<T>(ty.a0)),
-                                               Arith<T>::mul(bot, static_cast<T>(ty.a1)));
-                }
-            }
+            if (interior) resample_block<T, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Hf, a.Wf);
+            else          resample_block<T, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Hf, a.Wf);
             // 2x2 mean (cv::resize reroutes an exact 2x INTER_LINEAR shrink to the area path)
             lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
                                 T(0.25));
@@ -335,68 +382,74 @@ sfr_build_kernel(SfrArgs a) {
         my_count += hand ? 1 : 0;
         my_nan |= (isnan(o0.x) || isnan(o0.y) || isnan(o1.x) || isnan(o1.y) || isnan(labn)) ? 1 : 0;
     }
-    __syncthreads();                                      // label_s complete
     {
         // block totals of my_count / my_nan
         int c = my_count, n = my_nan;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); n |= __shfl_xor_sync(0xffffffffu, n, o); }
-        if (tid == 0) { band_flags[0] = 0; band_flags[1] = 0; }
-        __syncthreads();
         if ((tid & 31) == 0) { atomicAdd(&band_flags[0], c); atomicOr(&band_flags[1], n); }
     }
-    // Split cluster barrier: publish, keep working, and only look at the peers' flags (rank 0)
-    // once the footprint pass is done, so no band ever idles in the middle of the kernel.
-    __syncthreads();                                      // band_flags final
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();                                      // label_s and band_flags complete
 
-    // ---- phase 2, pass B: the <= 8x8 footprint of every joint in this band, float64 ----------
+    // ---- per-sample reject gate: every band pushes its totals into rank 0's shared memory and
+    // arrives on rank 0's mbarrier; bands 1..3 never wait for anybody (push, not pull).
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // rank 0 initialised its gate
+    if (tid == 0) {
+        const uint32_t rflags = cluster_addr_of_rank(sample_flags, 0);
+        const uint32_t rbar = cluster_addr_of_rank(&sample_bar, 0);
+        asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(rflags), "r"(band_flags[0]) : "memory");
+        asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(rflags + 4), "r"(band_flags[1]) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+    }
+
+    // ---- phase 2, pass B: the <= 8x8 footprint of every joint that touches this band, float64
     // (<= 11 candidate rows x 11 candidate columns per joint, most rejected by integer tests;
     // pass A zero-filled the maps before the barriers above, so CTA-scope order holds)
-    int joints_ok = 1;
-    if (TRAIN) {
-        for (int j = 0; j < a.J; ++j) joints_ok &= joints[j].ok;
-        if (g.ok) {
-            constexpr int kCand = 11;    // offsets -3..3 around tap 0, then 0..3 around tap 1
-            const int total = a.J * kCand * kCand;
-            const int y_lo = band * kBandRows, y_hi = y_lo + kBandRows;
-            for (int c = tid; c < total; c += kThreads) {
-                const int j = c / (kCand * kCand);
-                const int r = c - j * (kCand * kCand);
-                const int sy = r / kCand, sx = r - sy * kCand;
-                const JointParam& jp = joints[j];
-                if (!jp.ok) continue;
-                const int y = sy < 7 ? jp.ty0 + sy - 3 : jp.ty1 + sy - 7;
-                const int x = sx < 7 ? jp.tx0 + sx - 3 : jp.tx1 + sx - 7;
-                if (y < y_lo || y >= y_hi || x < 0 || x >= kLabel) continue;
-                if (sy >= 7 && abs(y - jp.ty0) <= 3) continue;     // already listed around tap 0
-                if (sx >= 7 && abs(x - jp.tx0) <= 3) continue;
-                const double wy0 = gauss_reach(y, jp.ty0), wy1 = gauss_reach(y, jp.ty1);
-                const double wx0 = gauss_reach(x, jp.tx0), wx1 = gauss_reach(x, jp.tx1);
-                // separable order of cv2.GaussianBlur: rows first, then columns
-                const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
-                const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
-                const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
-                const T lab = label_s[(y - y_lo) * kLabel + x];
-                const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + y * kLabel + x;
-                a.heatmaps[o] = __double2float_rn(h);
-                // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
-                if (h > 0.0 && lab != T(0))
-                    a.dmap[o] = __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube));
-            }
+    if (TRAIN && g.ok) {
+        constexpr int kCand = 11;    // offsets -3..3 around tap 0, then 0..3 around tap 1
+        const int total = band_list_n * kCand * kCand;
+        for (int c = tid; c < total; c += kThreads) {
+            const int jl = c / (kCand * kCand);
+            const int r = c - jl * (kCand * kCand);
+            const int sy = r / kCand, sx = r - sy * kCand;
+            const int j = band_list[jl];
+            const JointParam& jp = joints[j];
+            const int y = sy < 7 ? jp.ty0 + sy - 3 : jp.ty1 + sy - 7;
+            const int x = sx < 7 ? jp.tx0 + sx - 3 : jp.tx1 + sx - 7;
+            if (y < y_lo || y >= y_hi || x < 0 || x >= kLabel) continue;
+            if (sy >= 7 && abs(y - jp.ty0) <= 3) continue;     // already listed around tap 0
+            if (sx >= 7 && abs(x - jp.tx0) <= 3) continue;
+            const double wy0 = gauss_reach(y, jp.ty0), wy1 = gauss_reach(y, jp.ty1);
+            const double wx0 = gauss_reach(x, jp.tx0), wx1 = gauss_reach(x, jp.tx1);
+            // separable order of cv2.GaussianBlur: rows first, then columns
+            const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
+            const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
+            const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
+            const T lab = label_s[(y - y_lo) * kLabel + x];
+            const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + y * kLabel + x;
+            a.heatmaps[o] = __double2float_rn(h);
+            // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
+            if (h > 0.0 && lab != T(0))
+                a.dmap[o] = __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube));
         }
     }
 
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // all bands published
     if (band == 0 && tid == 0) {
-        int count = 0, nan_seen = 0;
-        for (int r = 0; r < kBands; ++r) {
-            const int* peer = cluster.map_shared_rank(band_flags, r);
-            count += peer[0];
-            nan_seen |= peer[1];
-        }
+        // all kBands bands (this one included) have pushed: phase 0 of sample_bar completes
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&sample_bar));
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "GATE_WAIT:\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra GATE_DONE;\n"
+            "bra GATE_WAIT;\n"
+            "GATE_DONE:\n"
+            "}" ::"r"(bar), "r"(0) : "memory");
+        const int count = *reinterpret_cast<volatile int*>(&sample_flags[0]);
+        const int nan_seen = *reinterpret_cast<volatile int*>(&sample_flags[1]);
         uint8_t v = g.ok ? 1 : 0;
-        if (TRAIN) v = (g.ok && joints_ok && !nan_seen && count >= 10) ? 1 : 0;   // datasets.py:362-365,385-390
+        if (TRAIN) v = (g.ok && !joints_bad && !nan_seen && count >= 10) ? 1 : 0;   // datasets.py:362-365,385-390
         a.valid[b] = v;
         a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
         a.cube_size[b] = static_cast<float>(g.cube);
@@ -404,9 +457,6 @@ sfr_build_kernel(SfrArgs a) {
         a.com_out[3 * b + 1] = static_cast<float>(g.r0);
         a.com_out[3 * b + 2] = static_cast<float>(g.z);
     }
-    // peers stay resident until rank 0 has read their shared memory
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------

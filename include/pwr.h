@@ -22,6 +22,7 @@
 #ifndef PWR_B200_H
 #define PWR_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -62,6 +63,12 @@ const char* pwr_error_string(int rc);
 int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com /*[B,3]*/,
                 int B, void* stream);
 
+/* Bytes of caller-allocated device scratch pwr_sfr_crop (J = 0) / pwr_sfr_build
+ * need: per-sample crop geometry and per-joint splat taps prepared once per
+ * sample, plus the counter of the per-sample reject gate.  Contents need no
+ * initialisation and are dead after the call.  0 for invalid B / J. */
+size_t pwr_sfr_workspace_bytes(int B, int J);
+
 /* Test-only SFR (the 6-tuple of datasets.py:334-348): crop box :306-309,
  * center_crop utils.py:167-173, depth window + centring :312-315, int CoM
  * :317-319, bilinear resize to 128x128 :323, 2x2 mean to 64x64 + mask
@@ -71,13 +78,15 @@ int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com /*[B,3]*/,
  *   image path is evaluated in float64 and rounded once at the end.
  * outputs: img [B,1,128,128], label_img [B,1,64,64], mask [B,1,64,64],
  *   box_size [B], cube_size [B], com_out [B,3] (int(u), int(v), z) all f32;
- *   valid [B] u8 = 0 where the reference raises (empty crop). */
+ *   valid [B] u8 = 0 where the reference raises (empty crop).
+ *   workspace: >= pwr_sfr_workspace_bytes(B, 0) bytes, 16-byte aligned. */
 int pwr_sfr_crop(const float* frames, int Hf, int Wf,
                  const double* com, const double* cube, double fx, double fy,
                  int frame_f64,
                  float* img, float* label_img, float* mask,
                  float* box_size, float* cube_size, float* com_out,
-                 uint8_t* valid, int B, void* stream);
+                 uint8_t* valid, void* workspace, size_t workspace_size,
+                 int B, void* stream);
 
 /* Train-mode SFR (the 9-tuple of datasets.py:403): everything pwr_sfr_crop
  * does plus uvd normalisation :350-353,381-383, heat-map coordinates
@@ -87,14 +96,16 @@ int pwr_sfr_crop(const float* frames, int Hf, int Wf,
  *   uvd [B,J,3] f64 joint pixel coordinates + depth.
  * extra outputs: uvd_norm [B,J,3], heatmaps [B,J,64,64], dmap [B,J,64,64] f32;
  *   valid [B] u8 = 0 where the reference raises (empty crop, heat-map index
- *   out of range, NaN, sum(mask) < 10). */
+ *   out of range, NaN, sum(mask) < 10).
+ *   workspace: >= pwr_sfr_workspace_bytes(B, J) bytes, 16-byte aligned. */
 int pwr_sfr_build(const float* frames, int Hf, int Wf,
                   const double* com, const double* cube, const double* uvd,
                   double fx, double fy, int frame_f64,
                   float* img, float* label_img, float* mask,
                   float* box_size, float* cube_size, float* com_out,
                   float* uvd_norm, float* heatmaps, float* dmap,
-                  uint8_t* valid, int B, int J, void* stream);
+                  uint8_t* valid, void* workspace, size_t workspace_size,
+                  int B, int J, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Differentiable decoder

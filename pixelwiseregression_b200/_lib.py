@@ -21,14 +21,16 @@ _I = ctypes.c_int
 _D = ctypes.c_double
 _F = ctypes.c_float
 _LL = ctypes.c_longlong
+_SZ = ctypes.c_size_t
 
 # name -> argtypes, exactly the prototypes of include/pwr.h
 SIGNATURES = {
     "pwr_version": [],
     "pwr_error_string": [_I],
     "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
-    "pwr_sfr_crop": [_P, _I, _I, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
-    "pwr_sfr_build": [_P, _I, _I, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "pwr_sfr_workspace_bytes": [_I, _I],
+    "pwr_sfr_crop": [_P, _I, _I, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
+    "pwr_sfr_build": [_P, _I, _I, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _I, _P],
     "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _P],
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _P],
     "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _P],
@@ -58,7 +60,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_char_p if name == "pwr_error_string" else _I
+        fn.restype = {"pwr_error_string": ctypes.c_char_p, "pwr_sfr_workspace_bytes": _SZ}.get(name, _I)
     _lib = lib
     return lib
 

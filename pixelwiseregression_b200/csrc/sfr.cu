@@ -1,25 +1,32 @@
 // SFR (Spatial-Form Representation) target builder for sm_100a.
 //
-// One launch turns raw depth frames + joint annotations into the reference's
-// training tuple (datasets.py:301-403): crop / window / centre / resize the
-// depth frame, build the label image and mask, render per-joint Gaussian heat
-// maps and depth maps.  In the reference this is ~40-60 ms of NumPy/OpenCV per
-// sample inside DataLoader workers.
+// Turns raw depth frames + joint annotations into the reference's training
+// tuple (datasets.py:301-403): crop / window / centre / resize the depth frame,
+// build the label image and mask, render per-joint Gaussian heat maps and depth
+// maps.  In the reference this is ~40-60 ms of NumPy/OpenCV per sample inside
+// DataLoader workers.
 //
-// Decomposition: a sample is split into kBands horizontal bands of the label
-// image; one CTA per band, the kBands CTAs of a sample form a thread-block
-// cluster.  Each CTA
-//   0. derives the sample geometry (thread 0, float64, reference op order) and
-//      the per-joint splat taps (threads 0..J-1) into shared memory,
-//   1. resamples its 2*R x 128 image rows straight from the frame in HBM
-//      (window + centring applied per tap), writes img, label, mask, and keeps
-//      the un-normalised label band in shared memory,
-//   2. writes its R rows of every joint's heat map and depth map: 128-bit
-//      zero stores outside the <= 8x8 support, float64 evaluation inside.
-// The per-sample reject gate (sum(mask) < 10, NaN; datasets.py:385-390) needs a
-// reduction over the bands: each CTA pushes its count into rank 0's shared
-// memory (distributed shared memory, red.shared::cluster) and arrives on rank
-// 0's mbarrier; only rank 0's thread 0 ever waits.
+// Two kernels per call, sharing a caller-provided workspace:
+//   sfr_prep_kernel   one warp per sample: lane 0 derives the crop geometry,
+//                     lanes 0..J-1 the splat taps of one joint each, all in
+//                     float64 with the reference's operation order; writes the
+//                     scalar outputs (box, cube, int CoM, normalised uvd) and
+//                     zeroes the sample's gate counter.  Dependent float64
+//                     division chains are latency-, not throughput-limited, so
+//                     they are done ONCE per sample here instead of stalling
+//                     every CTA of the main kernel.
+//   sfr_build_kernel  kBands CTAs per sample, one per horizontal band of the
+//                     label image.  Each CTA (a) streams zeros over its band
+//                     of all 2J maps with 128-bit stores while the prepared
+//                     geometry is fetched, (b) resamples its 2*R x 128 image
+//                     rows straight from the frame in HBM (window + centring
+//                     per tap), writes img / label / mask and keeps the
+//                     un-normalised label band in shared memory, (c) patches
+//                     the <= 8x8 float64 footprint of every joint that touches
+//                     the band.  The per-sample reject gate (sum(mask) < 10,
+//                     NaN; datasets.py:385-390) is one packed atomicAdd per
+//                     CTA on the sample's counter; the CTA that arrives last
+//                     writes `valid`.
 //
 // Arithmetic contract (bit-level where the result is discontinuous):
 //   * crop box, int CoM, slice extents: float64 with explicit _rn intrinsics
@@ -29,14 +36,11 @@
 //     un-fused multiplies/adds; 2x2 mean; mask = (label != 0).
 //   * joints, splat taps, Gaussian (cv::getGaussianKernel(7,1.5) constants,
 //     BORDER_REFLECT_101) and Dmap in float64, rounded to float32 at the store.
-#include <cooperative_groups.h>
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace pwr {
 
-constexpr int kBands = 4;                       // CTAs (= cluster size) per sample
+constexpr int kBands = 4;                       // CTAs per sample
 constexpr int kBandRows = kLabel / kBands;      // label rows per CTA
 constexpr int kLabelIters = kBandRows * kLabel / kThreads;
 
@@ -219,6 +223,10 @@ struct SfrArgs {
     float* uvd_norm; float* heatmaps; float* dmap;
     uint8_t* valid;
     int B, J;
+    SampleGeom* prep_geom;      // workspace: [B]
+    JointParam* prep_joints;    // workspace: [B*J]
+    int* prep_flags;            // workspace: [B] joints_bad
+    unsigned int* gate;         // workspace: [B] packed (bands arrived << 24 | NaN << 16 | mask count)
 };
 
 // Bilinear taps of one 2x2 image block (one label pixel), gathered from the frame with the
@@ -254,17 +262,57 @@ __device__ __forceinline__ void resample_block(T (&px)[2][2], const float* __res
     }
 }
 
-// remote (cluster) shared-memory helpers for the per-sample reject gate
-__device__ __forceinline__ uint32_t cluster_addr_of_rank(const void* smem_ptr, uint32_t rank) {
-    uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr)), remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
-    return remote;
+// ---------------------------------------------------------------------------
+// prep: per-sample geometry + per-joint taps, once per sample
+// ---------------------------------------------------------------------------
+constexpr int kPrepThreads = 128;                 // 4 samples (warps) per CTA
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kPrepThreads)
+sfr_prep_kernel(SfrArgs a) {
+    const int b = blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= a.B) return;
+    SampleGeom* gp = a.prep_geom + b;
+    if (lane == 0) {
+        SampleGeom g;
+        sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf);
+        *gp = g;
+        a.gate[b] = 0u;
+        a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
+        a.cube_size[b] = static_cast<float>(g.cube);
+        a.com_out[3 * b + 0] = static_cast<float>(g.c0);
+        a.com_out[3 * b + 1] = static_cast<float>(g.r0);
+        a.com_out[3 * b + 2] = static_cast<float>(g.z);
+    }
+    __syncwarp();
+    if (TRAIN) {
+        const SampleGeom g = *gp;
+        int bad = 0;
+        for (int j = lane; j < a.J; j += 32) {
+            float* un = a.uvd_norm + (static_cast<size_t>(b) * a.J + j) * 3;
+            JointParam jp;
+            if (g.ok) {
+                joint_param(jp, un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, g);
+            } else {
+                jp.ok = 0; jp.cd = 0.0; jp.tx0 = jp.tx1 = jp.ty0 = jp.ty1 = 0;
+                jp.tap[0] = jp.tap[1] = jp.tap[2] = jp.tap[3] = 0.0;
+                un[0] = 0.f; un[1] = 0.f; un[2] = 0.f;
+            }
+            bad |= jp.ok ? 0 : 1;
+            a.prep_joints[static_cast<size_t>(b) * a.J + j] = jp;
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) a.prep_flags[b] = bad;
+    }
 }
 
+// ---------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------
 template <typename T, bool TRAIN>
 __global__ void __launch_bounds__(kThreads)
 sfr_build_kernel(SfrArgs a) {
-    cg::cluster_group cluster = cg::this_cluster();
     __shared__ SampleGeom geom;
     __shared__ JointParam joints[TRAIN ? PWR_MAX_JOINTS : 1];
     __shared__ TapX xtap[kImage];
@@ -272,59 +320,33 @@ sfr_build_kernel(SfrArgs a) {
     __shared__ T label_s[kBandRows * kLabel];
     __shared__ int band_list[TRAIN ? PWR_MAX_JOINTS : 1];   // joints whose footprint touches this band
     __shared__ int band_list_n;
-    __shared__ int joints_bad;                              // some joint is out of range / NaN
     __shared__ int band_flags[2];                           // [0] mask count, [1] NaN seen (this CTA)
-    // rank 0 only: totals pushed by all bands of the sample + the barrier they arrive on
-    __shared__ int sample_flags[2];
-    __shared__ __align__(8) uint64_t sample_bar;
 
-    const int band = static_cast<int>(cluster.block_rank());
+    const int band = blockIdx.x % kBands;
     const int b = blockIdx.x / kBands;
     const int tid = threadIdx.x;
     const int y_lo = band * kBandRows, y_hi = y_lo + kBandRows;
+    static_assert(sizeof(SampleGeom) % 4 == 0 && sizeof(JointParam) % 4 == 0, "word copies");
 
-    if (tid == 0) {
-        band_list_n = 0; joints_bad = 0; band_flags[0] = 0; band_flags[1] = 0;
-        if (band == 0) {
-            sample_flags[0] = 0; sample_flags[1] = 0;
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
-                             static_cast<uint32_t>(__cvta_generic_to_shared(&sample_bar))), "r"(kBands) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-    }
-    // phase 0 of the cluster barrier: "rank 0's gate state is initialised"; waited for (by then
-    // long complete) right before a band pushes its totals
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-
-    // ---- prologue: warp 0 derives the sample geometry (thread 0) and the joint taps (one lane
-    // per joint) in float64 while warps 1..7 already stream the zeros of phase 2 (pass A): a
-    // heat map is zero outside the <= 8x8 footprint of the blurred 4-tap splat, and so is the
-    // depth map, so every map band is zero-filled with 128-bit stores and patched later.
-    if (tid < 32) {
-        if (tid == 0) sample_geometry(geom, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf);
-        __syncwarp();
+    // ---- prologue: fetch the prepared geometry / joint taps (L2-resident, written by the prep
+    // kernel) into shared memory with coalesced word loads ...
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.prep_geom + b);
+        if (tid < static_cast<int>(sizeof(SampleGeom) / 4)) reinterpret_cast<uint32_t*>(&geom)[tid] = __ldcg(src + tid);
         if (TRAIN) {
-            for (int j = tid; j < a.J; j += 32) {
-                float* un = (band == 0) ? a.uvd_norm + (static_cast<size_t>(b) * a.J + j) * 3 : nullptr;
-                JointParam& jp = joints[j];
-                if (geom.ok) {
-                    joint_param(jp, un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, geom);
-                } else {
-                    jp.ok = 0;
-                    if (un != nullptr) { un[0] = 0.f; un[1] = 0.f; un[2] = 0.f; }
-                }
-                if (!jp.ok) {
-                    joints_bad = 1;
-                } else if ((jp.ty0 + 3 >= y_lo && jp.ty0 - 3 < y_hi) || (jp.ty1 + 3 >= y_lo && jp.ty1 < y_hi)) {
-                    band_list[atomicAdd(&band_list_n, 1)] = j;       // rows ty0-3..ty0+3 or ty1..ty1+3 hit the band
-                }
-            }
+            const uint32_t* js = reinterpret_cast<const uint32_t*>(a.prep_joints + static_cast<size_t>(b) * a.J);
+            const int words = a.J * static_cast<int>(sizeof(JointParam) / 4);
+            for (int i = tid; i < words; i += kThreads) reinterpret_cast<uint32_t*>(joints)[i] = __ldcg(js + i);
         }
-    } else if (TRAIN) {
-        // 7 warps x (joints warp-1, warp+6, ...) x 2 maps x 256 float4 of zeros per band
+        if (tid == 0) { band_list_n = 0; band_flags[0] = 0; band_flags[1] = 0; }
+    }
+    // ... while pass A of phase 2 streams the zeros: a heat map is zero outside the <= 8x8
+    // footprint of the blurred 4-tap splat, and so is the depth map, so every map band is
+    // zero-filled with 128-bit stores here and patched after phase 1.
+    if (TRAIN) {
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const size_t band_off = static_cast<size_t>(b) * a.J * kMap + y_lo * kLabel + (tid & 31) * 4;
-        for (int j = (tid >> 5) - 1; j < a.J; j += kWarps - 1) {
+        for (int j = tid >> 5; j < a.J; j += kWarps) {
             float* hp = a.heatmaps + band_off + static_cast<size_t>(j) * kMap;
             float* dp = a.dmap + band_off + static_cast<size_t>(j) * kMap;
 #pragma unroll
@@ -340,6 +362,11 @@ sfr_build_kernel(SfrArgs a) {
         if (tid < kImage) xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);
         else if (tid < kImage + 2 * kBandRows)
             ytap[tid - kImage] = linear_tap(band * 2 * kBandRows + (tid - kImage), g.nrows, g.scale_y);
+        if (TRAIN && tid < a.J) {
+            const JointParam& jp = joints[tid];                     // rows ty0-3..ty0+3 or ty1..ty1+3 hit the band?
+            if (jp.ok && ((jp.ty0 + 3 >= y_lo && jp.ty0 - 3 < y_hi) || (jp.ty1 + 3 >= y_lo && jp.ty1 < y_hi)))
+                band_list[atomicAdd(&band_list_n, 1)] = tid;
+        }
     }
     __syncthreads();
 
@@ -391,15 +418,18 @@ sfr_build_kernel(SfrArgs a) {
     }
     __syncthreads();                                      // label_s and band_flags complete
 
-    // ---- per-sample reject gate: every band pushes its totals into rank 0's shared memory and
-    // arrives on rank 0's mbarrier; bands 1..3 never wait for anybody (push, not pull).
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // rank 0 initialised its gate
+    // ---- per-sample reject gate: one packed atomicAdd per band; the band that arrives last
+    // sees the totals of all kBands bands and writes `valid` (datasets.py:362-365, 385-390)
     if (tid == 0) {
-        const uint32_t rflags = cluster_addr_of_rank(sample_flags, 0);
-        const uint32_t rbar = cluster_addr_of_rank(&sample_bar, 0);
-        asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(rflags), "r"(band_flags[0]) : "memory");
-        asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(rflags + 4), "r"(band_flags[1]) : "memory");
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+        const unsigned int mine = (1u << 24) | (band_flags[1] ? (1u << 16) : 0u) | static_cast<unsigned int>(band_flags[0]);
+        const unsigned int total = atomicAdd(a.gate + b, mine) + mine;
+        if ((total >> 24) == static_cast<unsigned int>(kBands)) {
+            const int count = static_cast<int>(total & 0xffffu);        // <= 4096
+            const bool nan_seen = ((total >> 16) & 0xffu) != 0;
+            uint8_t v = g.ok ? 1 : 0;
+            if (TRAIN) v = (g.ok && !a.prep_flags[b] && !nan_seen && count >= 10) ? 1 : 0;
+            a.valid[b] = v;
+        }
     }
 
     // ---- phase 2, pass B: the <= 8x8 footprint of every joint that touches this band, float64
@@ -432,30 +462,6 @@ sfr_build_kernel(SfrArgs a) {
             if (h > 0.0 && lab != T(0))
                 a.dmap[o] = __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube));
         }
-    }
-
-    if (band == 0 && tid == 0) {
-        // all kBands bands (this one included) have pushed: phase 0 of sample_bar completes
-        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&sample_bar));
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "GATE_WAIT:\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
-            "@P1 bra GATE_DONE;\n"
-            "bra GATE_WAIT;\n"
-            "GATE_DONE:\n"
-            "}" ::"r"(bar), "r"(0) : "memory");
-        const int count = *reinterpret_cast<volatile int*>(&sample_flags[0]);
-        const int nan_seen = *reinterpret_cast<volatile int*>(&sample_flags[1]);
-        uint8_t v = g.ok ? 1 : 0;
-        if (TRAIN) v = (g.ok && !joints_bad && !nan_seen && count >= 10) ? 1 : 0;   // datasets.py:362-365,385-390
-        a.valid[b] = v;
-        a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
-        a.cube_size[b] = static_cast<float>(g.cube);
-        a.com_out[3 * b + 0] = static_cast<float>(g.c0);
-        a.com_out[3 * b + 1] = static_cast<float>(g.r0);
-        a.com_out[3 * b + 2] = static_cast<float>(g.z);
     }
 }
 
@@ -502,22 +508,29 @@ sfr_com_kernel(const float* __restrict__ frames, int Hf, int Wf, double* __restr
     }
 }
 
+// workspace layout: [B] SampleGeom | [B*J] JointParam | [B] int joints_bad | [B] u32 gate
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static size_t workspace_bytes(int B, int J) {
+    return align_up(sizeof(SampleGeom) * static_cast<size_t>(B), 256) +
+           align_up(sizeof(JointParam) * static_cast<size_t>(B) * (J > 0 ? J : 0), 256) +
+           align_up(sizeof(int) * static_cast<size_t>(B), 256) + align_up(sizeof(unsigned int) * static_cast<size_t>(B), 256);
+}
+static void carve_workspace(SfrArgs& a, void* ws) {
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    a.prep_geom = reinterpret_cast<SampleGeom*>(p);
+    p += align_up(sizeof(SampleGeom) * static_cast<size_t>(a.B), 256);
+    a.prep_joints = reinterpret_cast<JointParam*>(p);
+    p += align_up(sizeof(JointParam) * static_cast<size_t>(a.B) * a.J, 256);
+    a.prep_flags = reinterpret_cast<int*>(p);
+    p += align_up(sizeof(int) * static_cast<size_t>(a.B), 256);
+    a.gate = reinterpret_cast<unsigned int*>(p);
+}
+
 template <typename T, bool TRAIN>
 static int launch_sfr(const SfrArgs& a, cudaStream_t stream) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(a.B) * kBands, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kBands;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, sfr_build_kernel<T, TRAIN>, a);
-    if (err != cudaSuccess) { cudaGetLastError(); return static_cast<int>(err); }
+    sfr_prep_kernel<TRAIN><<<(a.B + kPrepThreads / 32 - 1) / (kPrepThreads / 32), kPrepThreads, 0, stream>>>(a);
+    if (int rc = launch_status()) return rc;
+    sfr_build_kernel<T, TRAIN><<<static_cast<unsigned>(a.B) * kBands, kThreads, 0, stream>>>(a);
     return launch_status();
 }
 
@@ -531,6 +544,11 @@ static int check_frames(int Hf, int Wf, int B) {
 
 using namespace pwr;
 
+extern "C" size_t pwr_sfr_workspace_bytes(int B, int J) {
+    if (B < 0 || J < 0 || J > PWR_MAX_JOINTS) return 0;
+    return workspace_bytes(B, J);
+}
+
 extern "C" int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com, int B, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
     if (B == 0) return 0;
@@ -541,15 +559,18 @@ extern "C" int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com, int
 
 extern "C" int pwr_sfr_crop(const float* frames, int Hf, int Wf, const double* com, const double* cube, double fx,
                             double fy, int frame_f64, float* img, float* label_img, float* mask, float* box_size,
-                            float* cube_size, float* com_out, uint8_t* valid, int B, void* stream) {
+                            float* cube_size, float* com_out, uint8_t* valid, void* workspace, size_t workspace_size,
+                            int B, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
     if (B == 0) return 0;
     if (frames == nullptr || com == nullptr || cube == nullptr || box_size == nullptr || cube_size == nullptr ||
         com_out == nullptr || valid == nullptr)
         return PWR_E_NULL;
-    PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
+    PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask); PWR_REQUIRE_PTR(workspace);
+    if (workspace_size < workspace_bytes(B, 0)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
-                 nullptr, nullptr, nullptr, valid, B, 0};
+                 nullptr, nullptr, nullptr, valid, B, 0, nullptr, nullptr, nullptr, nullptr};
+    carve_workspace(a, workspace);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return frame_f64 ? launch_sfr<double, false>(a, s) : launch_sfr<float, false>(a, s);
 }
@@ -557,17 +578,20 @@ extern "C" int pwr_sfr_crop(const float* frames, int Hf, int Wf, const double* c
 extern "C" int pwr_sfr_build(const float* frames, int Hf, int Wf, const double* com, const double* cube,
                              const double* uvd, double fx, double fy, int frame_f64, float* img, float* label_img,
                              float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
-                             float* heatmaps, float* dmap, uint8_t* valid, int B, int J, void* stream) {
+                             float* heatmaps, float* dmap, uint8_t* valid, void* workspace, size_t workspace_size,
+                             int B, int J, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
-    if (B == 0) return 0;
     if (J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
+    if (B == 0) return 0;
     if (frames == nullptr || com == nullptr || cube == nullptr || uvd == nullptr || box_size == nullptr ||
         cube_size == nullptr || com_out == nullptr || uvd_norm == nullptr || valid == nullptr)
         return PWR_E_NULL;
     PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
-    PWR_REQUIRE_PTR(heatmaps); PWR_REQUIRE_PTR(dmap);
+    PWR_REQUIRE_PTR(heatmaps); PWR_REQUIRE_PTR(dmap); PWR_REQUIRE_PTR(workspace);
+    if (workspace_size < workspace_bytes(B, J)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
-                 uvd_norm, heatmaps, dmap, valid, B, J};
+                 uvd_norm, heatmaps, dmap, valid, B, J, nullptr, nullptr, nullptr, nullptr};
+    carve_workspace(a, workspace);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return frame_f64 ? launch_sfr<double, true>(a, s) : launch_sfr<float, true>(a, s);
 }

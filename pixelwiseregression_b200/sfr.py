@@ -73,11 +73,14 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     com_out = torch.empty(B, 3, **f32)
     valid = torch.empty(B, device=dev, dtype=torch.uint8)
     s = stream_ptr(dev)
+    J = 0 if (test_only or uvd is None) else int(uvd.shape[1])
+    ws_bytes = int(lib.pwr_sfr_workspace_bytes(B, J))
+    workspace = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)     # scratch, no init needed
     if test_only:
         with torch.cuda.device(dev), _lib.timed("pwr_sfr_crop"):
             rc = lib.pwr_sfr_crop(ptr(frames), Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
                                   ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
-                                  ptr(valid), B, s)
+                                  ptr(valid), ptr(workspace), ws_bytes, B, s)
         check(rc, "pwr_sfr_crop")
         return SFRTestBatch(img, label_img, mask, box_size, cube_size, com_out, valid)
     if uvd is None:
@@ -92,6 +95,7 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     with torch.cuda.device(dev), _lib.timed("pwr_sfr_build"):
         rc = lib.pwr_sfr_build(ptr(frames), Hf, Wf, ptr(com), ptr(cube), ptr(uvd), float(fx), float(fy),
                                int(frame_f64), ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
-                               ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), B, J, s)
+                               ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), ptr(workspace),
+                               ws_bytes, B, J, s)
     check(rc, "pwr_sfr_build")
     return SFRBatch(img, label_img, mask, box_size, cube_size, com_out, uvd_norm, heatmaps, dmap, valid)

@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-samples", type=int, default=512, help="samples in the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager decoder baseline on the GPU")
     return ap.parse_args()
 
 
@@ -156,6 +157,48 @@ def run_reference(args):
     print(json.dumps(line), file=OUT, flush=True)
 
 
+def eager_decoder_baseline(z, D, w, batch, alpha, lambda_h, lambda_d, iters=5):
+    """model.py:83-95, 123-130, 151 and train.py:197-207 written as the reference writes them
+    (eager PyTorch, autograd backward), timed with CUDA events on the same GPU."""
+    import torch
+    from torch.functional import F
+    B, J, H, W = z.shape
+    idx = torch.arange(W, device=z.device, dtype=torch.float64)
+    coord = ((idx - W // 2) / (W - 1)).float()
+    U = coord.view(1, 1, 1, W)
+    V = coord.view(1, 1, H, 1)
+
+    def one():
+        zz = z.detach().requires_grad_(True)
+        DD = D.detach().requires_grad_(True)
+        ww = w.detach().requires_grad_(True)
+        heat = F.softmax(ww * zz.view(B, J, -1), dim=2).view(B, J, H, W)
+        u = torch.sum(U * heat, dim=(2, 3)).unsqueeze(-1)
+        v = torch.sum(V * heat, dim=(2, 3)).unsqueeze(-1)
+        rec = DD + batch.label_img
+        mr = batch.mask * rec
+        mh = heat * batch.mask
+        d = (torch.sum(mh * mr, dim=(2, 3)) / (torch.sum(mh, dim=(2, 3)) + 1e-14)).unsqueeze(-1)
+        uvd_out = torch.cat([torch.cat([u, v], dim=2), d], dim=2)
+        hl = lambda_h * torch.mean(torch.sum((heat - batch.heatmaps) ** 2, dim=(2, 3)))
+        dl = lambda_d * torch.mean(torch.sum((DD - batch.depthmaps) ** 2, dim=(2, 3)))
+        ul = torch.mean(torch.sum((uvd_out - batch.uvd) ** 2, dim=2))
+        (alpha * ul + (1 - alpha) * (hl + dl)).backward()
+
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        one()
+    e.record()
+    torch.cuda.synchronize()
+    return {"ms": s.elapsed_time(e) / iters, "iters": iters,
+            "what": "reference decoder + loss lines (model.py:83-95,123-130,151; train.py:197-207) as eager "
+                    "PyTorch ops with autograd backward, same GPU, same inputs"}
+
+
 # --------------------------------------------------------------------------- #
 # B200 arm
 # --------------------------------------------------------------------------- #
@@ -228,7 +271,7 @@ def run_b200(args):
     end.record()
     barrier()
     elapsed_ms = start.elapsed_time(end)
-    launches = _lib.launch_count() - launches0
+    launches = (_lib.launch_count() - launches0) * world      # every rank launches the same sequence
     prof, _lib.PROFILE = _lib.PROFILE, None
     clocks = sampler.summary()
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -296,6 +339,18 @@ def run_b200(args):
                "note": "per rank and step: frames+com+cube+uvd+z+D copied from pinned host memory, "
                        "loss[4]+uvd[B,J,3] read back; wall clock with device sync, max over ranks"}
 
+    # ---- GPU baseline of configs[1] ("vs reference PyTorch path"): the reference's decoder + loss
+    # lines as plain eager PyTorch ops on the same GPU and inputs (the SFR builder has no GPU
+    # reference: upstream it is CPU-only) ----
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        batch = sfr.build_sfr(frames, com, cube, uvd, fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
+        gpu_eager = eager_decoder_baseline(z, D, w, batch, alpha, lambda_h, lambda_d)
+        gpu_eager["fused_ms"] = kernels["pwr_decoder_fwd"]["avg_ms"] + kernels["pwr_decoder_bwd_loss"]["avg_ms"]
+        gpu_eager["speedup"] = gpu_eager["ms"] / gpu_eager["fused_ms"]
+        del batch
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline: oracle port on the host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,6 +382,7 @@ def run_b200(args):
             "host_issue_ms_per_step": issue_ms,
             "between_kernels_ms_per_step": gap_ms,
             "cpu_baseline": cpu,
+            "gpu_eager_decoder": gpu_eager,
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(traffic_file):

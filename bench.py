@@ -46,6 +46,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--shape", default="NYU")
     ap.add_argument("--alpha", type=float, default=1.0)
+    ap.add_argument("--frame-format", default="f32", choices=["f32", "nyu_gb16", "u16"],
+                    help="f32 = decoded frames (what process_single_data receives, default); nyu_gb16 / u16 = raw "
+                         "sensor samples decoded inside the SFR kernel (SURVEY 8f-1), with the load_from_text "
+                         "hand rectangle applied in the crop taps")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--cpu-samples", type=int, default=512, help="samples in the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -229,10 +233,15 @@ def run_b200(args):
     D = torch.randn(B, J, 64, 64, device=dev, generator=g).requires_grad_(True)
     w = (torch.rand(J, 1, device=dev, generator=g) + 0.5).requires_grad_(True)
     frames, com, cube, uvd = d["frames"], d["com"], d["cube"], d["uvd"]
+    sfr_kw = dict(fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
+    if args.frame_format != "f32":
+        frames = frames.round().clamp_(0, 65535).to(torch.int32).to(torch.uint16)      # sensor counts (mm)
+        sfr_kw.update(frame_format=args.frame_format, prefilter=(40.0, shape.halfu, shape.halfv), frame_f64=False)
+        d["frames"] = frames
 
     def step(frames_, com_, cube_, uvd_, z_, D_):
         """The public-API call sequence a training loop makes for this path."""
-        batch = sfr.build_sfr(frames_, com_, cube_, uvd_, fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
+        batch = sfr.build_sfr(frames_, com_, cube_, uvd_, **sfr_kw)
         total, terms, uvd_out, _ = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, batch.heatmaps,
                                                           batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
                                                           lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)
@@ -344,7 +353,7 @@ def run_b200(args):
     # reference: upstream it is CPU-only) ----
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_gpu_eager:
-        batch = sfr.build_sfr(frames, com, cube, uvd, fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
+        batch = sfr.build_sfr(frames, com, cube, uvd, **sfr_kw)
         gpu_eager = eager_decoder_baseline(z, D, w, batch, alpha, lambda_h, lambda_d)
         gpu_eager["fused_ms"] = kernels["pwr_decoder_fwd"]["avg_ms"] + kernels["pwr_decoder_bwd_loss"]["avg_ms"]
         gpu_eager["speedup"] = gpu_eager["ms"] / gpu_eager["fused_ms"]
@@ -366,9 +375,10 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(shape, B), "batch_per_gpu": B, "joints": J,
+                       "frame_format": args.frame_format,
                        "alpha": alpha, "lambda_h": lambda_h, "lambda_d": lambda_d,
                        "l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
-                             % (frames.numel() * 4 / 1e9, z.numel() * 4 / 1e9),
+                             % (frames.numel() * frames.element_size() / 1e9, z.numel() * 4 / 1e9),
                        "algorithmic_bytes_per_sample": roofline.step_bytes(J)},
             "clocks": clocks,
             "e2e": e2e,

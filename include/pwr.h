@@ -63,6 +63,16 @@ const char* pwr_error_string(int rc);
 int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com /*[B,3]*/,
                 int B, void* stream);
 
+/* Frame formats (raw sensor frames can be fed directly).  The
+ * float32 value the reference would hold after plt.imread + its decode line is
+ * reproduced bit for bit. */
+#define PWR_FRAME_F32   0   /* decoded float32 depth in mm (what
+                               process_single_data receives)                */
+#define PWR_FRAME_GB16  1   /* NYU PNG: uint16 = G << 8 | B; depth =
+                               ((G/255)*256 + B/255)*255, datasets.py:810   */
+#define PWR_FRAME_U16   2   /* 16-bit grey PNG (ICVL :632, HAND17 :940):
+                               (v/65535)*65535                              */
+
 /* Bytes of caller-allocated device scratch pwr_sfr_crop (J = 0) / pwr_sfr_build
  * need: per-sample crop geometry and per-joint splat taps prepared once per
  * sample, plus the counter of the per-sample reject gate.  Contents need no
@@ -73,16 +83,23 @@ size_t pwr_sfr_workspace_bytes(int B, int J);
  * center_crop utils.py:167-173, depth window + centring :312-315, int CoM
  * :317-319, bilinear resize to 128x128 :323, 2x2 mean to 64x64 + mask
  * :330-332, /cube normalisation :337-338.
- *   frames [B,Hf,Wf] f32; com [B,3] f64 (u,v,z); cube [B] f64;
+ *   frames [B,Hf,Wf] in `frame_format`; com [B,3] f64 (u,v,z); cube [B] f64;
+ *   prefilter_margin >= 0 applies the hand rectangle of load_from_text
+ *   (datasets.py:841-853 NYU / :956-968 HAND17 margin 40, :666-678 ICVL margin
+ *   30): pixels outside MM[top:buttom, left:right] read as 0, with
+ *   prefilter_umax = 2*halfu, prefilter_vmax = 2*halfv; < 0 = off.  (The depth
+ *   window of :855-857 is the same predicate as :312 and idempotent.)
  *   frame_f64 != 0: the reference held the frame as float64 (MSRA), so the
  *   image path is evaluated in float64 and rounded once at the end.
  * outputs: img [B,1,128,128], label_img [B,1,64,64], mask [B,1,64,64],
  *   box_size [B], cube_size [B], com_out [B,3] (int(u), int(v), z) all f32;
  *   valid [B] u8 = 0 where the reference raises (empty crop).
  *   workspace: >= pwr_sfr_workspace_bytes(B, 0) bytes, 16-byte aligned. */
-int pwr_sfr_crop(const float* frames, int Hf, int Wf,
+int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf,
                  const double* com, const double* cube, double fx, double fy,
                  int frame_f64,
+                 double prefilter_margin, double prefilter_umax,
+                 double prefilter_vmax,
                  float* img, float* label_img, float* mask,
                  float* box_size, float* cube_size, float* com_out,
                  uint8_t* valid, void* workspace, size_t workspace_size,
@@ -98,9 +115,11 @@ int pwr_sfr_crop(const float* frames, int Hf, int Wf,
  *   valid [B] u8 = 0 where the reference raises (empty crop, heat-map index
  *   out of range, NaN, sum(mask) < 10).
  *   workspace: >= pwr_sfr_workspace_bytes(B, J) bytes, 16-byte aligned. */
-int pwr_sfr_build(const float* frames, int Hf, int Wf,
+int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
                   const double* com, const double* cube, const double* uvd,
                   double fx, double fy, int frame_f64,
+                  double prefilter_margin, double prefilter_umax,
+                  double prefilter_vmax,
                   float* img, float* label_img, float* mask,
                   float* box_size, float* cube_size, float* com_out,
                   float* uvd_norm, float* heatmaps, float* dmap,

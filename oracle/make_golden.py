@@ -172,6 +172,67 @@ def golden_edge(datasets):
         print("  edge: valid=%d  %s" % (v, n))
 
 
+def golden_raw(datasets, name, shape, frame_format, margin, batch, seed, val_mode=False):
+    """Raw sensor frames through the reference's OWN load_from_text (PNG decode line, hand
+    rectangle, depth window; NYU datasets.py:797-859, HAND17 :925-972, ICVL :626-690) and then
+    its process_single_data.  plt.imread is the only stand-in: matplotlib is not installed, so
+    it is replaced by its documented conversion (oracle.sfr_oracle.imread_float) over in-memory
+    PNG sample arrays."""
+    from oracle import sfr_oracle as so
+    d = synth.make_frames(shape, batch, seed, mixed_cube=False)
+    raw = np.clip(np.rint(d["frames"]), 0, 65535).astype(np.uint16)          # sensor counts (mm)
+    store = {}
+    cls = {"NYU": datasets.NYUDataset, "HAND17": datasets.HAND17Dataset, "ICVL": datasets.ICVLDataset}[shape.name]
+    ds = object.__new__(cls)
+    ds.fx, ds.fy, ds.halfu, ds.halfv = shape.fx, shape.fy, shape.halfu, shape.halfv
+    ds.cube_size, ds.path = int(shape.cube), "/synthetic"
+    ds.dataset = "val" if val_mode else "train"
+    first = 2500 if val_mode else 0          # NYU val index > 2440 -> int(cube * 5 / 6)
+    centers = np.zeros((first + batch, 3))
+    centers[first:] = d["com"]
+    ds.train_centers = ds.test_centers = centers
+    ds.train_lookup = {}
+    old_imread = getattr(datasets.plt, "imread", None)
+    datasets.plt.imread = lambda path: so.imread_float(store[path])
+    images, uvds, coms, cubes = [], [], [], []
+    try:
+        for b in range(batch):
+            idx = first + b
+            if shape.name == "NYU":
+                path = "/synthetic/train/depth_1_%07d.png" % (idx + 1)
+                rgb = np.zeros(raw[b].shape + (3,), np.uint8)
+                rgb[..., 1] = raw[b] >> 8
+                rgb[..., 2] = raw[b] & 255
+                store[path] = rgb
+                joints = d["uvd"][b]
+            elif shape.name == "HAND17":
+                rel = "image_D%08d.png" % (idx + 1)
+                path = rel
+                store[os.path.join(ds.path, "training", "images", rel)] = raw[b]
+                uvd = d["uvd"][b]                                  # text holds xyz; the loader maps it to uvd
+                joints = uvd.copy()
+                joints[:, 0] = (uvd[:, 0] - ds.halfu) / ds.fx * uvd[:, 2]
+                joints[:, 1] = (uvd[:, 1] - ds.halfv) / ds.fy * uvd[:, 2]
+            else:
+                path = "/synthetic/Training/Depth/seq/image_%04d.png" % idx
+                store[path] = raw[b]
+                ds.train_lookup["/".join(path.split("/")[-2:])] = idx
+                joints = d["uvd"][b]
+            text = path + " " + " ".join(repr(float(x)) for x in joints.reshape(-1))
+            image, joint_uvd, com, cube = ds.load_from_text(text)
+            images.append(image)
+            uvds.append(np.asarray(joint_uvd, dtype=np.float64))
+            coms.append(np.asarray(com, dtype=np.float64))
+            cubes.append(float(ds.cube_size if cube is None else cube))
+    finally:
+        datasets.plt.imread = old_imread
+    res = run_reference_sfr(datasets, shape, images, uvds, coms, cubes)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), raw=raw, uvd=np.stack(uvds), com=np.stack(coms),
+                        cube=np.array(cubes), shape_name=np.array(shape.name), frame_format=np.array(frame_format),
+                        margin=np.float64(margin), test_only=np.array(False), versions=versions(), **res)
+    print(name, "valid", res["ref_valid"].tolist(), "cubes", sorted(set(cubes)))
+
+
 def golden_decoder(model_mod, name, method, B, J, seed, alpha, with_upstream):
     """Reference PlaneRegression/DepthRegression with `.conv` swapped for
     Identity (so the module input is the logit map itself), reference loss
@@ -234,6 +295,10 @@ def main():
     golden_sfr(datasets, "sfr_msra", synth.MSRA, 3, 2)
     golden_sfr(datasets, "sfr_icvl", synth.ICVL, 2, 3)
     golden_edge(datasets)
+    golden_raw(datasets, "sfr_nyu_raw", synth.NYU, "nyu_gb16", 40, 3, 20)
+    golden_raw(datasets, "sfr_nyu_raw_val", synth.NYU, "nyu_gb16", 40, 2, 21, val_mode=True)
+    golden_raw(datasets, "sfr_hand17_raw", synth.HAND17, "u16", 40, 2, 22)
+    golden_raw(datasets, "sfr_icvl_raw", synth.ICVL, "u16", 30, 2, 23)
     golden_decoder(model_mod, "decoder_softmax_a1", "softmax", 2, 3, 10, 1.0, False)
     golden_decoder(model_mod, "decoder_softmax_a05_up", "softmax", 2, 3, 11, 0.5, True)
     golden_decoder(model_mod, "decoder_sum_a05_up", "sum", 2, 3, 12, 0.5, True)

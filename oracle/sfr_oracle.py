@@ -115,6 +115,50 @@ def window_and_centre(crop, com_z, cube):
 
 
 # --------------------------------------------------------------------------- #
+# raw sensor frames: PNG channel decode and the load_from_text prefilter
+# --------------------------------------------------------------------------- #
+def imread_float(png):
+    """matplotlib.pyplot.imread on a PNG (matplotlib is not in the reference tree nor
+    installed here; restated from matplotlib.image._pil_png_to_float_array): 8-bit
+    channels -> float32(v / 255), 16-bit grey -> float32(v / 65535), correctly
+    rounded float32 divisions."""
+    png = np.asarray(png)
+    if png.dtype == np.uint8:
+        return np.divide(png, 2 ** 8 - 1, dtype=np.float32)
+    if png.dtype == np.uint16:
+        return np.divide(png, 2 ** 16 - 1, dtype=np.float32)
+    raise TypeError("PNG sample type %s" % png.dtype)
+
+
+def decode_nyu(rgb_u8):
+    """datasets.py:809-810: depth = (G * 256 + B) * 255 on the float32 channels."""
+    img = imread_float(rgb_u8)
+    return (img[:, :, 1] * 256 + img[:, :, 2]) * 255
+
+
+def decode_u16(grey_u16):
+    """datasets.py:632 (ICVL), :940/:950 (HAND17): plt.imread(path) * 65535."""
+    return imread_float(grey_u16) * 65535
+
+
+def prefilter(image, com, cube, fx, fy, halfu, halfv, margin):
+    """The hand rectangle + depth window of load_from_text (NYU datasets.py:841-857 with
+    margin 40, HAND17 :956-972 margin 40, ICVL :666-681 margin 30).  Python slice
+    semantics (a negative `right` wraps) are the reference's."""
+    du = (cube - margin) / com[2] * fx
+    dv = (cube - margin) / com[2] * fy
+    left = max(int(com[0] - du), 0)
+    top = max(int(com[1] - dv), 0)
+    right = int(min(int(com[0] + du), halfu * 2))
+    buttom = int(min(int(com[1] + dv), halfv * 2))
+    mm = np.zeros_like(image)
+    mm[top:buttom, left:right] = 1
+    image = image * mm
+    keep = np.logical_and(image < com[2] + cube, image > com[2] - cube)
+    return image * keep
+
+
+# --------------------------------------------------------------------------- #
 # OpenCV restatements
 # --------------------------------------------------------------------------- #
 def _linear_taps(dst, src):

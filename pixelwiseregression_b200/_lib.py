@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("PWR_LIB_PATH") or os.path.join(_PKG, "libpwr_b200.so"
 
 METHOD_SOFTMAX, METHOD_SUM, METHOD_GIVEN = 0, 1, 2
 METHODS = {"softmax": METHOD_SOFTMAX, "sum": METHOD_SUM, "given": METHOD_GIVEN}
+FRAME_FORMATS = {"f32": 0, "nyu_gb16": 1, "u16": 2}
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -29,8 +30,9 @@ SIGNATURES = {
     "pwr_error_string": [_I],
     "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
     "pwr_sfr_workspace_bytes": [_I, _I],
-    "pwr_sfr_crop": [_P, _I, _I, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
-    "pwr_sfr_build": [_P, _I, _I, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _I, _P],
+    "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
+    "pwr_sfr_build": [_P, _I, _I, _I, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                      _SZ, _I, _I, _P],
     "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _P],
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _P],
     "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _P],
@@ -65,7 +67,8 @@ def load():
     return lib
 
 
-LAUNCHES = {}          # entry point -> number of successful launches (one kernel each)
+LAUNCHES = {}          # entry point -> number of kernels launched through it
+KERNELS_PER_CALL = {"pwr_sfr_build": 2, "pwr_sfr_crop": 2}    # prep + main; every other entry point is one kernel
 PROFILE = None         # when a list: (entry point, start event, end event) per launch
 
 
@@ -73,7 +76,7 @@ def check(rc, what):
     if rc != 0:
         msg = load().pwr_error_string(rc)
         raise PwrError("%s failed: rc=%d (%s)" % (what, rc, msg.decode() if msg else "?"))
-    LAUNCHES[what] = LAUNCHES.get(what, 0) + 1
+    LAUNCHES[what] = LAUNCHES.get(what, 0) + KERNELS_PER_CALL.get(what, 1)
 
 
 def launch_count():

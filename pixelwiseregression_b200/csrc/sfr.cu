@@ -58,6 +58,8 @@ struct SampleGeom {
     int fr0, fc0;              // frame row / column of crop(0,0) (may be negative)
     int nrows, ncols;          // crop extent (== 2*shift unless truncated)
     int r0, c0;                // int(com_v), int(com_u)
+    int pr0, pr1, pc0, pc1;    // frame rows [pr0,pr1) x cols [pc0,pc1) that may be non-zero: the whole frame,
+                               // or the hand rectangle of load_from_text when the prefilter is on
 };
 
 struct JointParam {
@@ -77,9 +79,19 @@ __device__ __forceinline__ void py_slice(long long start, long long stop, long l
     count = stop > start ? static_cast<int>(stop - start) : 0;
 }
 
-__device__ void sample_geometry(SampleGeom& g, const double* com, double cube, double fx, double fy, int Hf, int Wf) {
+// int(x) for a float64 that may be far outside the int range (Python ints are unbounded; every use
+// below is followed by a clamp to the frame, so saturating first gives the same result)
+__device__ __forceinline__ long long py_int(double x) {
+    if (x > 1.0e12) x = 1.0e12;
+    if (x < -1.0e12) x = -1.0e12;
+    return static_cast<long long>(x);
+}
+
+__device__ void sample_geometry(SampleGeom& g, const double* com, double cube, double fx, double fy, int Hf, int Wf,
+                                double pf_margin, double pf_umax, double pf_vmax) {
     const double cu = com[0], cv = com[1], z = com[2];
     g.z = z; g.cube = cube; g.ok = 0;
+    g.pr0 = 0; g.pr1 = Hf; g.pc0 = 0; g.pc1 = Wf;
     g.fr0 = g.fc0 = 0; g.nrows = g.ncols = 0; g.r0 = g.c0 = 0;
     g.scale_x = g.scale_y = 1.0;
     // datasets.py:306-309
@@ -103,6 +115,23 @@ __device__ void sample_geometry(SampleGeom& g, const double* com, double cube, d
     py_slice(g.c0, static_cast<long long>(g.c0) + 2 * shift, static_cast<long long>(Wf) + 2 * shift, cs, g.ncols);
     g.fr0 = rs - shift;
     g.fc0 = cs - shift;
+    if (pf_margin >= 0.0) {
+        // load_from_text (NYU datasets.py:841-853, HAND17 :956-968, ICVL :666-678): zero everything
+        // outside MM[top:buttom, left:right]; Python slice semantics included
+        const double pdu = __dmul_rn(__ddiv_rn(__dsub_rn(cube, pf_margin), z), fx);
+        const double pdv = __dmul_rn(__ddiv_rn(__dsub_rn(cube, pf_margin), z), fy);
+        long long left = py_int(__dsub_rn(cu, pdu)), right = py_int(__dadd_rn(cu, pdu));
+        long long top = py_int(__dsub_rn(cv, pdv)), buttom = py_int(__dadd_rn(cv, pdv));
+        if (left < 0) left = 0;
+        if (top < 0) top = 0;
+        right = py_int(fmin(static_cast<double>(right), pf_umax));
+        buttom = py_int(fmin(static_cast<double>(buttom), pf_vmax));
+        int first, count;
+        py_slice(top, buttom, Hf, first, count);
+        g.pr0 = first; g.pr1 = first + count;
+        py_slice(left, right, Wf, first, count);
+        g.pc0 = first; g.pc1 = first + count;
+    }
     if (g.nrows == 0 || g.ncols == 0) return;  // cv2.resize raises on an empty crop
     g.scale_y = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(kImage), static_cast<double>(g.nrows)));
     g.scale_x = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(kImage), static_cast<double>(g.ncols)));
@@ -215,7 +244,7 @@ template <> struct Arith<double> {
 };
 
 struct SfrArgs {
-    const float* frames; int Hf, Wf;
+    const void* frames; int Hf, Wf;
     const double* com; const double* cube; const double* uvd;
     double fx, fy;
     float* img; float* label_img; float* mask;
@@ -227,29 +256,50 @@ struct SfrArgs {
     JointParam* prep_joints;    // workspace: [B*J]
     int* prep_flags;            // workspace: [B] joints_bad
     unsigned int* gate;         // workspace: [B] packed (bands arrived << 24 | NaN << 16 | mask count)
+    double pf_margin, pf_umax, pf_vmax;   // load_from_text prefilter: margin < 0 = off; 2*halfu, 2*halfv
 };
+
+// Raw sensor formats.  The float32 value the reference would hold is reproduced bit
+// for bit: plt.imread turns PNG samples into float32(v / 255) resp. float32(v / 65535).
+//   FMT_F32   frames already decoded (what process_single_data receives)
+//   FMT_GB16  NYU: uint16 = G << 8 | B of the PNG;  depth = ((G/255)*256 + B/255)*255, datasets.py:810
+//   FMT_U16   16-bit grey PNG (ICVL :632, HAND17 :940): (v/65535)*65535 == v exactly for all 65536 values
+enum { FMT_F32 = 0, FMT_GB16 = 1, FMT_U16 = 2 };
+
+template <int FMT>
+__device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx) {
+    if (FMT == FMT_F32) return __ldg(static_cast<const float*>(frame) + idx);
+    const unsigned int v = __ldg(static_cast<const unsigned short*>(frame) + idx);
+    if (FMT == FMT_U16) return static_cast<float>(v);
+    // x / 255 correctly rounded through the reciprocal (exact for x = 0..255, checked exhaustively)
+    const float rc = 0x1.010102p-8f;                     // RN(1/255)
+    const float gq = static_cast<float>(v >> 8), bq = static_cast<float>(v & 255u);
+    float g = __fmul_rn(gq, rc); g = __fmaf_rn(__fmaf_rn(-g, 255.f, gq), rc, g);
+    float bl = __fmul_rn(bq, rc); bl = __fmaf_rn(__fmaf_rn(-bl, 255.f, bq), rc, bl);
+    return __fmul_rn(__fadd_rn(__fmul_rn(g, 256.f), bl), 255.f);
+}
 
 // Bilinear taps of one 2x2 image block (one label pixel), gathered from the frame with the
 // depth window + centring applied per tap.  INTERIOR: every source row / column of this band
 // lies inside the frame, so no bounds predicates are needed.
-template <typename T, bool INTERIOR>
-__device__ __forceinline__ void resample_block(T (&px)[2][2], const float* __restrict__ frame, const SampleGeom& g,
-                                               const TapX* ytap2, const TapX* xtap2, int Hf, int Wf) {
+template <typename T, int FMT, bool INTERIOR>
+__device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __restrict__ frame, const SampleGeom& g,
+                                               const TapX* ytap2, const TapX* xtap2, int Wf) {
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
         const TapX ty = ytap2[dy];
         const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
-        const bool ra = INTERIOR || (fr_a >= 0 && fr_a < Hf), rb = INTERIOR || (fr_b >= 0 && fr_b < Hf);
+        const bool ra = INTERIOR || (fr_a >= g.pr0 && fr_a < g.pr1), rb = INTERIOR || (fr_b >= g.pr0 && fr_b < g.pr1);
         const int row_a = fr_a * Wf, row_b = fr_b * Wf;          // Hf*Wf < 2^31 (checked on the host)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
             const TapX tx = xtap2[dx];
             const int fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
-            const bool ca = INTERIOR || (fc_a >= 0 && fc_a < Wf), cb = INTERIOR || (fc_b >= 0 && fc_b < Wf);
-            const float v00 = (ra && ca) ? __ldg(frame + (row_a + fc_a)) : 0.f;
-            const float v01 = (ra && cb) ? __ldg(frame + (row_a + fc_b)) : 0.f;
-            const float v10 = (rb && ca) ? __ldg(frame + (row_b + fc_a)) : 0.f;
-            const float v11 = (rb && cb) ? __ldg(frame + (row_b + fc_b)) : 0.f;
+            const bool ca = INTERIOR || (fc_a >= g.pc0 && fc_a < g.pc1), cb = INTERIOR || (fc_b >= g.pc0 && fc_b < g.pc1);
+            const float v00 = (ra && ca) ? load_px<FMT>(frame, row_a + fc_a) : 0.f;
+            const float v01 = (ra && cb) ? load_px<FMT>(frame, row_a + fc_b) : 0.f;
+            const float v10 = (rb && ca) ? load_px<FMT>(frame, row_b + fc_a) : 0.f;
+            const float v11 = (rb && cb) ? load_px<FMT>(frame, row_b + fc_b) : 0.f;
             const T w00 = Arith<T>::window(static_cast<T>(v00), g);
             const T w01 = Arith<T>::window(static_cast<T>(v01), g);
             const T w10 = Arith<T>::window(static_cast<T>(v10), g);
@@ -276,7 +326,7 @@ sfr_prep_kernel(SfrArgs a) {
     SampleGeom* gp = a.prep_geom + b;
     if (lane == 0) {
         SampleGeom g;
-        sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf);
+        sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
         *gp = g;
         a.gate[b] = 0u;
         a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
@@ -310,7 +360,7 @@ sfr_prep_kernel(SfrArgs a) {
 // ---------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------
-template <typename T, bool TRAIN>
+template <typename T, int FMT, bool TRAIN>
 __global__ void __launch_bounds__(kThreads)
 sfr_build_kernel(SfrArgs a) {
     __shared__ SampleGeom geom;
@@ -374,11 +424,12 @@ sfr_build_kernel(SfrArgs a) {
     float* img_b = a.img + static_cast<size_t>(b) * kImage * kImage;
     float* lab_b = a.label_img + static_cast<size_t>(b) * kMap;
     float* msk_b = a.mask + static_cast<size_t>(b) * kMap;
-    const float* frame = a.frames + static_cast<size_t>(b) * a.Hf * a.Wf;
+    const void* frame = static_cast<const unsigned char*>(a.frames) +
+                        static_cast<size_t>(b) * a.Hf * a.Wf * (FMT == FMT_F32 ? 4 : 2);
     const T cube_t = static_cast<T>(g.cube);
     const T cube_r = Arith<T>::rcp(cube_t);
-    const bool interior = g.ok && g.fc0 >= 0 && g.fc0 + g.ncols <= a.Wf && g.fr0 + ytap[0].s0 >= 0 &&
-                          g.fr0 + ytap[2 * kBandRows - 1].s1 < a.Hf;
+    const bool interior = g.ok && g.fc0 >= g.pc0 && g.fc0 + g.ncols <= g.pc1 && g.fr0 + ytap[0].s0 >= g.pr0 &&
+                          g.fr0 + ytap[2 * kBandRows - 1].s1 < g.pr1;
     int my_count = 0, my_nan = 0;
 #pragma unroll 2
     for (int it = 0; it < kLabelIters; ++it) {
@@ -389,8 +440,8 @@ sfr_build_kernel(SfrArgs a) {
         float2 o0 = make_float2(0.f, 0.f), o1 = o0;
         if (g.ok) {
             T px[2][2];
-            if (interior) resample_block<T, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Hf, a.Wf);
-            else          resample_block<T, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Hf, a.Wf);
+            if (interior) resample_block<T, FMT, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Wf);
+            else          resample_block<T, FMT, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Wf);
             // 2x2 mean (cv::resize reroutes an exact 2x INTER_LINEAR shrink to the area path)
             lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
                                 T(0.25));
@@ -526,11 +577,17 @@ static void carve_workspace(SfrArgs& a, void* ws) {
     a.gate = reinterpret_cast<unsigned int*>(p);
 }
 
-template <typename T, bool TRAIN>
-static int launch_sfr(const SfrArgs& a, cudaStream_t stream) {
+template <bool TRAIN>
+static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t stream) {
+    if (fmt != FMT_F32 && fmt != FMT_GB16 && fmt != FMT_U16) return PWR_E_METHOD;
+    if (frame_f64 && fmt != FMT_F32) return PWR_E_METHOD;       // float64 semantics exist for decoded frames only
     sfr_prep_kernel<TRAIN><<<(a.B + kPrepThreads / 32 - 1) / (kPrepThreads / 32), kPrepThreads, 0, stream>>>(a);
     if (int rc = launch_status()) return rc;
-    sfr_build_kernel<T, TRAIN><<<static_cast<unsigned>(a.B) * kBands, kThreads, 0, stream>>>(a);
+    const unsigned grid = static_cast<unsigned>(a.B) * kBands;
+    if (frame_f64)            sfr_build_kernel<double, FMT_F32, TRAIN><<<grid, kThreads, 0, stream>>>(a);
+    else if (fmt == FMT_F32)  sfr_build_kernel<float, FMT_F32, TRAIN><<<grid, kThreads, 0, stream>>>(a);
+    else if (fmt == FMT_GB16) sfr_build_kernel<float, FMT_GB16, TRAIN><<<grid, kThreads, 0, stream>>>(a);
+    else                      sfr_build_kernel<float, FMT_U16, TRAIN><<<grid, kThreads, 0, stream>>>(a);
     return launch_status();
 }
 
@@ -557,8 +614,9 @@ extern "C" int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com, int
     return launch_status();
 }
 
-extern "C" int pwr_sfr_crop(const float* frames, int Hf, int Wf, const double* com, const double* cube, double fx,
-                            double fy, int frame_f64, float* img, float* label_img, float* mask, float* box_size,
+extern "C" int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf, const double* com,
+                            const double* cube, double fx, double fy, int frame_f64, double prefilter_margin,
+                            double prefilter_umax, double prefilter_vmax, float* img, float* label_img, float* mask, float* box_size,
                             float* cube_size, float* com_out, uint8_t* valid, void* workspace, size_t workspace_size,
                             int B, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
@@ -569,14 +627,16 @@ extern "C" int pwr_sfr_crop(const float* frames, int Hf, int Wf, const double* c
     PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask); PWR_REQUIRE_PTR(workspace);
     if (workspace_size < workspace_bytes(B, 0)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
-                 nullptr, nullptr, nullptr, valid, B, 0, nullptr, nullptr, nullptr, nullptr};
+                 nullptr, nullptr, nullptr, valid, B, 0, nullptr, nullptr, nullptr, nullptr,
+                 prefilter_margin, prefilter_umax, prefilter_vmax};
     carve_workspace(a, workspace);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return frame_f64 ? launch_sfr<double, false>(a, s) : launch_sfr<float, false>(a, s);
+    return launch_sfr<false>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int pwr_sfr_build(const float* frames, int Hf, int Wf, const double* com, const double* cube,
-                             const double* uvd, double fx, double fy, int frame_f64, float* img, float* label_img,
+extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf, const double* com,
+                             const double* cube, const double* uvd, double fx, double fy, int frame_f64,
+                             double prefilter_margin, double prefilter_umax, double prefilter_vmax, float* img,
+                             float* label_img,
                              float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
                              float* heatmaps, float* dmap, uint8_t* valid, void* workspace, size_t workspace_size,
                              int B, int J, void* stream) {
@@ -590,8 +650,8 @@ extern "C" int pwr_sfr_build(const float* frames, int Hf, int Wf, const double* 
     PWR_REQUIRE_PTR(heatmaps); PWR_REQUIRE_PTR(dmap); PWR_REQUIRE_PTR(workspace);
     if (workspace_size < workspace_bytes(B, J)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
-                 uvd_norm, heatmaps, dmap, valid, B, J, nullptr, nullptr, nullptr, nullptr};
+                 uvd_norm, heatmaps, dmap, valid, B, J, nullptr, nullptr, nullptr, nullptr,
+                 prefilter_margin, prefilter_umax, prefilter_vmax};
     carve_workspace(a, workspace);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return frame_f64 ? launch_sfr<double, true>(a, s) : launch_sfr<float, true>(a, s);
+    return launch_sfr<true>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }

@@ -40,8 +40,18 @@ def center_of_mass(frames):
     return com
 
 
-def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only=False):
-    """frames [B,Hf,Wf] float32 CUDA depth frames (mm); com [B,3] float64 hand
+_FRAME_DTYPES = {"f32": torch.float32, "nyu_gb16": torch.uint16, "u16": torch.uint16}
+
+
+def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only=False, frame_format="f32",
+              prefilter=None):
+    """frames [B,Hf,Wf] CUDA depth frames: float32 mm (`frame_format="f32"`, what
+    process_single_data receives), or raw sensor samples decoded on the fly exactly as
+    the reference's loaders do: "nyu_gb16" = uint16 G<<8|B of the NYU PNG
+    (datasets.py:810), "u16" = 16-bit grey PNG (ICVL :632, HAND17 :940).
+    `prefilter=(margin, halfu, halfv)` applies the hand rectangle of load_from_text
+    (NYU/HAND17 margin 40, ICVL 30; datasets.py:841-853) inside the crop taps.
+    com [B,3] float64 hand
     centre (u, v, z) or None to use the centre-of-mass fallback; cube [B] (or a
     scalar) half cube size; uvd [B,J,3] float64 joint annotations (train mode).
     `frame_f64=True` reproduces datasets whose frames the reference holds as
@@ -50,13 +60,22 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     Returns SFRBatch (train) or SFRTestBatch (test_only), all float32 except
     `valid` (uint8)."""
     require_cuda(frames)
-    if frames.dtype != torch.float32 or frames.dim() != 3:
-        raise _lib.PwrError("frames must be a [B, Hf, Wf] float32 tensor")
+    if frame_format not in _FRAME_DTYPES:
+        raise _lib.PwrError("unknown frame_format %r" % (frame_format,))
+    if frames.dtype != _FRAME_DTYPES[frame_format] or frames.dim() != 3:
+        raise _lib.PwrError("frames must be a [B, Hf, Wf] %s tensor for frame_format=%r" % (
+            _FRAME_DTYPES[frame_format], frame_format))
+    if frame_f64 and frame_format != "f32":
+        raise _lib.PwrError("float64 frame semantics (MSRA) exist for decoded float32 frames only")
     lib = _lib.load()
     frames = frames.contiguous()
     dev = frames.device
     B, Hf, Wf = frames.shape
+    fmt = _lib.FRAME_FORMATS[frame_format]
+    pf = (-1.0, 0.0, 0.0) if prefilter is None else (float(prefilter[0]), 2.0 * prefilter[1], 2.0 * prefilter[2])
     if com is None:
+        if frame_format != "f32":
+            raise _lib.PwrError("the centre-of-mass fallback (MSRA) takes decoded float32 frames")
         com = center_of_mass(frames)
     com = _f64(com, dev)
     if not isinstance(cube, torch.Tensor) and np.ndim(cube) == 0:
@@ -78,8 +97,8 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     workspace = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)     # scratch, no init needed
     if test_only:
         with torch.cuda.device(dev), _lib.timed("pwr_sfr_crop"):
-            rc = lib.pwr_sfr_crop(ptr(frames), Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
-                                  ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
+            rc = lib.pwr_sfr_crop(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
+                                  pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
                                   ptr(valid), ptr(workspace), ws_bytes, B, s)
         check(rc, "pwr_sfr_crop")
         return SFRTestBatch(img, label_img, mask, box_size, cube_size, com_out, valid)
@@ -93,8 +112,8 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     heatmaps = torch.empty(B, J, 64, 64, **f32)
     dmap = torch.empty(B, J, 64, 64, **f32)
     with torch.cuda.device(dev), _lib.timed("pwr_sfr_build"):
-        rc = lib.pwr_sfr_build(ptr(frames), Hf, Wf, ptr(com), ptr(cube), ptr(uvd), float(fx), float(fy),
-                               int(frame_f64), ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
+        rc = lib.pwr_sfr_build(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), ptr(uvd), float(fx), float(fy),
+                               int(frame_f64), pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
                                ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), ptr(workspace),
                                ws_bytes, B, J, s)
     check(rc, "pwr_sfr_build")

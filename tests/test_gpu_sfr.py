@@ -52,6 +52,56 @@ def test_gpu_matches_oracle_seeded(shape_name, batch, seed):
     assert ref["valid"].all()
 
 
+RAW_SETS = ["sfr_nyu_raw", "sfr_nyu_raw_val", "sfr_hand17_raw", "sfr_icvl_raw"]
+
+
+def gpu_on_raw(g):
+    shape = golden_shape(g)
+    out = sfr.build_sfr(torch.from_numpy(g["raw"]).cuda(), g["com"], g["cube"], g["uvd"], fx=shape.fx, fy=shape.fy,
+                        frame_format=str(g["frame_format"]), prefilter=(float(g["margin"]), shape.halfu, shape.halfv))
+    torch.cuda.synchronize()
+    d = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    d["dmap"] = d.pop("depthmaps")
+    return d
+
+
+@pytest.mark.parametrize("name", RAW_SETS)
+def test_gpu_raw_frames_match_reference_load_from_text(name):
+    """Raw sensor samples + in-kernel PNG decode + hand rectangle == the reference's own
+    load_from_text followed by process_single_data."""
+    g = load_golden(name)
+    got = gpu_on_raw(g)
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS}
+    assert_sfr_matches(got, ref, SFR_FIELDS, g["ref_valid"], prefix=name + ":")
+
+
+@pytest.mark.parametrize("name", RAW_SETS)
+def test_gpu_raw_frames_bitwise_equal_oracle(name):
+    from test_oracle_sfr import oracle_on_raw_golden
+    g = load_golden(name)
+    got, ref = gpu_on_raw(g), oracle_on_raw_golden(g)
+    for n in ("img", "label_img", "mask"):
+        assert (got[n] == ref[n]).all(), n
+
+
+def test_prefilter_rectangle_python_slice_semantics():
+    """A CoM near the left edge makes `right` small / `left` clamp; one far outside makes the
+    Python slice wrap: compare against the oracle's literal restatement."""
+    shape = synth.NYU
+    d = synth.make_frames(shape, 4, 31, mixed_cube=False)
+    com = d["com"].copy()
+    com[0, 0] = 20.3
+    com[1, 0] = -150.0          # int(com_u + du) < 0 -> negative `right` wraps around the frame
+    com[2, 1] = 470.9
+    frames = [so.prefilter(d["frames"][b], com[b], 150, shape.fx, shape.fy, shape.halfu, shape.halfv, 40) for b in range(4)]
+    ref = so.process_batch(frames, d["uvd"], com, d["cube"], shape.fx, shape.fy, test_only=True)
+    out = sfr.build_sfr(torch.from_numpy(d["frames"]).cuda(), com, d["cube"], fx=shape.fx, fy=shape.fy, test_only=True,
+                        prefilter=(40, shape.halfu, shape.halfv))
+    got = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    assert_sfr_matches(got, ref, SFR_FIELDS[:6], ref["valid"])
+    assert (got["img"] == ref["img"]).all()
+
+
 def test_gpu_test_only_matches_oracle():
     shape = synth.NYU
     d = synth.make_frames(shape, 8, 7)

@@ -28,6 +28,45 @@ def test_oracle_matches_reference_golden(name):
     assert_sfr_matches(got, ref, names, g["ref_valid"], prefix=name + ":")
 
 
+RAW_SETS = ["sfr_nyu_raw", "sfr_nyu_raw_val", "sfr_hand17_raw", "sfr_icvl_raw"]
+
+
+def oracle_on_raw_golden(g, backend="numpy"):
+    """Raw sensor samples -> decode -> load_from_text prefilter -> SFR, all oracle code."""
+    shape = golden_shape(g)
+    fmt, margin = str(g["frame_format"]), float(g["margin"])
+    frames = []
+    for b in range(len(g["raw"])):
+        raw = g["raw"][b]
+        if fmt == "nyu_gb16":
+            rgb = np.zeros(raw.shape + (3,), np.uint8)
+            rgb[..., 1] = raw >> 8
+            rgb[..., 2] = raw & 255
+            img = so.decode_nyu(rgb)
+        else:
+            img = so.decode_u16(raw)
+        cube = int(g["cube"][b])
+        frames.append(so.prefilter(img, g["com"][b], cube, shape.fx, shape.fy, shape.halfu, shape.halfv, int(margin)))
+    return so.process_batch(frames, g["uvd"], g["com"], g["cube"], shape.fx, shape.fy, backend=backend)
+
+
+@pytest.mark.parametrize("name", RAW_SETS)
+def test_oracle_raw_frames_match_reference_load_from_text(name):
+    g = load_golden(name)
+    got = oracle_on_raw_golden(g)
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS}
+    assert_sfr_matches(got, ref, SFR_FIELDS, g["ref_valid"], prefix=name + ":")
+    assert g["ref_valid"].all()
+
+
+def test_u16_png_decode_is_the_identity_and_nyu_decode_is_not():
+    u = np.arange(65536, dtype=np.uint32).astype(np.uint16).reshape(256, 256)
+    assert (so.decode_u16(u) == u.astype(np.float32)).all()
+    rgb = np.zeros((1, 1, 3), np.uint8)
+    rgb[..., 1], rgb[..., 2] = 2, 238
+    assert so.decode_nyu(rgb)[0, 0] == np.float32(750.00006)       # float32 rounding of the reference's decode line
+
+
 def test_edge_golden_covers_reject_and_accept():
     g = load_golden("sfr_edge")
     v = g["ref_valid"]

@@ -239,9 +239,9 @@ def run_b200(args):
         sfr_kw.update(frame_format=args.frame_format, prefilter=(40.0, shape.halfu, shape.halfv), frame_f64=False)
         d["frames"] = frames
 
-    def step(frames_, com_, cube_, uvd_, z_, D_):
+    def step(frames_, com_, cube_, uvd_, z_, D_, kw=None):
         """The public-API call sequence a training loop makes for this path."""
-        batch = sfr.build_sfr(frames_, com_, cube_, uvd_, **sfr_kw)
+        batch = sfr.build_sfr(frames_, com_, cube_, uvd_, **(kw or sfr_kw))
         total, terms, uvd_out, _ = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, batch.heatmaps,
                                                           batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
                                                           lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)
@@ -308,11 +308,10 @@ def run_b200(args):
     step_kernel_ms = sum(k["avg_ms"] for k in kernels.values())
 
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region ----
-    e2e = None
-    if not args.no_e2e:
-        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in
-                dict(frames=frames, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach()).items()}
-        for k, v in dict(frames=frames, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach()).items():
+    def run_e2e(frames_dev, kw, what):
+        src = dict(frames=frames_dev, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach())
+        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in src.items()}
+        for k, v in src.items():
             host[k].copy_(v)
         out_host = {"loss": torch.empty(4, pin_memory=True), "uvd": torch.empty(B, J, 3, pin_memory=True)}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -324,7 +323,7 @@ def run_b200(args):
                 dev_in[k].copy_(host[k], non_blocking=True)
             z_ = dev_in["z"].requires_grad_(True)
             D_ = dev_in["D"].requires_grad_(True)
-            total, terms, uvd_out = step(dev_in["frames"], dev_in["com"], dev_in["cube"], dev_in["uvd"], z_, D_)
+            total, terms, uvd_out = step(dev_in["frames"], dev_in["com"], dev_in["cube"], dev_in["uvd"], z_, D_, kw)
             out_host["loss"].copy_(torch.cat([total.detach().reshape(1), terms]), non_blocking=True)
             out_host["uvd"].copy_(uvd_out, non_blocking=True)
             torch.cuda.synchronize()
@@ -343,10 +342,23 @@ def run_b200(args):
         te = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": n_e2e,
-               "note": "per rank and step: frames+com+cube+uvd+z+D copied from pinned host memory, "
-                       "loss[4]+uvd[B,J,3] read back; wall clock with device sync, max over ranks"}
+        del host, dev_in
+        return {"value": B * world * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                "note": "per rank and step: %s + com + cube + uvd + z + D copied from pinned host memory, "
+                        "loss[4] + uvd[B,J,3] read back; wall clock with device sync, max over ranks" % what}
+
+    e2e = e2e_raw = None
+    if not args.no_e2e:
+        e2e = run_e2e(frames, sfr_kw, "%s frames" % args.frame_format)
+        if args.frame_format == "f32" and not shape.frame_f64:
+            # the same step fed with the raw 16-bit sensor frame (what the host actually holds before
+            # load_from_text decodes it): PNG decode + hand rectangle run inside the SFR kernel
+            raw_fmt = "nyu_gb16" if shape.name == "NYU" else "u16"
+            raw = frames.round().clamp_(0, 65535).to(torch.int32).to(torch.uint16)
+            raw_kw = dict(fx=shape.fx, fy=shape.fy, frame_format=raw_fmt, prefilter=(40.0, shape.halfu, shape.halfv))
+            e2e_raw = run_e2e(raw, raw_kw, "raw uint16 (%s) frames" % raw_fmt)
+            del raw
 
     # ---- GPU baseline of configs[1] ("vs reference PyTorch path"): the reference's decoder + loss
     # lines as plain eager PyTorch ops on the same GPU and inputs (the SFR builder has no GPU
@@ -382,6 +394,7 @@ def run_b200(args):
                        "algorithmic_bytes_per_sample": roofline.step_bytes(J)},
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_raw_frames": e2e_raw,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
                          "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,

@@ -216,6 +216,14 @@ int pwr_recover_uvd(const float* uvd_norm, const float* box_size,
                     double fx, double fy, double halfu, double halfv,
                     float* uvd_px, float* xyz, int B, int J, void* stream);
 
+/* Evaluation metric of train.py:254-276 / test.py:106-113 without the .cpu()
+ * round trip: err[b] = mean_j | xyz(recover_uvd(uvd_pred)) -
+ * xyz(recover_uvd(uvd_true)) |_2 in mm, float32 in the reference's order. */
+int pwr_joint_error(const float* uvd_pred, const float* uvd_true,
+                    const float* box_size, const float* cube_size,
+                    const float* com, double fx, double fy, double halfu,
+                    double halfv, float* err, int B, int J, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

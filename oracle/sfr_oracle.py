@@ -383,3 +383,18 @@ def recover_uvd(uvd, box_size, com, cube):
     out[:, :, :2] = out[:, :, :2] * (box_size.astype(np.float32) - 1).reshape(-1, 1, 1)
     out[:, :, 2] = out[:, :, 2] * cube.astype(np.float32)[:, None]
     return out + com.astype(np.float32)[:, None, :]
+
+
+def uvd2xyz(uvd, fx, fy, halfu, halfv):
+    """datasets.py:100-111 on a float32 [B,J,3] array (NumPy float32 arithmetic)."""
+    x = uvd.copy()
+    x[:, :, 0] = (x[:, :, 0] - halfu) / fx * x[:, :, 2]
+    x[:, :, 1] = (x[:, :, 1] - halfv) / fy * x[:, :, 2]
+    return x
+
+
+def joint_error(uvd_pred, uvd_true, box_size, com, cube, fx, fy, halfu, halfv):
+    """train.py:254-276: per-sample mean joint error (mm) from normalised uvd."""
+    p = uvd2xyz(recover_uvd(uvd_pred, box_size, com, cube), fx, fy, halfu, halfv)
+    t = uvd2xyz(recover_uvd(uvd_true, box_size, com, cube), fx, fy, halfu, halfv)
+    return np.mean(np.sqrt(np.sum((p - t) ** 2, axis=2)), axis=1)

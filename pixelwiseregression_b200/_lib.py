@@ -40,6 +40,7 @@ SIGNATURES = {
     "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P],
     "pwr_scale_inplace": [_P, _P, _LL, _P],
     "pwr_recover_uvd": [_P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _I, _I, _P],
+    "pwr_joint_error": [_P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _I, _I, _P],
 }
 
 _lib = None

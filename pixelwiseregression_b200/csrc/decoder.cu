@@ -637,6 +637,36 @@ __global__ void recover_uvd_kernel(const float* __restrict__ uvd_norm, const flo
     }
 }
 
+// train.py:254-276 / test.py:106-113: mean over joints of |xyz_pred - xyz_true| per sample, both
+// sides through recover_uvd (float32 torch order) and uvd2xyz (float32 NumPy order)
+__global__ void joint_error_kernel(const float* __restrict__ uvd_pred, const float* __restrict__ uvd_true,
+                                   const float* __restrict__ box, const float* __restrict__ cube,
+                                   const float* __restrict__ com, float fx, float fy, float halfu, float halfv,
+                                   float* __restrict__ err, int B, int J) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float s = __fsub_rn(box[b], 1.f), cb = cube[b];
+    const float cu = com[b * 3 + 0], cv = com[b * 3 + 1], cz = com[b * 3 + 2];
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) {
+        float xyz[2][3];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float* p = (k == 0 ? uvd_pred : uvd_true) + (static_cast<size_t>(b) * J + j) * 3;
+            const float u = __fadd_rn(__fmul_rn(p[0], s), cu);
+            const float v = __fadd_rn(__fmul_rn(p[1], s), cv);
+            const float d = __fadd_rn(__fmul_rn(p[2], cb), cz);
+            xyz[k][0] = __fmul_rn(__fdiv_rn(__fsub_rn(u, halfu), fx), d);
+            xyz[k][1] = __fmul_rn(__fdiv_rn(__fsub_rn(v, halfv), fy), d);
+            xyz[k][2] = d;
+        }
+        const float dx = __fsub_rn(xyz[0][0], xyz[1][0]), dy = __fsub_rn(xyz[0][1], xyz[1][1]);
+        const float dz = __fsub_rn(xyz[0][2], xyz[1][2]);
+        acc = __fadd_rn(acc, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+    }
+    err[b] = __fdiv_rn(acc, static_cast<float>(J));
+}
+
 static int check_bj(int B, int J) {
     if (B < 0 || J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
     if (static_cast<long long>(B) * J > 0x7fffffffLL / 4) return PWR_E_SHAPE;
@@ -808,6 +838,20 @@ extern "C" int pwr_recover_uvd(const float* uvd_norm, const float* box_size, con
     recover_uvd_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         uvd_norm, box_size, cube_size, com, static_cast<float>(fx), static_cast<float>(fy),
         static_cast<float>(halfu), static_cast<float>(halfv), uvd_px, xyz, B, J);
+    return launch_status();
+}
+
+extern "C" int pwr_joint_error(const float* uvd_pred, const float* uvd_true, const float* box_size,
+                               const float* cube_size, const float* com, double fx, double fy, double halfu,
+                               double halfv, float* err, int B, int J, void* stream) {
+    if (B < 0 || J < 1) return PWR_E_SHAPE;
+    if (B == 0) return 0;
+    if (uvd_pred == nullptr || uvd_true == nullptr || box_size == nullptr || cube_size == nullptr ||
+        com == nullptr || err == nullptr)
+        return PWR_E_NULL;
+    joint_error_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        uvd_pred, uvd_true, box_size, cube_size, com, static_cast<float>(fx), static_cast<float>(fy),
+        static_cast<float>(halfu), static_cast<float>(halfv), err, B, J);
     return launch_status();
 }
 

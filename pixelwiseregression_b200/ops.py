@@ -313,3 +313,19 @@ def recover_uvd(uvd_norm, box_size, com, cube_size, intrinsics=None):
                                          stream_ptr(uvd_norm.device))
     check(rc, "pwr_recover_uvd")
     return (uvd_px, xyz) if intrinsics is not None else uvd_px
+
+
+def joint_error(uvd_pred, uvd_true, box_size, com, cube_size, intrinsics):
+    """Mean joint error per sample in mm (train.py:254-276, test.py:106-113) on the GPU:
+    both normalised uvd tensors go through recover_uvd and uvd2xyz inside one kernel.
+    intrinsics = (fx, fy, halfu, halfv).  Returns [B] float32."""
+    require_cuda(uvd_pred, uvd_true, box_size, com, cube_size)
+    B, J = uvd_pred.shape[0], uvd_pred.shape[1]
+    err = torch.empty(B, device=uvd_pred.device, dtype=torch.float32)
+    fx, fy, hu, hv = intrinsics
+    with torch.cuda.device(uvd_pred.device):
+        rc = _lib.load().pwr_joint_error(ptr(as_f32(uvd_pred)), ptr(as_f32(uvd_true)), ptr(as_f32(box_size)),
+                                         ptr(as_f32(cube_size)), ptr(as_f32(com)), fx, fy, hu, hv, ptr(err), B, J,
+                                         stream_ptr(uvd_pred.device))
+    check(rc, "pwr_joint_error")
+    return err

@@ -262,3 +262,23 @@ def test_cpu_tensors_are_rejected():
     z = torch.zeros(1, 2, 64, 64)
     with pytest.raises(PwrError):
         ops.decoder_forward_raw(z, torch.ones(2, 1), z, torch.zeros(1, 1, 64, 64), torch.zeros(1, 1, 64, 64))
+
+
+def test_recover_uvd_and_joint_error_match_oracle():
+    """utils.py:332-337, datasets.py:100-111, train.py:254-276 on the GPU vs the NumPy restatement."""
+    from oracle import sfr_oracle as so
+    rng = np.random.default_rng(4)
+    B, J = 257, 21
+    shape = synth.HAND17
+    pred = rng.uniform(-0.5, 0.5, (B, J, 3)).astype(np.float32)
+    true = (pred + rng.normal(0, 0.02, (B, J, 3))).astype(np.float32)
+    box = rng.integers(100, 352, B).astype(np.float32)
+    cube = np.full(B, 150, np.float32)
+    com = np.stack([rng.integers(100, 500, B), rng.integers(100, 400, B), rng.uniform(500, 1000, B)], 1).astype(np.float32)
+    intr = (shape.fx, shape.fy, shape.halfu, shape.halfv)
+    uvd_px, xyz = ops.recover_uvd(cu(pred), cu(box), cu(com), cu(cube), intrinsics=intr)
+    ref_px = so.recover_uvd(pred, box, com, cube)
+    assert (uvd_px.cpu().numpy() == ref_px).all()                         # same float32 operation order
+    assert_close("xyz", xyz.cpu().numpy(), so.uvd2xyz(ref_px, *intr))
+    err = ops.joint_error(cu(pred), cu(true), cu(box), cu(com), cu(cube), intr)
+    assert_close("joint error", err.cpu().numpy(), so.joint_error(pred, true, box, com, cube, *intr))

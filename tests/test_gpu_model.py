@@ -149,3 +149,52 @@ def test_standalone_submodules_keep_reference_signatures():
     assert_close("d", d.detach().cpu().numpy(), dr.detach().cpu().numpy())
     (uv.sum() + d.sum()).backward()
     assert plane.w.grad is not None and depth.conv[0].weight.grad is not None
+
+
+def test_full_size_nyu_training_step_matches_reference_formulas():
+    """BASELINE config 3 shape: train.py defaults (features 128, level 4, 2 stages, InstanceNorm, J=14),
+    targets from the GPU SFR builder; fused criterion vs the reference's decoder + loss lines."""
+    from pixelwiseregression_b200 import sfr, synth
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    shape = synth.NYU
+    B = 16
+    d = synth.make_frames_device(shape, B, seed=5)
+    batch = sfr.build_sfr(d["frames"], d["com"], d["cube"], d["uvd"], fx=shape.fx, fy=shape.fy)
+    assert bool(batch.valid.all())
+    net = M.PixelwiseRegression(14, stage=2, features=128, level=4, norm_method="instance").to(DEV)
+    ref_net = copy.deepcopy(net)
+    loss, every, uvds = net.forward_loss(batch.img, batch.label_img, batch.mask, batch.uvd, batch.heatmaps,
+                                         batch.depthmaps, 0.7, 1.0, 0.01)
+    loss.backward()
+    res_ref = reference_forward(ref_net, batch.img, batch.label_img, batch.mask)
+    loss_ref, every_ref = train_loss(res_ref, batch.uvd, batch.heatmaps, batch.depthmaps, 0.7, 1.0, 0.01)
+    loss_ref.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    for t, tr in zip(every, every_ref):
+        assert_close("terms", t.cpu().numpy(), [x.item() for x in tr])
+    compare_param_grads(net, ref_net)
+
+
+def test_hand17_inference_sweep_shape():
+    """BASELINE config 5 shape: J=21, large-batch no_grad decode + recover_uvd (properties only)."""
+    from pixelwiseregression_b200 import ops, synth
+    shape = synth.HAND17
+    B, J = 8192, shape.joints
+    g = torch.Generator(device=DEV).manual_seed(1)
+    z = torch.randn(B, J, 64, 64, device=DEV, generator=g) * 4
+    D = torch.randn(B, J, 64, 64, device=DEV, generator=g)
+    w = torch.ones(J, 1, device=DEV)
+    m = (torch.rand(B, 1, 64, 64, device=DEV, generator=g) < 0.4).float()
+    L = torch.rand(B, 1, 64, 64, device=DEV, generator=g) * m
+    with torch.no_grad():
+        _, uvd, _, _ = ops.decoder_forward_raw(z, w, D, L, m, store_heat=False, want_stats=False)   # last stage: H elided
+        H, uvd2, _, _ = ops.decoder_forward_raw(z[:64], w, D[:64], L[:64], m[:64])
+    assert torch.equal(uvd[:64], uvd2)
+    assert float((H.sum(dim=(2, 3)) - 1).abs().max()) < 1e-5
+    box = torch.full((B,), 201.0, device=DEV)
+    cube = torch.full((B,), 150.0, device=DEV)
+    com = torch.tensor([[320.0, 240.0, 700.0]], device=DEV).repeat(B, 1)
+    px = ops.recover_uvd(uvd, box, com, cube)
+    assert torch.allclose(px[:, :, 0], uvd[:, :, 0] * 200 + 320) and torch.allclose(px[:, :, 2], uvd[:, :, 2] * 150 + 700)

@@ -233,6 +233,64 @@ def golden_raw(datasets, name, shape, frame_format, margin, batch, seed, val_mod
     print(name, "valid", res["ref_valid"].tolist(), "cubes", sorted(set(cubes)))
 
 
+def golden_augmented(datasets, name, shape, batch, seed, spread=0.6):
+    """The reference's augmented branch (datasets.py:216-299, train.py's default flags) with
+    `random.random` replaced by a recorded sequence, so the draws can be replayed on the GPU."""
+    import random
+    d = synth.make_frames(shape, batch, seed)
+    if spread != 0.6:                                   # push joints towards the crop border
+        rng = np.random.default_rng(seed + 99)
+        for b in range(batch):
+            z0 = d["com"][b, 2]
+            sh = max(int(d["cube"][b] / z0 * shape.fx + d["cube"][b] / z0 * shape.fy), 2) // 2
+            d["uvd"][b, :, 0] = d["com"][b, 0] + rng.uniform(-spread, spread, shape.joints) * sh
+            d["uvd"][b, :, 1] = d["com"][b, 1] + rng.uniform(-spread, spread, shape.joints) * sh
+            d["uvd"][b, 0, :2] = d["com"][b, :2] + 0.9 * sh      # a corner joint: leaves the map once rotated
+    frames = d["frames"].astype(np.float64) if shape.frame_f64 else d["frames"]
+    samples = [dict(frame=frames[b], uvd=d["uvd"][b], com=d["com"][b], cube=int(d["cube"][b])) for b in range(batch)]
+    ds = ref_shim.make_synthetic_dataset(datasets, samples, shape.fx, shape.fy, shape.halfu, shape.halfv,
+                                         int(shape.cube), shape.joints, msra_com=shape.com_from_frame, augment=True)
+    draw_rng = np.random.default_rng(seed + 7)
+    real_random = random.random
+    outs, augs, valid = [], [], []
+    try:
+        for b in range(batch):
+            log = []
+
+            def fake():
+                v = float(draw_rng.uniform())
+                log.append(v)
+                return v
+            random.random = fake
+            try:
+                import contextlib
+                import io
+                with contextlib.redirect_stdout(io.StringIO()):
+                    tup = ds[b]
+                outs.append({n: t.numpy() for n, t in zip(FIELDS, tup)})
+                valid.append(1)
+            except Exception:
+                outs.append(None)
+                valid.append(0)
+            random.random = real_random
+            # draws: angle (discarded, datasets.py:225), scale :230, shift_x :236, shift_y :237, angle (utils.py:72)
+            assert len(log) == 5, log
+            augs.append([0.8 + log[1] * 0.4, -5 + log[2] * 10, -5 + log[3] * 10, log[4] * 60 - 30])
+    finally:
+        random.random = real_random
+    J = shape.joints
+    zero = dict(img=np.zeros((1, 128, 128), np.float32), label_img=np.zeros((1, 64, 64), np.float32),
+                mask=np.zeros((1, 64, 64), np.float32), box_size=np.float32(0), cube_size=np.float32(0),
+                com=np.zeros(3, np.float32), uvd=np.zeros((J, 3), np.float32),
+                heatmaps=np.zeros((J, 64, 64), np.float32), dmap=np.zeros((J, 64, 64), np.float32))
+    res = {"ref_" + n: np.stack([(o or zero)[n] for o in outs]) for n in FIELDS}
+    res["ref_valid"] = np.array(valid, dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), frames=d["frames"], uvd=d["uvd"], com=d["com"],
+                        cube=d["cube"], aug=np.array(augs), shape_name=np.array(shape.name),
+                        test_only=np.array(False), versions=versions(), **res)
+    print(name, "valid", valid, "aug[0]", np.round(augs[0], 3).tolist())
+
+
 def golden_decoder(model_mod, name, method, B, J, seed, alpha, with_upstream):
     """Reference PlaneRegression/DepthRegression with `.conv` swapped for
     Identity (so the module input is the logit map itself), reference loss
@@ -295,6 +353,9 @@ def main():
     golden_sfr(datasets, "sfr_msra", synth.MSRA, 3, 2)
     golden_sfr(datasets, "sfr_icvl", synth.ICVL, 2, 3)
     golden_edge(datasets)
+    golden_augmented(datasets, "sfr_nyu_aug", synth.NYU, 4, 30)
+    golden_augmented(datasets, "sfr_nyu_aug_fallback", synth.NYU, 6, 31, spread=0.5)
+    golden_augmented(datasets, "sfr_msra_aug", synth.MSRA, 2, 32)
     golden_raw(datasets, "sfr_nyu_raw", synth.NYU, "nyu_gb16", 40, 3, 20)
     golden_raw(datasets, "sfr_nyu_raw_val", synth.NYU, "nyu_gb16", 40, 2, 21, val_mode=True)
     golden_raw(datasets, "sfr_hand17_raw", synth.HAND17, "u16", 40, 2, 22)

@@ -71,7 +71,7 @@ def load():
 
 
 def make_synthetic_dataset(datasets, samples, fx, fy, halfu, halfv, cube, joints,
-                           test_only=False, msra_com=False):
+                           test_only=False, msra_com=False, augment=False):
     """Drive the reference's own HandDataset.process_single_data on in-memory
     synthetic samples: `samples` is a list of dicts(frame, uvd, com, cube).
     Only build_data()/load_from_text() are overridden (they are file I/O)."""
@@ -92,5 +92,6 @@ def make_synthetic_dataset(datasets, samples, fx, fy, halfu, halfv, cube, joints
                 return s["frame"], s["uvd"], None, None
             return s["frame"], s["uvd"], s["com"], s["cube"]
 
+    # augment: train.py's defaults (rotation, scale, shift on; flip off), train.py:35-38
     return _Synthetic(fx, fy, halfu, halfv, tmp, 1.5, 128, 7, 64, test_only,
-                      False, False, False, False, cube, joints)
+                      augment, augment, augment, False, cube, joints)

@@ -284,19 +284,85 @@ def joint_coords(uvd, com_int, box):
 # --------------------------------------------------------------------------- #
 # one sample, end to end
 # --------------------------------------------------------------------------- #
-def process_sample(frame, uvd, com, cube, fx, fy, test_only=False, backend="numpy"):
-    """Non-augmented branch of HandDataset.process_single_data
-    (datasets.py:301-403).  `frame` float32 (NYU/ICVL/HAND17 semantics) or
-    float64 (MSRA semantics); `com` None -> CoM fallback.  Returns a dict with
-    float32 arrays named like the reference tuple plus `valid` (False where
-    the reference raises)."""
+# --------------------------------------------------------------------------- #
+# augmentation (datasets.py:216-299, utils.py:67-82)
+# --------------------------------------------------------------------------- #
+def rotation_matrix(angle_deg, scale, center=(IMAGE_SIZE // 2, IMAGE_SIZE // 2)):
+    """cv2.getRotationMatrix2D (utils.py:74): `angle *= CV_PI/180` folds the constant first."""
+    a = angle_deg * (np.pi / 180)
+    alpha = math.cos(a) * scale
+    beta = math.sin(a) * scale
+    return np.array([[alpha, beta, (1 - alpha) * center[0] - beta * center[1]],
+                     [-beta, alpha, beta * center[0] + (1 - alpha) * center[1]]])
+
+
+def invert_affine(M):
+    """cv::invertAffineTransform, as cv::warpAffine applies it to a forward matrix."""
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22, A12, A21 = M[1, 1] * D, M[0, 0] * D, -M[0, 1] * D, -M[1, 0] * D
+    b1 = -A11 * M[0, 2] - A12 * M[1, 2]
+    b2 = -A21 * M[0, 2] - A22 * M[1, 2]
+    return np.array([[A11, A12, b1], [A21, A22, b2]])
+
+
+def warp_affine(src, M):
+    """cv2.warpAffine(src, M, src.shape) with the defaults the reference uses (utils.py:75):
+    INTER_LINEAR, BORDER_CONSTANT 0.  OpenCV evaluates the inverse map in 10-bit fixed
+    point, quantises the source position to 1/32 pixel and blends the four neighbours with
+    float table weights (1-fy/32)(1-fx/32)...; this restatement is bit-exact against OpenCV
+    4.13.0 for float32 and float64 images (tests/test_oracle_sfr.py)."""
+    size = src.shape[0]
+    iM = invert_affine(M)
+    ab_bits, inter_bits = 10, 5
+    ab_scale = 1 << ab_bits
+    round_delta = ab_scale // 32 // 2
+    xs = np.arange(size)
+    adelta = np.rint(iM[0, 0] * xs * ab_scale).astype(np.int64)
+    bdelta = np.rint(iM[1, 0] * xs * ab_scale).astype(np.int64)
+    X0 = np.rint((iM[0, 1] * xs + iM[0, 2]) * ab_scale).astype(np.int64) + round_delta      # per row y
+    Y0 = np.rint((iM[1, 1] * xs + iM[1, 2]) * ab_scale).astype(np.int64) + round_delta
+    X = (X0[:, None] + adelta[None, :]) >> (ab_bits - inter_bits)
+    Y = (Y0[:, None] + bdelta[None, :]) >> (ab_bits - inter_bits)
+    sx, sy, fx, fy = X >> inter_bits, Y >> inter_bits, X & 31, Y & 31
+    tab = np.stack([1 - np.arange(32, dtype=np.float32) / np.float32(32), np.arange(32, dtype=np.float32) / np.float32(32)], 1)
+    padded = np.zeros((size + 2, size + 2), src.dtype)
+    padded[1:-1, 1:-1] = src
+
+    def S(r, c):
+        ok = (r >= -1) & (r <= size) & (c >= -1) & (c <= size)
+        return np.where(ok, padded[np.clip(r + 1, 0, size + 1), np.clip(c + 1, 0, size + 1)], src.dtype.type(0))
+    w00 = tab[fy, 0] * tab[fx, 0]
+    w01 = tab[fy, 0] * tab[fx, 1]
+    w10 = tab[fy, 1] * tab[fx, 0]
+    w11 = tab[fy, 1] * tab[fx, 1]
+    out = S(sy, sx) * w00 + S(sy, sx + 1) * w01 + S(sy + 1, sx) * w10 + S(sy + 1, sx + 1) * w11
+    return out.astype(src.dtype)
+
+
+def rotate_joints(r, angle_deg, scale):
+    """utils.py:77-80: uvd[:, :2] @ Rot.T * scale (written out without FMA)."""
+    a = angle_deg / 180.0 * np.pi
+    c, s = np.cos(a), np.sin(a)
+    u, v = r[:, 0].copy(), r[:, 1].copy()
+    r = r.copy()
+    r[:, 0] = (u * c + v * s) * scale
+    r[:, 1] = (u * -s + v * c) * scale
+    return r
+
+
+def _process(frame, uvd, com, cube, fx, fy, test_only, backend, aug):
+    """One pass of process_single_data; `aug` None = the non-augmented branch
+    (datasets.py:301-365), else (scale, shift_u, shift_v, angle_deg) = the augmented branch
+    (:216-299).  Returns (out dict, raised) where `raised` mirrors a Python exception."""
     if backend == "cv2":
         import cv2
         do_resize = lambda s: cv2.resize(s, (IMAGE_SIZE, IMAGE_SIZE))
         do_half = lambda s: cv2.resize(s, (LABEL_SIZE, LABEL_SIZE))
         do_blur = lambda s: cv2.GaussianBlur(s, (KSIZE, KSIZE), SIGMA)
+        do_warp = lambda s, M: cv2.warpAffine(s, M, (IMAGE_SIZE, IMAGE_SIZE))
     else:
-        do_resize, do_half, do_blur = resize_bilinear, resize_half, gaussian_blur7
+        do_resize, do_half, do_blur, do_warp = resize_bilinear, resize_half, gaussian_blur7, warp_affine
 
     J = 0 if uvd is None else uvd.shape[0]
     f32 = np.float32
@@ -313,21 +379,35 @@ def process_sample(frame, uvd, com, cube, fx, fy, test_only=False, backend="nump
     com = np.array(com, dtype=np.float64)
     # integral cube sizes are Python ints in the reference (weak scalars)
     cube_w = int(cube) if float(cube) == int(cube) else float(cube)
+    if aug is not None:
+        # datasets.py:234-241: uvd2xyz / xyz2uvd do nothing to a 1-D array, so the "mm" shift is
+        # applied to the pixel coordinates of the centre as they are
+        scale, shift_u, shift_v, angle = (float(a) for a in aug)
+        com[0] += shift_u
+        com[1] += shift_v
 
     box = crop_box(com[2], cube_w, fx, fy)
     crop = center_crop(frame, com, box)
     if crop.shape[0] == 0 or crop.shape[1] == 0:
-        return out                                  # cv2.resize raises
+        return out, True                            # cv2.resize raises
     crop = window_and_centre(crop.copy(), com[2], cube_w)
     com[0] = int(com[0])
     com[1] = int(com[1])
     box = crop.shape[0]
 
     img = do_resize(crop)
+    wt = img.dtype.type
+    if aug is not None:
+        r, _ = joint_coords(uvd, com, box)
+        img = do_warp(img, rotation_matrix(angle, scale))                  # utils.py:74-75
+        r = rotate_joints(r, angle, scale)                                 # utils.py:77-80
+        img = (img * wt(scale)).astype(wt)                                 # datasets.py:284
+        r[:, 2] *= scale                                                   # datasets.py:285
+        k = r.copy()
+        k[:, :2] = k[:, :2] / (IMAGE_SIZE - 1) * (LABEL_SIZE - 1) + np.array([LABEL_SIZE // 2, LABEL_SIZE // 2])
     label = do_half(img)
     mask = (label != 0).astype(np.float64)
 
-    wt = img.dtype.type
     out["img"] = (img / wt(cube_w)).astype(f32)[None]
     out["label_img"] = (label / wt(cube_w)).astype(f32)[None]
     out["mask"] = mask.astype(f32)[None]
@@ -337,15 +417,16 @@ def process_sample(frame, uvd, com, cube, fx, fy, test_only=False, backend="nump
     if test_only:
         # datasets.py:334-348 returns before the reject gate
         out["valid"] = True
-        return out
+        return out, False
 
-    r, k = joint_coords(uvd, com, box)
+    if aug is None:
+        r, k = joint_coords(uvd, com, box)
     heat = np.zeros((LABEL_SIZE, LABEL_SIZE, J))
     try:
         for j in range(J):
             heat[:, :, j] = do_blur(splat4(k[j, 0], k[j, 1]))
     except (IndexError, ValueError, OverflowError):
-        return out                                  # "heatmap error"
+        return out, True                            # "heatmap error"
     dmap = np.zeros_like(heat)
     for j in range(J):
         heatmask = (heat[:, :, j] > 0).astype(np.float64) * mask
@@ -360,18 +441,33 @@ def process_sample(frame, uvd, com, cube, fx, fy, test_only=False, backend="nump
     out["dmap"] = np.ascontiguousarray(dmap.transpose(2, 0, 1)).astype(f32)
     bad = bad or bool(np.isnan(nuvd).any() or np.isnan(heat).any() or np.isnan(dmap).any())
     out["valid"] = (not bad) and float(mask.sum()) >= 10
-    return out
+    return out, False
+
+
+def process_sample(frame, uvd, com, cube, fx, fy, test_only=False, backend="numpy", aug=None):
+    """HandDataset.process_single_data (datasets.py:185-403).  `frame` float32
+    (NYU/ICVL/HAND17 semantics) or float64 (MSRA semantics); `com` None -> CoM fallback.
+    `aug` = (scale, shift_u, shift_v, angle_deg): the augmented branch with these draws; as
+    in the reference (`try:` :216 / `except:` :301) anything that raises inside it silently
+    falls back to the non-augmented branch.  Returns a dict with float32 arrays named like
+    the reference tuple plus `valid` (False where the reference raises)."""
+    if aug is not None:
+        out, raised = _process(frame, uvd, com, cube, fx, fy, test_only, backend, aug)
+        if not raised:
+            return out
+    return _process(frame, uvd, com, cube, fx, fy, test_only, backend, None)[0]
 
 
 FIELDS = ("img", "label_img", "mask", "box_size", "cube_size", "com", "uvd", "heatmaps", "dmap")
 
 
-def process_batch(frames, uvd, com, cube, fx, fy, test_only=False, backend="numpy"):
+def process_batch(frames, uvd, com, cube, fx, fy, test_only=False, backend="numpy", aug=None):
     """Stack process_sample over a batch (the DataLoader's default_collate)."""
     B = len(frames)
     outs = [process_sample(frames[b], None if uvd is None else uvd[b],
                            None if com is None else com[b], cube[b], fx, fy,
-                           test_only=test_only, backend=backend) for b in range(B)]
+                           test_only=test_only, backend=backend, aug=None if aug is None else aug[b])
+            for b in range(B)]
     res = {k: np.stack([o[k] for o in outs]) for k in FIELDS}
     res["valid"] = np.array([o["valid"] for o in outs], dtype=np.uint8)
     return res

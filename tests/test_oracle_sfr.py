@@ -67,6 +67,43 @@ def test_u16_png_decode_is_the_identity_and_nyu_decode_is_not():
     assert so.decode_nyu(rgb)[0, 0] == np.float32(750.00006)       # float32 rounding of the reference's decode line
 
 
+AUG_SETS = ["sfr_nyu_aug", "sfr_nyu_aug_fallback", "sfr_msra_aug"]
+
+
+def oracle_on_aug_golden(g, backend="numpy"):
+    shape = golden_shape(g)
+    frames = g["frames"].astype(np.float64) if shape.frame_f64 else g["frames"]
+    com = None if shape.com_from_frame else g["com"]
+    return so.process_batch(frames, g["uvd"], com, g["cube"], shape.fx, shape.fy, backend=backend, aug=g["aug"])
+
+
+@pytest.mark.parametrize("name", AUG_SETS)
+def test_oracle_augmented_branch_matches_reference(name):
+    """datasets.py:216-299 with train.py's default flags; the reference's random draws were
+    recorded (oracle/make_golden.py) and are replayed here."""
+    g = load_golden(name)
+    got = oracle_on_aug_golden(g)
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS}
+    assert_sfr_matches(got, ref, SFR_FIELDS, g["ref_valid"], prefix=name + ":")
+    if name == "sfr_nyu_aug_fallback":
+        # at least one sample raised inside the augmented branch and silently fell back
+        plain = so.process_batch(g["frames"], g["uvd"], g["com"], g["cube"], golden_shape(g).fx, golden_shape(g).fy)
+        same = [np.abs(plain["img"][b] - g["ref_img"][b]).max() < 1e-6 for b in range(len(g["frames"]))]
+        assert any(same) and not all(same), same
+
+
+def test_warp_affine_restatement_is_bit_exact_vs_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for dt in (np.float32, np.float64):
+        for _ in range(6):
+            src = (rng.uniform(-100, 100, (128, 128)) * (rng.uniform(size=(128, 128)) < 0.7)).astype(dt)
+            angle, scale = rng.uniform(-30, 30), rng.uniform(0.8, 1.2)
+            M = cv2.getRotationMatrix2D((64, 64), angle, scale)
+            assert (M == so.rotation_matrix(angle, scale)).all()
+            assert (so.warp_affine(src, M) == cv2.warpAffine(src, M, (128, 128))).all()
+
+
 def test_edge_golden_covers_reject_and_accept():
     g = load_golden("sfr_edge")
     v = g["ref_valid"]

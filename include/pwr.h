@@ -111,12 +111,22 @@ int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf,
  * (cv2.GaussianBlur, BORDER_REFLECT_101) utils.py:64-65, Dmap :369-380 and
  * the reject gate :385-390 / :362-365.
  *   uvd [B,J,3] f64 joint pixel coordinates + depth.
+ *   aug [B,8] f64 or NULL: the draws of the augmented branch, datasets.py:216-299
+ *   with train.py's default flags (rotation, scale, shift; no flip): (scale,
+ *   shift_u, shift_v, cos(a*(pi/180)), sin(a*(pi/180)), cos(a/180*pi),
+ *   sin(a/180*pi), unused) for rotation angle a in degrees (utils.py:72-80; the
+ *   two spellings of the radian conversion are the reference's: OpenCV's
+ *   getRotationMatrix2D and the joint rotation).  The image is rotated and
+ *   scaled with cv2.warpAffine's fixed-point bilinear recipe; a sample whose
+ *   augmented branch would raise falls back to the plain branch, as the
+ *   reference's try/except does.
  * extra outputs: uvd_norm [B,J,3], heatmaps [B,J,64,64], dmap [B,J,64,64] f32;
  *   valid [B] u8 = 0 where the reference raises (empty crop, heat-map index
  *   out of range, NaN, sum(mask) < 10).
  *   workspace: >= pwr_sfr_workspace_bytes(B, J) bytes, 16-byte aligned. */
 int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
                   const double* com, const double* cube, const double* uvd,
+                  const double* aug,
                   double fx, double fy, int frame_f64,
                   double prefilter_margin, double prefilter_umax,
                   double prefilter_vmax,

@@ -31,8 +31,8 @@ SIGNATURES = {
     "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
     "pwr_sfr_workspace_bytes": [_I, _I],
     "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
-    "pwr_sfr_build": [_P, _I, _I, _I, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                      _SZ, _I, _I, _P],
+    "pwr_sfr_build": [_P, _I, _I, _I, _P, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                      _P, _SZ, _I, _I, _P],
     "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _P],
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _P],
     "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _P],

@@ -71,6 +71,15 @@ struct JointParam {
 
 struct TapX { int s0, s1; float a0, a1; };
 
+// Augmentation of one sample (datasets.py:216-299): rotation + scale about the centre of the
+// 128x128 image through cv2.warpAffine's inverse fixed-point map, intensity * scale.
+struct WarpParam {
+    double iM[6];              // inverse affine map, cv::invertAffineTransform of getRotationMatrix2D
+    double scale;
+    int active;                // 0: the augmented branch raised -> plain branch (datasets.py:301)
+    int pad;
+};
+
 // Python slice(start, stop).indices(n) for step 1
 __device__ __forceinline__ void py_slice(long long start, long long stop, long long n, int& first, int& count) {
     if (start < 0) { start += n; if (start < 0) start = 0; } else if (start > n) start = n;
@@ -154,13 +163,23 @@ __device__ __forceinline__ TapX linear_tap(int d, int n, double scale) {
 }
 
 // utils.py:37-62 + datasets.py:350-358 for one joint
-__device__ void joint_param(JointParam& p, float* uvd_norm_out, const double* uvd, const SampleGeom& g) {
+// `rot` = {cos, sin, scale} of the augmentation (utils.py:77-80, datasets.py:285) or nullptr.
+__device__ void joint_param(JointParam& p, float* uvd_norm_out, const double* uvd, const SampleGeom& g,
+                            const double* rot = nullptr) {
     const double cu = __dsub_rn(uvd[0], static_cast<double>(g.c0));
     const double cv = __dsub_rn(uvd[1], static_cast<double>(g.r0));
-    const double cd = __dsub_rn(uvd[2], g.z);
+    double cd = __dsub_rn(uvd[2], g.z);
     const double bm1 = static_cast<double>(g.nrows - 1);          // box_size = crop.shape[0]
-    const double ru = __dmul_rn(__ddiv_rn(cu, bm1), 127.0);
-    const double rv = __dmul_rn(__ddiv_rn(cv, bm1), 127.0);
+    double ru = __dmul_rn(__ddiv_rn(cu, bm1), 127.0);
+    double rv = __dmul_rn(__ddiv_rn(cv, bm1), 127.0);
+    if (rot != nullptr) {
+        // uvd[:, :2] @ Rot.T with Rot = [[c, s], [-s, c]], then * scale; depth * scale
+        const double c = rot[0], sn = rot[1], sc = rot[2];
+        const double u2 = __dmul_rn(__dadd_rn(__dmul_rn(ru, c), __dmul_rn(rv, sn)), sc);
+        const double v2 = __dmul_rn(__dadd_rn(__dmul_rn(ru, -sn), __dmul_rn(rv, c)), sc);
+        ru = u2; rv = v2;
+        cd = __dmul_rn(cd, sc);
+    }
     const double ku = __dadd_rn(__dmul_rn(__ddiv_rn(ru, 127.0), 63.0), 32.0);
     const double kv = __dadd_rn(__dmul_rn(__ddiv_rn(rv, 127.0), 63.0), 32.0);
     p.cd = cd;
@@ -257,6 +276,8 @@ struct SfrArgs {
     int* prep_flags;            // workspace: [B] joints_bad
     unsigned int* gate;         // workspace: [B] packed (bands arrived << 24 | NaN << 16 | mask count)
     double pf_margin, pf_umax, pf_vmax;   // load_from_text prefilter: margin < 0 = off; 2*halfu, 2*halfv
+    const double* aug;          // [B,8] (scale, shift_u, shift_v, cos a, sin a, cos a', sin a', -) or NULL
+    WarpParam* prep_warp;       // workspace: [B] (augmentation only)
 };
 
 // Raw sensor formats.  The float32 value the reference would hold is reproduced bit
@@ -312,48 +333,131 @@ __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __rest
     }
 }
 
+// Phase 2, pass B: the float64 footprint of the listed joints inside label rows [y_lo, y_hi):
+// <= 11 candidate rows x 11 candidate columns per joint (offsets -3..3 around tap 0, then 0..3
+// around tap 1), most rejected by integer tests.  `label_s` holds rows y_lo.. of the un-normalised label.
+template <typename T>
+__device__ __forceinline__ void patch_footprints(const SfrArgs& a, const SampleGeom& g, const JointParam* joints,
+                                                 const int* list, int list_n, const T* label_s, int b, int y_lo,
+                                                 int y_hi, int tid, int nthreads) {
+    constexpr int kCand = 11;
+    const int total = list_n * kCand * kCand;
+    for (int c = tid; c < total; c += nthreads) {
+        const int jl = c / (kCand * kCand);
+        const int r = c - jl * (kCand * kCand);
+        const int sy = r / kCand, sx = r - sy * kCand;
+        const int j = list[jl];
+        const JointParam& jp = joints[j];
+        const int y = sy < 7 ? jp.ty0 + sy - 3 : jp.ty1 + sy - 7;
+        const int x = sx < 7 ? jp.tx0 + sx - 3 : jp.tx1 + sx - 7;
+        if (y < y_lo || y >= y_hi || x < 0 || x >= kLabel) continue;
+        if (sy >= 7 && abs(y - jp.ty0) <= 3) continue;     // already listed around tap 0
+        if (sx >= 7 && abs(x - jp.tx0) <= 3) continue;
+        const double wy0 = gauss_reach(y, jp.ty0), wy1 = gauss_reach(y, jp.ty1);
+        const double wx0 = gauss_reach(x, jp.tx0), wx1 = gauss_reach(x, jp.tx1);
+        // separable order of cv2.GaussianBlur: rows first, then columns
+        const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
+        const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
+        const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
+        const T lab = label_s[(y - y_lo) * kLabel + x];
+        const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + y * kLabel + x;
+        a.heatmaps[o] = __double2float_rn(h);
+        // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
+        if (h > 0.0 && lab != T(0))
+            a.dmap[o] = __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // prep: per-sample geometry + per-joint taps, once per sample
 // ---------------------------------------------------------------------------
 constexpr int kPrepThreads = 128;                 // 4 samples (warps) per CTA
 
-template <bool TRAIN>
+__device__ void write_scalar_outputs(const SfrArgs& a, int b, const SampleGeom& g) {
+    a.gate[b] = 0u;
+    a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
+    a.cube_size[b] = static_cast<float>(g.cube);
+    a.com_out[3 * b + 0] = static_cast<float>(g.c0);
+    a.com_out[3 * b + 1] = static_cast<float>(g.r0);
+    a.com_out[3 * b + 2] = static_cast<float>(g.z);
+}
+
+// all joints of sample b with geometry g (one lane per joint); returns true if any joint raised
+__device__ bool prep_joints(const SfrArgs& a, int b, int lane, const SampleGeom& g, const double* rot) {
+    int bad = 0;
+    for (int j = lane; j < a.J; j += 32) {
+        float* un = a.uvd_norm + (static_cast<size_t>(b) * a.J + j) * 3;
+        JointParam jp;
+        if (g.ok) {
+            joint_param(jp, un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, g, rot);
+        } else {
+            jp.ok = 0; jp.cd = 0.0; jp.tx0 = jp.tx1 = jp.ty0 = jp.ty1 = 0;
+            jp.tap[0] = jp.tap[1] = jp.tap[2] = jp.tap[3] = 0.0;
+            un[0] = 0.f; un[1] = 0.f; un[2] = 0.f;
+        }
+        bad |= jp.ok ? 0 : 1;
+        a.prep_joints[static_cast<size_t>(b) * a.J + j] = jp;
+    }
+    return __any_sync(0xffffffffu, bad) != 0;
+}
+
+template <bool TRAIN, bool AUG>
 __global__ void __launch_bounds__(kPrepThreads)
 sfr_prep_kernel(SfrArgs a) {
     const int b = blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= a.B) return;
     SampleGeom* gp = a.prep_geom + b;
+    if (AUG) {
+        // augmented branch first (datasets.py:216-299); whatever raises in it falls back to the
+        // plain branch (:301), exactly like the reference's try / except
+        const double* au = a.aug + 8 * static_cast<size_t>(b);
+        if (lane == 0) {
+            SampleGeom g;
+            const double com2[3] = {__dadd_rn(a.com[3 * b + 0], au[1]), __dadd_rn(a.com[3 * b + 1], au[2]), a.com[3 * b + 2]};
+            sample_geometry(g, com2, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+            *gp = g;
+        }
+        __syncwarp();
+        const double rot[3] = {au[5], au[6], au[0]};
+        bool raised = !gp->ok;
+        if (!raised) raised = prep_joints(a, b, lane, *gp, rot);
+        raised = __any_sync(0xffffffffu, raised) != 0;
+        if (lane == 0) {
+            WarpParam wp;
+            wp.active = raised ? 0 : 1;
+            wp.scale = au[0];
+            // cv2.getRotationMatrix2D((64, 64), angle, scale) and cv::invertAffineTransform
+            const double alpha = __dmul_rn(au[3], au[0]), beta = __dmul_rn(au[4], au[0]), cx = 64.0, cy = 64.0;
+            const double m02 = __dsub_rn(__dmul_rn(__dsub_rn(1.0, alpha), cx), __dmul_rn(beta, cy));
+            const double m12 = __dadd_rn(__dmul_rn(beta, cx), __dmul_rn(__dsub_rn(1.0, alpha), cy));
+            double D = __dsub_rn(__dmul_rn(alpha, alpha), __dmul_rn(beta, -beta));
+            D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+            const double A11 = __dmul_rn(alpha, D), A22 = __dmul_rn(alpha, D);
+            const double A12 = __dmul_rn(-beta, D), A21 = __dmul_rn(beta, D);       // -M01*D, -M10*D
+            wp.iM[0] = A11; wp.iM[1] = A12;
+            wp.iM[2] = __dsub_rn(__dmul_rn(-A11, m02), __dmul_rn(A12, m12));
+            wp.iM[3] = A21; wp.iM[4] = A22;
+            wp.iM[5] = __dsub_rn(__dmul_rn(-A21, m02), __dmul_rn(A22, m12));
+            wp.pad = 0;
+            a.prep_warp[b] = wp;
+        }
+        if (!raised) {
+            if (lane == 0) { write_scalar_outputs(a, b, *gp); a.prep_flags[b] = 0; }
+            return;
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
         SampleGeom g;
         sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
         *gp = g;
-        a.gate[b] = 0u;
-        a.box_size[b] = static_cast<float>(g.nrows);     // datasets.py:319
-        a.cube_size[b] = static_cast<float>(g.cube);
-        a.com_out[3 * b + 0] = static_cast<float>(g.c0);
-        a.com_out[3 * b + 1] = static_cast<float>(g.r0);
-        a.com_out[3 * b + 2] = static_cast<float>(g.z);
+        write_scalar_outputs(a, b, g);
     }
     __syncwarp();
     if (TRAIN) {
-        const SampleGeom g = *gp;
-        int bad = 0;
-        for (int j = lane; j < a.J; j += 32) {
-            float* un = a.uvd_norm + (static_cast<size_t>(b) * a.J + j) * 3;
-            JointParam jp;
-            if (g.ok) {
-                joint_param(jp, un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, g);
-            } else {
-                jp.ok = 0; jp.cd = 0.0; jp.tx0 = jp.tx1 = jp.ty0 = jp.ty1 = 0;
-                jp.tap[0] = jp.tap[1] = jp.tap[2] = jp.tap[3] = 0.0;
-                un[0] = 0.f; un[1] = 0.f; un[2] = 0.f;
-            }
-            bad |= jp.ok ? 0 : 1;
-            a.prep_joints[static_cast<size_t>(b) * a.J + j] = jp;
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) a.prep_flags[b] = bad;
+        const bool bad = prep_joints(a, b, lane, *gp, nullptr);
+        if (lane == 0) a.prep_flags[b] = bad ? 1 : 0;
     }
 }
 
@@ -483,37 +587,175 @@ sfr_build_kernel(SfrArgs a) {
         }
     }
 
-    // ---- phase 2, pass B: the <= 8x8 footprint of every joint that touches this band, float64
-    // (<= 11 candidate rows x 11 candidate columns per joint, most rejected by integer tests;
-    // pass A zero-filled the maps before the barriers above, so CTA-scope order holds)
-    if (TRAIN && g.ok) {
-        constexpr int kCand = 11;    // offsets -3..3 around tap 0, then 0..3 around tap 1
-        const int total = band_list_n * kCand * kCand;
-        for (int c = tid; c < total; c += kThreads) {
-            const int jl = c / (kCand * kCand);
-            const int r = c - jl * (kCand * kCand);
-            const int sy = r / kCand, sx = r - sy * kCand;
-            const int j = band_list[jl];
-            const JointParam& jp = joints[j];
-            const int y = sy < 7 ? jp.ty0 + sy - 3 : jp.ty1 + sy - 7;
-            const int x = sx < 7 ? jp.tx0 + sx - 3 : jp.tx1 + sx - 7;
-            if (y < y_lo || y >= y_hi || x < 0 || x >= kLabel) continue;
-            if (sy >= 7 && abs(y - jp.ty0) <= 3) continue;     // already listed around tap 0
-            if (sx >= 7 && abs(x - jp.tx0) <= 3) continue;
-            const double wy0 = gauss_reach(y, jp.ty0), wy1 = gauss_reach(y, jp.ty1);
-            const double wx0 = gauss_reach(x, jp.tx0), wx1 = gauss_reach(x, jp.tx1);
-            // separable order of cv2.GaussianBlur: rows first, then columns
-            const double r0 = __dadd_rn(__dmul_rn(jp.tap[0], wx0), __dmul_rn(jp.tap[1], wx1));
-            const double r1 = __dadd_rn(__dmul_rn(jp.tap[2], wx0), __dmul_rn(jp.tap[3], wx1));
-            const double h = __dadd_rn(__dmul_rn(wy0, r0), __dmul_rn(wy1, r1));
-            const T lab = label_s[(y - y_lo) * kLabel + x];
-            const size_t o = (static_cast<size_t>(b) * a.J + j) * kMap + y * kLabel + x;
-            a.heatmaps[o] = __double2float_rn(h);
-            // datasets.py:372-374,380: (d_j - label) * [heat > 0] * mask / cube
-            if (h > 0.0 && lab != T(0))
-                a.dmap[o] = __double2float_rn(__ddiv_rn(__dsub_rn(jp.cd, static_cast<double>(lab)), g.cube));
+    // ---- phase 2, pass B: the <= 8x8 footprint of every joint that touches this band
+    // (pass A zero-filled the maps before the barriers above, so CTA-scope order holds)
+    if (TRAIN && g.ok)
+        patch_footprints<T>(a, g, joints, band_list, band_list_n, label_s, b, y_lo, y_hi, tid, kThreads);
+}
+
+// ---------------------------------------------------------------------------
+// augmented samples: one CTA per sample (the rotation mixes all rows of the image)
+// ---------------------------------------------------------------------------
+constexpr int kAugThreads = 512;
+
+template <typename T>
+struct AugSmem {
+    T img[kImage * kImage];          // un-normalised resized crop before the warp (datasets.py:271)
+    T label[kMap];                   // un-normalised label of the augmented image
+    TapX xtap[kImage], ytap[kImage];
+    int adelta[kImage], bdelta[kImage], x0[kImage], y0[kImage];   // cv::warpAffine fixed-point tables
+    SampleGeom geom;
+    WarpParam warp;
+    JointParam joints[PWR_MAX_JOINTS];
+    int list[PWR_MAX_JOINTS];
+    int list_n;
+    int count, nan_seen;
+};
+
+// One pixel of cv2.warpAffine(img, M, (128,128)) * scale (utils.py:75, datasets.py:284): 10-bit
+// fixed-point inverse map, source position quantised to 1/32 px, float table weights, BORDER_CONSTANT 0.
+template <typename T>
+__device__ __forceinline__ T warp_pixel(const AugSmem<T>& sm, int x, int y, T scale_t) {
+    const int X = (sm.x0[y] + sm.adelta[x]) >> 5, Y = (sm.y0[y] + sm.bdelta[x]) >> 5;
+    const int sx = X >> 5, sy = Y >> 5;
+    const float fx1 = static_cast<float>(X & 31) * 0.03125f, fy1 = static_cast<float>(Y & 31) * 0.03125f;
+    const float fx0 = __fsub_rn(1.f, fx1), fy0 = __fsub_rn(1.f, fy1);
+    const bool r0 = sy >= 0 && sy < kImage, r1 = sy + 1 >= 0 && sy + 1 < kImage;
+    const bool c0 = sx >= 0 && sx < kImage, c1 = sx + 1 >= 0 && sx + 1 < kImage;
+    const T s00 = (r0 && c0) ? sm.img[sy * kImage + sx] : T(0);
+    const T s01 = (r0 && c1) ? sm.img[sy * kImage + sx + 1] : T(0);
+    const T s10 = (r1 && c0) ? sm.img[(sy + 1) * kImage + sx] : T(0);
+    const T s11 = (r1 && c1) ? sm.img[(sy + 1) * kImage + sx + 1] : T(0);
+    T v = Arith<T>::mul(s00, static_cast<T>(__fmul_rn(fy0, fx0)));
+    v = Arith<T>::add(v, Arith<T>::mul(s01, static_cast<T>(__fmul_rn(fy0, fx1))));
+    v = Arith<T>::add(v, Arith<T>::mul(s10, static_cast<T>(__fmul_rn(fy1, fx0))));
+    v = Arith<T>::add(v, Arith<T>::mul(s11, static_cast<T>(__fmul_rn(fy1, fx1))));
+    return Arith<T>::mul(v, scale_t);
+}
+
+template <typename T, int FMT>
+__global__ void __launch_bounds__(kAugThreads)
+sfr_aug_kernel(SfrArgs a) {
+    extern __shared__ __align__(16) unsigned char aug_smem_raw[];
+    AugSmem<T>& sm = *reinterpret_cast<AugSmem<T>*>(aug_smem_raw);
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+
+    {   // prepared geometry / warp / joint taps -> shared memory
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.prep_geom + b);
+        if (tid < static_cast<int>(sizeof(SampleGeom) / 4)) reinterpret_cast<uint32_t*>(&sm.geom)[tid] = __ldcg(src + tid);
+        const uint32_t* ws = reinterpret_cast<const uint32_t*>(a.prep_warp + b);
+        if (tid >= 64 && tid < 64 + static_cast<int>(sizeof(WarpParam) / 4))
+            reinterpret_cast<uint32_t*>(&sm.warp)[tid - 64] = __ldcg(ws + tid - 64);
+        const uint32_t* js = reinterpret_cast<const uint32_t*>(a.prep_joints + static_cast<size_t>(b) * a.J);
+        const int words = a.J * static_cast<int>(sizeof(JointParam) / 4);
+        for (int i = tid; i < words; i += kAugThreads) reinterpret_cast<uint32_t*>(sm.joints)[i] = __ldcg(js + i);
+        if (tid == 0) { sm.list_n = 0; sm.count = 0; sm.nan_seen = 0; }
+    }
+    {   // pass A of phase 2: zero every map of the sample
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* hp = a.heatmaps + static_cast<size_t>(b) * a.J * kMap;
+        float* dp = a.dmap + static_cast<size_t>(b) * a.J * kMap;
+        for (int i = tid; i < a.J * (kMap / 4); i += kAugThreads) {
+            st_stream(hp + i * 4, zero4);
+            st_stream(dp + i * 4, zero4);
         }
     }
+    __syncthreads();
+    const SampleGeom g = sm.geom;
+    const bool warp_on = sm.warp.active != 0;
+    if (g.ok) {
+        if (tid < kImage) {
+            sm.xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);
+            // cv::warpAffine: adelta[x] = saturate_cast<int>(M[0]*x*1024), X0(y) = saturate_cast<int>((M[1]*y + M[2])*1024) + 16
+            const double* m = sm.warp.iM;
+            const double t = static_cast<double>(tid);
+            sm.adelta[tid] = __double2int_rn(__dmul_rn(__dmul_rn(m[0], t), 1024.0));
+            sm.bdelta[tid] = __double2int_rn(__dmul_rn(__dmul_rn(m[3], t), 1024.0));
+            sm.x0[tid] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], t), m[2]), 1024.0)) + 16;
+            sm.y0[tid] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], t), m[5]), 1024.0)) + 16;
+        } else if (tid < 2 * kImage) {
+            sm.ytap[tid - kImage] = linear_tap(tid - kImage, g.nrows, g.scale_y);
+        } else if (tid < 2 * kImage + a.J) {
+            const int j = tid - 2 * kImage;
+            if (sm.joints[j].ok) sm.list[atomicAdd(&sm.list_n, 1)] = j;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1a: the resized crop (datasets.py:271), one pixel per thread and iteration
+    const void* frame = static_cast<const unsigned char*>(a.frames) +
+                        static_cast<size_t>(b) * a.Hf * a.Wf * (FMT == FMT_F32 ? 4 : 2);
+    if (g.ok) {
+        for (int p = tid; p < kImage * kImage; p += kAugThreads) {
+            const int y = p >> 7, x = p & (kImage - 1);
+            const TapX ty = sm.ytap[y], tx = sm.xtap[x];
+            const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1, fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
+            const bool ra = fr_a >= g.pr0 && fr_a < g.pr1, rb = fr_b >= g.pr0 && fr_b < g.pr1;
+            const bool ca = fc_a >= g.pc0 && fc_a < g.pc1, cb = fc_b >= g.pc0 && fc_b < g.pc1;
+            const float v00 = (ra && ca) ? load_px<FMT>(frame, fr_a * a.Wf + fc_a) : 0.f;
+            const float v01 = (ra && cb) ? load_px<FMT>(frame, fr_a * a.Wf + fc_b) : 0.f;
+            const float v10 = (rb && ca) ? load_px<FMT>(frame, fr_b * a.Wf + fc_a) : 0.f;
+            const float v11 = (rb && cb) ? load_px<FMT>(frame, fr_b * a.Wf + fc_b) : 0.f;
+            const T w00 = Arith<T>::window(static_cast<T>(v00), g), w01 = Arith<T>::window(static_cast<T>(v01), g);
+            const T w10 = Arith<T>::window(static_cast<T>(v10), g), w11 = Arith<T>::window(static_cast<T>(v11), g);
+            const T xa0 = static_cast<T>(tx.a0), xa1 = static_cast<T>(tx.a1);
+            const T top = Arith<T>::add(Arith<T>::mul(w00, xa0), Arith<T>::mul(w01, xa1));
+            const T bot = Arith<T>::add(Arith<T>::mul(w10, xa0), Arith<T>::mul(w11, xa1));
+            sm.img[p] = Arith<T>::add(Arith<T>::mul(top, static_cast<T>(ty.a0)), Arith<T>::mul(bot, static_cast<T>(ty.a1)));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1b: rotate + scale (utils.py:74-75, datasets.py:284), 2x2 mean, outputs
+    float* img_b = a.img + static_cast<size_t>(b) * kImage * kImage;
+    float* lab_b = a.label_img + static_cast<size_t>(b) * kMap;
+    float* msk_b = a.mask + static_cast<size_t>(b) * kMap;
+    const T cube_t = static_cast<T>(g.cube);
+    const T cube_r = Arith<T>::rcp(cube_t);
+    const T scale_t = static_cast<T>(sm.warp.scale);
+    int my_count = 0, my_nan = 0;
+    for (int p = tid; p < kMap; p += kAugThreads) {
+        const int ly = p >> 6, lx = p & (kLabel - 1);
+        T lab = T(0);
+        float2 o0 = make_float2(0.f, 0.f), o1 = o0;
+        if (g.ok) {
+            T px[2][2];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+                    px[dy][dx] = warp_on ? warp_pixel<T>(sm, 2 * lx + dx, 2 * ly + dy, scale_t)
+                                         : sm.img[(2 * ly + dy) * kImage + 2 * lx + dx];
+            lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
+                                T(0.25));
+            o0 = make_float2(static_cast<float>(Arith<T>::div_by(px[0][0], cube_t, cube_r)),
+                             static_cast<float>(Arith<T>::div_by(px[0][1], cube_t, cube_r)));
+            o1 = make_float2(static_cast<float>(Arith<T>::div_by(px[1][0], cube_t, cube_r)),
+                             static_cast<float>(Arith<T>::div_by(px[1][1], cube_t, cube_r)));
+        }
+        const float labn = static_cast<float>(Arith<T>::div_by(lab, cube_t, cube_r));
+        const bool hand = g.ok && (lab != T(0));
+        *reinterpret_cast<float2*>(img_b + (2 * ly) * kImage + 2 * lx) = o0;
+        *reinterpret_cast<float2*>(img_b + (2 * ly + 1) * kImage + 2 * lx) = o1;
+        lab_b[p] = g.ok ? labn : 0.f;
+        msk_b[p] = hand ? 1.f : 0.f;
+        sm.label[p] = lab;
+        my_count += hand ? 1 : 0;
+        my_nan |= (isnan(o0.x) || isnan(o0.y) || isnan(o1.x) || isnan(o1.y) || isnan(labn)) ? 1 : 0;
+    }
+    {
+        int c = my_count, n = my_nan;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); n |= __shfl_xor_sync(0xffffffffu, n, o); }
+        if ((tid & 31) == 0) { atomicAdd(&sm.count, c); atomicOr(&sm.nan_seen, n); }
+    }
+    __syncthreads();
+    if (tid == 0)   // reject gate, datasets.py:362-365, 385-390 (one CTA owns the whole sample)
+        a.valid[b] = (g.ok && !a.prep_flags[b] && !sm.nan_seen && sm.count >= 10) ? 1 : 0;
+
+    // ---- phase 2, pass B
+    if (g.ok) patch_footprints<T>(a, g, sm.joints, sm.list, sm.list_n, sm.label, b, 0, kLabel, tid, kAugThreads);
 }
 
 // ---------------------------------------------------------------------------
@@ -559,12 +801,13 @@ sfr_com_kernel(const float* __restrict__ frames, int Hf, int Wf, double* __restr
     }
 }
 
-// workspace layout: [B] SampleGeom | [B*J] JointParam | [B] int joints_bad | [B] u32 gate
+// workspace layout: [B] SampleGeom | [B*J] JointParam | [B] int joints_bad | [B] u32 gate | [B] WarpParam
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t workspace_bytes(int B, int J) {
     return align_up(sizeof(SampleGeom) * static_cast<size_t>(B), 256) +
            align_up(sizeof(JointParam) * static_cast<size_t>(B) * (J > 0 ? J : 0), 256) +
-           align_up(sizeof(int) * static_cast<size_t>(B), 256) + align_up(sizeof(unsigned int) * static_cast<size_t>(B), 256);
+           align_up(sizeof(int) * static_cast<size_t>(B), 256) + align_up(sizeof(unsigned int) * static_cast<size_t>(B), 256) +
+           align_up(sizeof(WarpParam) * static_cast<size_t>(B), 256);
 }
 static void carve_workspace(SfrArgs& a, void* ws) {
     unsigned char* p = static_cast<unsigned char*>(ws);
@@ -575,13 +818,33 @@ static void carve_workspace(SfrArgs& a, void* ws) {
     a.prep_flags = reinterpret_cast<int*>(p);
     p += align_up(sizeof(int) * static_cast<size_t>(a.B), 256);
     a.gate = reinterpret_cast<unsigned int*>(p);
+    p += align_up(sizeof(unsigned int) * static_cast<size_t>(a.B), 256);
+    a.prep_warp = reinterpret_cast<WarpParam*>(p);
 }
 
 template <bool TRAIN>
 static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t stream) {
     if (fmt != FMT_F32 && fmt != FMT_GB16 && fmt != FMT_U16) return PWR_E_METHOD;
     if (frame_f64 && fmt != FMT_F32) return PWR_E_METHOD;       // float64 semantics exist for decoded frames only
-    sfr_prep_kernel<TRAIN><<<(a.B + kPrepThreads / 32 - 1) / (kPrepThreads / 32), kPrepThreads, 0, stream>>>(a);
+    const unsigned prep_grid = (a.B + kPrepThreads / 32 - 1) / (kPrepThreads / 32);
+    if (TRAIN && a.aug != nullptr) {
+        // augmented batch: one CTA per sample, the whole resized image staged in shared memory
+        sfr_prep_kernel<true, true><<<prep_grid, kPrepThreads, 0, stream>>>(a);
+        if (int rc = launch_status()) return rc;
+#define PWR_LAUNCH_AUG(T, F)                                                                                  \
+    do {                                                                                                      \
+        cudaFuncSetAttribute(sfr_aug_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                             static_cast<int>(sizeof(AugSmem<T>)));                                           \
+        sfr_aug_kernel<T, F><<<a.B, kAugThreads, sizeof(AugSmem<T>), stream>>>(a);                            \
+    } while (0)
+        if (frame_f64)            PWR_LAUNCH_AUG(double, FMT_F32);
+        else if (fmt == FMT_F32)  PWR_LAUNCH_AUG(float, FMT_F32);
+        else if (fmt == FMT_GB16) PWR_LAUNCH_AUG(float, FMT_GB16);
+        else                      PWR_LAUNCH_AUG(float, FMT_U16);
+#undef PWR_LAUNCH_AUG
+        return launch_status();
+    }
+    sfr_prep_kernel<TRAIN, false><<<prep_grid, kPrepThreads, 0, stream>>>(a);
     if (int rc = launch_status()) return rc;
     const unsigned grid = static_cast<unsigned>(a.B) * kBands;
     if (frame_f64)            sfr_build_kernel<double, FMT_F32, TRAIN><<<grid, kThreads, 0, stream>>>(a);
@@ -628,14 +891,15 @@ extern "C" int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf
     if (workspace_size < workspace_bytes(B, 0)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  nullptr, nullptr, nullptr, valid, B, 0, nullptr, nullptr, nullptr, nullptr,
-                 prefilter_margin, prefilter_umax, prefilter_vmax};
+                 prefilter_margin, prefilter_umax, prefilter_vmax, nullptr, nullptr};
     carve_workspace(a, workspace);
     return launch_sfr<false>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf, const double* com,
-                             const double* cube, const double* uvd, double fx, double fy, int frame_f64,
-                             double prefilter_margin, double prefilter_umax, double prefilter_vmax, float* img,
+                             const double* cube, const double* uvd, const double* aug, double fx, double fy,
+                             int frame_f64, double prefilter_margin, double prefilter_umax, double prefilter_vmax,
+                             float* img,
                              float* label_img,
                              float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
                              float* heatmaps, float* dmap, uint8_t* valid, void* workspace, size_t workspace_size,
@@ -651,7 +915,7 @@ extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int W
     if (workspace_size < workspace_bytes(B, J)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  uvd_norm, heatmaps, dmap, valid, B, J, nullptr, nullptr, nullptr, nullptr,
-                 prefilter_margin, prefilter_umax, prefilter_vmax};
+                 prefilter_margin, prefilter_umax, prefilter_vmax, aug, nullptr};
     carve_workspace(a, workspace);
     return launch_sfr<true>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }

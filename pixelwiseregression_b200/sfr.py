@@ -43,14 +43,50 @@ def center_of_mass(frames):
 _FRAME_DTYPES = {"f32": torch.float32, "nyu_gb16": torch.uint16, "u16": torch.uint16}
 
 
+def draw_augmentation(batch, generator=None, rotation=True, scale=True, shift=True):
+    """The random draws of the reference's augmented branch for `batch` samples, as a float64
+    [B,4] array (scale, shift_u, shift_v, angle_deg): scale = 0.8 + U*0.4 (datasets.py:230),
+    shifts = -5 + U*10 (:236-237), angle = U*60 - 30.  Upstream quirks kept: the rotation is
+    redrawn inside random_rotated and applied whenever ANY augmentation is on (utils.py:72),
+    and the "mm" shift lands on the pixel coordinates of the centre (uvd2xyz is a no-op on a
+    1-D array, :238-241).  `generator`: a numpy Generator (default: fresh, unseeded)."""
+    rng = generator if generator is not None else np.random.default_rng()
+    aug = np.empty((batch, 4), dtype=np.float64)
+    aug[:, 0] = 0.8 + rng.random(batch) * 0.4 if scale else 1.0
+    aug[:, 1] = -5 + rng.random(batch) * 10 if shift else 0.0
+    aug[:, 2] = -5 + rng.random(batch) * 10 if shift else 0.0
+    aug[:, 3] = rng.random(batch) * 60 - 30
+    if not (rotation or scale or shift):
+        return None
+    return aug
+
+
+def _aug_device_params(aug, B, device):
+    """[B,4] (scale, shift_u, shift_v, angle_deg) -> the [B,8] float64 block of include/pwr.h.
+    The trigonometry is done here in float64 NumPy (the reference's libm), not on the GPU."""
+    aug = np.asarray(aug.cpu() if isinstance(aug, torch.Tensor) else aug, dtype=np.float64)
+    if aug.shape != (B, 4):
+        raise _lib.PwrError("augment must be [B, 4] = (scale, shift_u, shift_v, angle_deg)")
+    a_m = aug[:, 3] * (np.pi / 180)          # cv2.getRotationMatrix2D: angle *= CV_PI/180
+    a_j = aug[:, 3] / 180.0 * np.pi          # utils.py:77
+    out = np.zeros((B, 8), dtype=np.float64)
+    out[:, 0:3] = aug[:, 0:3]
+    out[:, 3], out[:, 4] = np.cos(a_m), np.sin(a_m)
+    out[:, 5], out[:, 6] = np.cos(a_j), np.sin(a_j)
+    return torch.from_numpy(out).to(device)
+
+
 def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only=False, frame_format="f32",
-              prefilter=None):
+              prefilter=None, augment=None):
     """frames [B,Hf,Wf] CUDA depth frames: float32 mm (`frame_format="f32"`, what
     process_single_data receives), or raw sensor samples decoded on the fly exactly as
     the reference's loaders do: "nyu_gb16" = uint16 G<<8|B of the NYU PNG
     (datasets.py:810), "u16" = 16-bit grey PNG (ICVL :632, HAND17 :940).
     `prefilter=(margin, halfu, halfv)` applies the hand rectangle of load_from_text
     (NYU/HAND17 margin 40, ICVL 30; datasets.py:841-853) inside the crop taps.
+    `augment` = [B,4] (scale, shift_u, shift_v, angle_deg), e.g. from `draw_augmentation`: the
+    reference's augmented branch (datasets.py:216-299, train.py's default flags) with these
+    draws; samples whose augmented branch would raise fall back to the plain branch.
     com [B,3] float64 hand
     centre (u, v, z) or None to use the centre-of-mass fallback; cube [B] (or a
     scalar) half cube size; uvd [B,J,3] float64 joint annotations (train mode).
@@ -96,6 +132,8 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     ws_bytes = int(lib.pwr_sfr_workspace_bytes(B, J))
     workspace = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)     # scratch, no init needed
     if test_only:
+        if augment is not None:
+            raise _lib.PwrError("you can not transform the test data")     # datasets.py:64-65
         with torch.cuda.device(dev), _lib.timed("pwr_sfr_crop"):
             rc = lib.pwr_sfr_crop(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
                                   pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
@@ -111,8 +149,9 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     uvd_norm = torch.empty(B, J, 3, **f32)
     heatmaps = torch.empty(B, J, 64, 64, **f32)
     dmap = torch.empty(B, J, 64, 64, **f32)
+    aug_dev = _aug_device_params(augment, B, dev) if augment is not None else None
     with torch.cuda.device(dev), _lib.timed("pwr_sfr_build"):
-        rc = lib.pwr_sfr_build(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), ptr(uvd), float(fx), float(fy),
+        rc = lib.pwr_sfr_build(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), ptr(uvd), ptr(aug_dev), float(fx), float(fy),
                                int(frame_f64), pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
                                ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), ptr(workspace),
                                ws_bytes, B, J, s)

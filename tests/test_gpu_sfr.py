@@ -102,6 +102,60 @@ def test_prefilter_rectangle_python_slice_semantics():
     assert (got["img"] == ref["img"]).all()
 
 
+AUG_SETS = ["sfr_nyu_aug", "sfr_nyu_aug_fallback", "sfr_msra_aug"]
+
+
+def gpu_on_aug(g):
+    shape = golden_shape(g)
+    out = sfr.build_sfr(torch.from_numpy(g["frames"]).cuda(), None if shape.com_from_frame else g["com"], g["cube"],
+                        g["uvd"], fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64, augment=g["aug"])
+    torch.cuda.synchronize()
+    d = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    d["dmap"] = d.pop("depthmaps")
+    return d
+
+
+@pytest.mark.parametrize("name", AUG_SETS)
+def test_gpu_augmented_branch_matches_reference(name):
+    """The reference's augmented branch (shift, cv2.warpAffine rotation + scale, joint rotation)
+    replayed on the GPU with the reference's own recorded random draws, including samples that
+    fall back to the plain branch."""
+    g = load_golden(name)
+    got = gpu_on_aug(g)
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS}
+    assert_sfr_matches(got, ref, SFR_FIELDS, g["ref_valid"], prefix=name + ":")
+
+
+@pytest.mark.parametrize("name", AUG_SETS)
+def test_gpu_augmented_bitwise_equal_oracle(name):
+    from test_oracle_sfr import oracle_on_aug_golden
+    g = load_golden(name)
+    got, ref = gpu_on_aug(g), oracle_on_aug_golden(g)
+    for n in ("img", "label_img", "mask", "box_size", "com"):
+        assert (got[n] == ref[n]).all(), n
+    assert_sfr_matches(got, ref, SFR_FIELDS, ref["valid"])
+
+
+def test_gpu_augmented_seeded_batch_matches_oracle():
+    shape = synth.NYU
+    B = 32
+    d = synth.make_frames(shape, B, 41)
+    aug = sfr.draw_augmentation(B, np.random.default_rng(5))
+    ref = so.process_batch(d["frames"], d["uvd"], d["com"], d["cube"], shape.fx, shape.fy, aug=aug)
+    out = sfr.build_sfr(torch.from_numpy(d["frames"]).cuda(), d["com"], d["cube"], d["uvd"], fx=shape.fx, fy=shape.fy,
+                        augment=aug)
+    got = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    got["dmap"] = got.pop("depthmaps")
+    assert_sfr_matches(got, ref, SFR_FIELDS, ref["valid"])
+    assert (got["img"] == ref["img"]).all()
+    # augmentation actually changes the sample
+    plain = so.process_batch(d["frames"], d["uvd"], d["com"], d["cube"], shape.fx, shape.fy)
+    assert np.abs(plain["img"] - ref["img"]).max() > 1e-3
+    with pytest.raises(Exception):
+        sfr.build_sfr(torch.from_numpy(d["frames"]).cuda(), d["com"], d["cube"], fx=shape.fx, fy=shape.fy,
+                      test_only=True, augment=aug)
+
+
 def test_gpu_test_only_matches_oracle():
     shape = synth.NYU
     d = synth.make_frames(shape, 8, 7)

@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--cpu-samples", type=int, default=512, help="samples in the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--augment", action="store_true",
+                    help="build the SFR targets through the augmented branch (datasets.py:216-299, train.py defaults)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager decoder baseline on the GPU")
     return ap.parse_args()
@@ -238,6 +240,9 @@ def run_b200(args):
         frames = frames.round().clamp_(0, 65535).to(torch.int32).to(torch.uint16)      # sensor counts (mm)
         sfr_kw.update(frame_format=args.frame_format, prefilter=(40.0, shape.halfu, shape.halfv), frame_f64=False)
         d["frames"] = frames
+    if args.augment:
+        import numpy as np
+        sfr_kw["augment"] = sfr.draw_augmentation(B, np.random.default_rng(rank))
 
     def step(frames_, com_, cube_, uvd_, z_, D_, kw=None):
         """The public-API call sequence a training loop makes for this path."""
@@ -387,7 +392,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(shape, B), "batch_per_gpu": B, "joints": J,
-                       "frame_format": args.frame_format,
+                       "frame_format": args.frame_format, "augment": bool(args.augment),
                        "alpha": alpha, "lambda_h": lambda_h, "lambda_d": lambda_d,
                        "l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
                              % (frames.numel() * frames.element_size() / 1e9, z.numel() * 4 / 1e9),

@@ -49,6 +49,15 @@ extern "C" {
                                     DepthRegression.forward is called on its
                                     own with caller-supplied heat maps :116 */
 
+/* element type of the conv outputs z, D, of gD_up and of the gradients gz, gD
+ * (`map_dtype`): float32, or the float16 / bfloat16 tensors autocast hands over
+ * under --mixed_precision (train.py:170-172).  All arithmetic is float32, as
+ * autocast runs softmax / sum / mul-with-a-float32-operand; every other map
+ * (L, m, H, targets, gH_up) is float32. */
+#define PWR_DTYPE_F32  0
+#define PWR_DTYPE_F16  1
+#define PWR_DTYPE_BF16 2
+
 int pwr_version(void);
 const char* pwr_error_string(int rc);
 
@@ -154,12 +163,12 @@ int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
  *   log2 units, 1/sum, masked-heat sum + 1e-14, d) saved for the backward
  *   (NULL = do not store); loss_partial [B,J,3] per-(b,j) sums of squares
  *   (heat, dmap, uvd) before lambda/mean scaling (NULL = no loss). */
-int pwr_decoder_fwd(const float* z, const float* w, const float* D,
+int pwr_decoder_fwd(const void* z, const float* w, const void* D,
                     const float* L, const float* m,
                     const float* heat_gt, const float* dmap_gt,
                     const float* uvd_gt,
                     float* H, float* uvd, float* stats, float* loss_partial,
-                    int B, int J, int method, void* stream);
+                    int B, int J, int method, int map_dtype, void* stream);
 
 /* Backward of pwr_decoder_fwd (what autograd derives from model.py:79-132).
  *   g_uvd [B,J,3] upstream gradient on uvd (NULL = zeros);
@@ -169,12 +178,12 @@ int pwr_decoder_fwd(const float* z, const float* w, const float* D,
  * outputs: gz, gD [B,J,64,64] (either may be NULL = not wanted); gw_partial
  *   [B,J] (sum over pixels of dL/d(w z) * z; reduce over B with
  *   pwr_reduce_partials; NULL unless PWR_METHOD_SOFTMAX). */
-int pwr_decoder_bwd(const float* z, const float* w, const float* D,
+int pwr_decoder_bwd(const void* z, const float* w, const void* D,
                     const float* L, const float* m, const float* stats,
                     const float* uvd, const float* g_uvd,
-                    const float* gH_up, const float* gD_up,
-                    float* gz, float* gD, float* gw_partial,
-                    int B, int J, int method, void* stream);
+                    const float* gH_up, const void* gD_up,
+                    void* gz, void* gD, float* gw_partial,
+                    int B, int J, int method, int map_dtype, void* stream);
 
 /* Backward fused with the stage loss of train.py:197-205:
  *   loss = alpha*mean(sum (uvd-uvd_gt)^2) + (1-alpha)*(lambda_h*mean(sum
@@ -187,18 +196,18 @@ int pwr_decoder_bwd(const float* z, const float* w, const float* D,
  * uvd) BEFORE lambda/mean scaling (NULL = not wanted; the target maps are
  * then only read if their weight (1-alpha)*lambda is non-zero).  `n_mean` is
  * the B*J of the mean (the global batch under data parallelism; 0 = B*J). */
-int pwr_decoder_bwd_loss(const float* z, const float* w, const float* D,
+int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D,
                          const float* L, const float* m, const float* stats,
                          const float* uvd, const float* g_uvd,
-                         const float* gH_up, const float* gD_up,
+                         const float* gH_up, const void* gD_up,
                          const float* heat_gt, const float* dmap_gt,
                          const float* uvd_gt,
                          float alpha, float lambda_h, float lambda_d,
                          float loss_scale, const float* loss_scale_dev,
                          int n_mean,
-                         float* gz, float* gD, float* gw_partial,
+                         void* gz, void* gD, float* gw_partial,
                          float* loss_partial,
-                         int B, int J, int method, void* stream);
+                         int B, int J, int method, int map_dtype, void* stream);
 
 /* Deterministic sum over the batch axis: out[j*C + c] = sum_b in[(b*J+j)*C+c]
  * (gw_partial -> gw: C=1; loss_partial -> per-joint sums: C=3). */
@@ -213,10 +222,10 @@ int pwr_stage_loss(const float* loss_partial, int B, int J,
                    float lambda_h, float lambda_d, float alpha, int n_mean,
                    float* out4, void* stream);
 
-/* In-place multiply n floats by *scale_dev (device scalar); used to apply a
+/* In-place multiply n elements (n % 4 == 0, element type map_dtype) by *scale_dev (device scalar); used to apply a
  * non-unit upstream gradient to gradients that were produced eagerly. */
-int pwr_scale_inplace(float* x, const float* scale_dev, long long n,
-                      void* stream);
+int pwr_scale_inplace(void* x, const float* scale_dev, long long n,
+                      int map_dtype, void* stream);
 
 /* utils.py:332-337 recover_uvd fused with uvd2xyz datasets.py:100-111:
  *   uvd_px = uvd_norm * (box-1 | box-1 | cube) + com ; xyz = ((u-halfu)/fx*d,

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PWR_LIB_PATH") or os.path.join(_PKG, "libpwr_b200.so"
 METHOD_SOFTMAX, METHOD_SUM, METHOD_GIVEN = 0, 1, 2
 METHODS = {"softmax": METHOD_SOFTMAX, "sum": METHOD_SUM, "given": METHOD_GIVEN}
 FRAME_FORMATS = {"f32": 0, "nyu_gb16": 1, "u16": 2}
+MAP_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -33,12 +34,12 @@ SIGNATURES = {
     "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
     "pwr_sfr_build": [_P, _I, _I, _I, _P, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                       _P, _SZ, _I, _I, _P],
-    "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _P],
-    "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _P],
-    "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _P],
+    "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _I, _P],
+    "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _I, _P],
+    "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _I, _P],
     "pwr_reduce_partials": [_P, _P, _I, _I, _I, _P],
     "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P],
-    "pwr_scale_inplace": [_P, _P, _LL, _P],
+    "pwr_scale_inplace": [_P, _P, _LL, _I, _P],
     "pwr_recover_uvd": [_P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _I, _I, _P],
     "pwr_joint_error": [_P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _I, _I, _P],
 }

@@ -19,9 +19,68 @@
 // synthesised from the indices: sums are taken over the integer offsets
 // (x-32), (y-32) and scaled by 1/63 once.
 #include <cstdlib>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace pwr {
+
+// Element type of the conv outputs z, D and of their gradients: float32, or the
+// float16 / bfloat16 tensors autocast produces under --mixed_precision (train.py:170-172).  The
+// arithmetic is float32 either way (what autocast does for softmax / sum / mul with a float32
+// operand); only the HBM traffic of z, D, gz, gD halves.
+template <typename TZ> struct MapIO;
+template <> struct MapIO<float> {
+    static __device__ __forceinline__ float4 ld(const void* base, size_t e) {
+        return __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(base) + e));
+    }
+    static __device__ __forceinline__ void st(void* base, size_t e, float4 v) {
+        __stcs(reinterpret_cast<float4*>(static_cast<float*>(base) + e), v);
+    }
+    static __device__ __forceinline__ float4 smem(const void* slot, int chunk) {
+        return static_cast<const float4*>(slot)[chunk];
+    }
+};
+template <> struct MapIO<__half> {
+    static __device__ __forceinline__ float4 cvt(uint2 r) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ float4 ld(const void* base, size_t e) {
+        return cvt(__ldcs(reinterpret_cast<const uint2*>(static_cast<const __half*>(base) + e)));
+    }
+    static __device__ __forceinline__ void st(void* base, size_t e, float4 v) {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned int*>(&a);
+        r.y = *reinterpret_cast<const unsigned int*>(&b);
+        __stcs(reinterpret_cast<uint2*>(static_cast<__half*>(base) + e), r);
+    }
+    static __device__ __forceinline__ float4 smem(const void* slot, int chunk) {
+        return cvt(static_cast<const uint2*>(slot)[chunk]);
+    }
+};
+template <> struct MapIO<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 cvt(uint2 r) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ float4 ld(const void* base, size_t e) {
+        return cvt(__ldcs(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(base) + e)));
+    }
+    static __device__ __forceinline__ void st(void* base, size_t e, float4 v) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned int*>(&a);
+        r.y = *reinterpret_cast<const unsigned int*>(&b);
+        __stcs(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + e), r);
+    }
+    static __device__ __forceinline__ float4 smem(const void* slot, int chunk) {
+        return cvt(static_cast<const uint2*>(slot)[chunk]);
+    }
+};
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kEps = 1e-14f;             // model.py:89,128
@@ -83,9 +142,9 @@ __device__ __forceinline__ float heat_raw(float z, float c, float off) {
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int METHOD, bool LOSS>
+template <int METHOD, bool LOSS, typename TZ>
 __global__ void __launch_bounds__(kThreads)
-decoder_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ D,
+decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, const void* __restrict__ D,
                    const float* __restrict__ L, const float* __restrict__ m,
                    const float* __restrict__ heat_gt, const float* __restrict__ dmap_gt,
                    const float* __restrict__ uvd_gt, float* __restrict__ H,
@@ -100,14 +159,14 @@ decoder_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, con
 
     float4 zv[kVec], dv[kVec], lv[kVec], mv[kVec];
 #pragma unroll
-    for (int i = 0; i < kVec; ++i) zv[i] = ld_stream(z + off + i * (kThreads * 4));
+    for (int i = 0; i < kVec; ++i) zv[i] = MapIO<TZ>::ld(z, off + i * (kThreads * 4));
     if (depth) {
 #pragma unroll
         for (int i = 0; i < kVec; ++i) mv[i] = ld_keep(m + offb + i * (kThreads * 4));
 #pragma unroll
         for (int i = 0; i < kVec; ++i) lv[i] = ld_keep(L + offb + i * (kThreads * 4));
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) dv[i] = ld_stream(D + off + i * (kThreads * 4));
+        for (int i = 0; i < kVec; ++i) dv[i] = MapIO<TZ>::ld(D, off + i * (kThreads * 4));
     } else {
 #pragma unroll
         for (int i = 0; i < kVec; ++i) mv[i] = lv[i] = dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -191,15 +250,15 @@ struct LossCoef {
 // the target maps are only read when they matter (non-zero map weights or
 // loss_partial requested), so the default alpha = 1 costs no extra traffic
 // unless the caller wants the logged loss values.
-template <int METHOD, bool LOSS>
+template <int METHOD, bool LOSS, typename TZ>
 __global__ void __launch_bounds__(kThreads)
-decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ D,
+decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, const void* __restrict__ D,
                    const float* __restrict__ L, const float* __restrict__ m, const float* __restrict__ stats,
                    const float* __restrict__ uvd, const float* __restrict__ g_uvd,
-                   const float* __restrict__ gH_up, const float* __restrict__ gD_up,
+                   const float* __restrict__ gH_up, const void* __restrict__ gD_up,
                    const float* __restrict__ heat_gt, const float* __restrict__ dmap_gt,
                    const float* __restrict__ uvd_gt, LossCoef coef,
-                   float* __restrict__ gz, float* __restrict__ gD, float* __restrict__ gw_partial,
+                   void* __restrict__ gz, void* __restrict__ gD, float* __restrict__ gw_partial,
                    float* __restrict__ loss_partial, int J) {
     __shared__ float scratch[kWarps * 3];
     if (LOSS && coef.scale_dev != nullptr) {
@@ -216,7 +275,7 @@ decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, con
 
     float4 zv[kVec], pv[kVec], gv[kVec];   // logits, heat p, dL/dp
 #pragma unroll
-    for (int i = 0; i < kVec; ++i) zv[i] = ld_stream(z + off + i * (kThreads * 4));
+    for (int i = 0; i < kVec; ++i) zv[i] = MapIO<TZ>::ld(z, off + i * (kThreads * 4));
 
     const float4 st = reinterpret_cast<const float4*>(stats)[bj];   // (shift, 1/sum, den, d)
     const float wj = (METHOD == PWR_METHOD_SOFTMAX) ? w[j] : 1.f;
@@ -242,10 +301,10 @@ decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, con
         const size_t o = off + i * (kThreads * 4);
         const size_t ob = offb + i * (kThreads * 4);
         float4 d4 = zero4, l4 = zero4, m4 = zero4, hg = zero4, dg = zero4, uh = zero4, ud = zero4;
-        if (depth) { d4 = ld_stream(D + o); l4 = ld_keep(L + ob); m4 = ld_keep(m + ob); }
+        if (depth) { d4 = MapIO<TZ>::ld(D, o); l4 = ld_keep(L + ob); m4 = ld_keep(m + ob); }
         if (map_loss) { hg = ld_stream(heat_gt + o); if (depth) dg = ld_stream(dmap_gt + o); }
         if (gH_up != nullptr) uh = ld_stream(gH_up + o);
-        if (gD_up != nullptr) ud = ld_stream(gD_up + o);
+        if (gD_up != nullptr) ud = MapIO<TZ>::ld(gD_up, o);
         const float gyrow = gv63 * (pc.ys0 + 16.f * i);
         float4 gd4;
 #pragma unroll
@@ -271,7 +330,7 @@ decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, con
             set_comp(gv[i], k, gp);
             set_comp(gd4, k, gdk);
         }
-        if (gD != nullptr) st_stream(gD + o, gd4);
+        if (gD != nullptr) MapIO<TZ>::st(gD, o, gd4);
     }
     if (METHOD != PWR_METHOD_GIVEN || LOSS) block_sum<3>(acc, scratch);
 
@@ -296,7 +355,7 @@ decoder_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, con
                 }
                 set_comp(g4, k, g);
             }
-            st_stream(gz + off + i * (kThreads * 4), g4);
+            MapIO<TZ>::st(gz, off + i * (kThreads * 4), g4);
         }
     }
     if (METHOD == PWR_METHOD_SOFTMAX && gw_partial != nullptr) {
@@ -383,17 +442,17 @@ __device__ __forceinline__ void pipe_block_sum(float (&v)[N], float* scratch) {
 }
 
 struct PipeArgs {
-    const float* z; const float* w; const float* D; const float* L; const float* m;
+    const void* z; const float* w; const void* D; const float* L; const float* m;
     const float* stats; const float* uvd; const float* g_uvd;
-    const float* slot2; const float* slot3;    // (heat_gt, dmap_gt) or (gH_up, gD_up); either may be NULL
+    const float* slot2; const void* slot3;     // (heat_gt, dmap_gt) or (gH_up, gD_up); either may be NULL
     const float* uvd_gt;
     LossCoef coef;
-    float* gz; float* gD; float* gw_partial; float* loss_partial;
+    void* gz; void* gD; float* gw_partial; float* loss_partial;
     int J; int items;
     int slots_are_targets;                     // 1: slot2/3 = heat_gt/dmap_gt, 0: = gH_up/gD_up
 };
 
-template <int METHOD, bool LOSS>
+template <int METHOD, bool LOSS, typename TZ>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 decoder_bwd_pipe_kernel(PipeArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -418,7 +477,10 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
     __syncthreads();
 
     const bool has2 = a.slot2 != nullptr, has3 = a.slot3 != nullptr;
-    const uint32_t stage_tx = (2 + (has2 ? 1 : 0) + (has3 ? 1 : 0)) * kSlotBytes;
+    const bool tg = a.slots_are_targets != 0;
+    constexpr uint32_t kZBytes = kMap * sizeof(TZ);                  // z, D (and gD_up) in the conv dtype
+    const uint32_t slot3_bytes = tg ? kSlotBytes : kZBytes;          // dmap_gt is float32, gD_up is TZ
+    const uint32_t stage_tx = 2 * kZBytes + (has2 ? kSlotBytes : 0) + (has3 ? slot3_bytes : 0);
 
     // producer (thread 0): stream item `it` into stage `s`; fetch L, m when the sample changes
     auto issue = [&](long long it, int s, int prev_b, int lm_buf) {
@@ -427,10 +489,13 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
         float* st = stage_base + s * 4 * kMap;
         const bool new_lm = (b != prev_b);
         mbar_expect_tx(&full[s], stage_tx + (new_lm ? 2 * kSlotBytes : 0));
-        bulk_g2s(st, a.z + off, kSlotBytes, &full[s]);
-        bulk_g2s(st + kMap, a.D + off, kSlotBytes, &full[s]);
+        bulk_g2s(st, static_cast<const TZ*>(a.z) + off, kZBytes, &full[s]);
+        bulk_g2s(st + kMap, static_cast<const TZ*>(a.D) + off, kZBytes, &full[s]);
         if (has2) bulk_g2s(st + 2 * kMap, a.slot2 + off, kSlotBytes, &full[s]);
-        if (has3) bulk_g2s(st + 3 * kMap, a.slot3 + off, kSlotBytes, &full[s]);
+        if (has3) {
+            if (tg) bulk_g2s(st + 3 * kMap, static_cast<const float*>(a.slot3) + off, kSlotBytes, &full[s]);
+            else    bulk_g2s(st + 3 * kMap, static_cast<const TZ*>(a.slot3) + off, kZBytes, &full[s]);
+        }
         if (new_lm) {
             float* lm = lm_base + lm_buf * 2 * kMap;
             bulk_g2s(lm, a.L + static_cast<size_t>(b) * kMap, kSlotBytes, &full[s]);
@@ -475,25 +540,24 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
         const float gdd = gd / st.z;
         const float dcoord = st.w;
 
-        const float4* sz = reinterpret_cast<const float4*>(stage_base + s * 4 * kMap);
-        const float4* sD = sz + kMap / 4;
-        const float4* s2 = sz + 2 * (kMap / 4);
-        const float4* s3 = sz + 3 * (kMap / 4);
+        const float* sz = stage_base + s * 4 * kMap;          // slot bases (each slot is 16 KiB apart)
+        const float* sD = sz + kMap;
+        const float4* s2 = reinterpret_cast<const float4*>(sz + 2 * kMap);
+        const float* s3 = sz + 3 * kMap;
         const float4* sL = reinterpret_cast<const float4*>(lm_base + lm_cur * 2 * kMap);
         const float4* sM = sL + kMap / 4;
 
         mbar_wait(&full[s], parity);
 
-        const bool tg = a.slots_are_targets != 0;
         float4 pv[kPipeVec], gv[kPipeVec];
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < kPipeVec; ++i) {
             const int cidx = tid + i * kPipeThreads;
-            const float4 z4 = sz[cidx], d4 = sD[cidx], l4 = sL[cidx], m4 = sM[cidx];
+            const float4 z4 = MapIO<TZ>::smem(sz, cidx), d4 = MapIO<TZ>::smem(sD, cidx), l4 = sL[cidx], m4 = sM[cidx];
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 q2 = has2 ? s2[cidx] : zero4;
-            const float4 q3 = has3 ? s3[cidx] : zero4;
+            const float4 q3 = has3 ? (tg ? MapIO<float>::smem(s3, cidx) : MapIO<TZ>::smem(s3, cidx)) : zero4;
             const float gyrow = gv63 * (ys0 + 32.f * i);
             float4 gd4;
 #pragma unroll
@@ -518,7 +582,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
                 set_comp(gv[i], kk, gp);
                 set_comp(gd4, kk, gdk);
             }
-            if (a.gD != nullptr) st_stream(a.gD + static_cast<size_t>(bj) * kMap + cidx * 4, gd4);
+            if (a.gD != nullptr) MapIO<TZ>::st(a.gD, static_cast<size_t>(bj) * kMap + cidx * 4, gd4);
         }
         if (METHOD != PWR_METHOD_GIVEN || LOSS) pipe_block_sum<3>(acc, scratch);
 
@@ -528,7 +592,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
 #pragma unroll
             for (int i = 0; i < kPipeVec; ++i) {
                 const int cidx = tid + i * kPipeThreads;
-                const float4 z4 = sz[cidx];
+                const float4 z4 = MapIO<TZ>::smem(sz, cidx);
                 float4 g4;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
@@ -545,7 +609,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
                     }
                     set_comp(g4, kk, g);
                 }
-                st_stream(a.gz + static_cast<size_t>(bj) * kMap + cidx * 4, g4);
+                MapIO<TZ>::st(a.gz, static_cast<size_t>(bj) * kMap + cidx * 4, g4);
             }
         }
         if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr) {
@@ -604,17 +668,17 @@ stage_loss_kernel(const float* __restrict__ loss_partial, int n_items, float sca
     }
 }
 
+template <typename TZ>
 __global__ void __launch_bounds__(kThreads)
-scale_inplace_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n4, long long n) {
+scale_inplace_kernel(void* __restrict__ x, const float* __restrict__ scale, long long n4) {
     const float s = *scale;
     if (s == 1.0f) return;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
     for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < n4; i += stride) {
-        float4 v = reinterpret_cast<float4*>(x)[i];
+        float4 v = MapIO<TZ>::ld(x, static_cast<size_t>(i) * 4);
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
-        reinterpret_cast<float4*>(x)[i] = v;
+        MapIO<TZ>::st(x, static_cast<size_t>(i) * 4, v);
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) x[n4 * 4 + threadIdx.x] *= s;
 }
 
 // utils.py:332-337 (float32 torch arithmetic) + datasets.py:100-111
@@ -685,11 +749,31 @@ static bool bad_method(int method) {
 
 using namespace pwr;
 
-extern "C" int pwr_decoder_fwd(const float* z, const float* w, const float* D, const float* L, const float* m,
+// Dispatch over (method, loss, conv dtype).  PWR_METHOD_GIVEN (caller-supplied heat maps) exists in
+// float32 only.
+static bool bad_dtype(int method, int map_dtype) {
+    if (map_dtype != PWR_DTYPE_F32 && map_dtype != PWR_DTYPE_F16 && map_dtype != PWR_DTYPE_BF16) return true;
+    return method == PWR_METHOD_GIVEN && map_dtype != PWR_DTYPE_F32;
+}
+#define PWR_DISPATCH(LAUNCH)                                                                          \
+    do {                                                                                              \
+        if (method == PWR_METHOD_GIVEN)        { if (loss) LAUNCH(PWR_METHOD_GIVEN, true, float);  else LAUNCH(PWR_METHOD_GIVEN, false, float); }    \
+        else if (method == PWR_METHOD_SOFTMAX) {                                                      \
+            if (map_dtype == PWR_DTYPE_F32)      { if (loss) LAUNCH(PWR_METHOD_SOFTMAX, true, float);  else LAUNCH(PWR_METHOD_SOFTMAX, false, float); }  \
+            else if (map_dtype == PWR_DTYPE_F16) { if (loss) LAUNCH(PWR_METHOD_SOFTMAX, true, __half); else LAUNCH(PWR_METHOD_SOFTMAX, false, __half); } \
+            else                                 { if (loss) LAUNCH(PWR_METHOD_SOFTMAX, true, __nv_bfloat16); else LAUNCH(PWR_METHOD_SOFTMAX, false, __nv_bfloat16); } \
+        } else {                                                                                      \
+            if (map_dtype == PWR_DTYPE_F32)      { if (loss) LAUNCH(PWR_METHOD_SUM, true, float);  else LAUNCH(PWR_METHOD_SUM, false, float); }  \
+            else if (map_dtype == PWR_DTYPE_F16) { if (loss) LAUNCH(PWR_METHOD_SUM, true, __half); else LAUNCH(PWR_METHOD_SUM, false, __half); } \
+            else                                 { if (loss) LAUNCH(PWR_METHOD_SUM, true, __nv_bfloat16); else LAUNCH(PWR_METHOD_SUM, false, __nv_bfloat16); } \
+        }                                                                                             \
+    } while (0)
+
+extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, const float* L, const float* m,
                                const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
                                float* H, float* uvd, float* stats, float* loss_partial,
-                               int B, int J, int method, void* stream) {
-    if (bad_method(method)) return PWR_E_METHOD;
+                               int B, int J, int method, int map_dtype, void* stream) {
+    if (bad_method(method) || bad_dtype(method, map_dtype)) return PWR_E_METHOD;
     if (int rc = check_bj(B, J)) return rc;
     if (B == 0) return 0;
     PWR_REQUIRE_PTR(z);
@@ -703,22 +787,20 @@ extern "C" int pwr_decoder_fwd(const float* z, const float* w, const float* D, c
         if (uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define PWR_LAUNCH_FWD(M, LS)                                                                               \
-    decoder_fwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, H, uvd, stats, \
-                                                         loss_partial, J)
-    if (method == PWR_METHOD_SOFTMAX)  { if (loss) PWR_LAUNCH_FWD(PWR_METHOD_SOFTMAX, true); else PWR_LAUNCH_FWD(PWR_METHOD_SOFTMAX, false); }
-    else if (method == PWR_METHOD_SUM) { if (loss) PWR_LAUNCH_FWD(PWR_METHOD_SUM, true);     else PWR_LAUNCH_FWD(PWR_METHOD_SUM, false); }
-    else                               { if (loss) PWR_LAUNCH_FWD(PWR_METHOD_GIVEN, true);   else PWR_LAUNCH_FWD(PWR_METHOD_GIVEN, false); }
+#define PWR_LAUNCH_FWD(M, LS, TZ)                                                                            \
+    decoder_fwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, H, uvd, \
+                                                             stats, loss_partial, J)
+    PWR_DISPATCH(PWR_LAUNCH_FWD);
 #undef PWR_LAUNCH_FWD
     return launch_status();
 }
 
-static int launch_bwd(bool loss, const float* z, const float* w, const float* D, const float* L, const float* m,
+static int launch_bwd(bool loss, const void* z, const float* w, const void* D, const float* L, const float* m,
                       const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
-                      const float* gD_up, const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
-                      LossCoef coef, float* gz, float* gD, float* gw_partial, float* loss_partial, int B, int J,
-                      int method, void* stream) {
-    if (bad_method(method)) return PWR_E_METHOD;
+                      const void* gD_up, const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
+                      LossCoef coef, void* gz, void* gD, float* gw_partial, float* loss_partial, int B, int J,
+                      int method, int map_dtype, void* stream) {
+    if (bad_method(method) || bad_dtype(method, map_dtype)) return PWR_E_METHOD;
     if (int rc = check_bj(B, J)) return rc;
     if (B == 0) return 0;
     PWR_REQUIRE_PTR(z); PWR_REQUIRE_PTR(stats);
@@ -739,7 +821,7 @@ static int launch_bwd(bool loss, const float* z, const float* w, const float* D,
         PipeArgs a;
         a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.stats = stats; a.uvd = uvd; a.g_uvd = g_uvd;
         a.slot2 = need_targets ? heat_gt : gH_up;
-        a.slot3 = need_targets ? dmap_gt : gD_up;
+        a.slot3 = need_targets ? static_cast<const void*>(dmap_gt) : gD_up;
         a.uvd_gt = uvd_gt; a.coef = coef; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial;
         a.loss_partial = loss_partial; a.J = J; a.items = B * J;
         a.slots_are_targets = need_targets ? 1 : 0;
@@ -747,45 +829,41 @@ static int launch_bwd(bool loss, const float* z, const float* w, const float* D,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int grid = a.items < sms ? a.items : sms;
-#define PWR_LAUNCH_PIPE(M, LS)                                                                             \
-    do {                                                                                                   \
-        cudaFuncSetAttribute(decoder_bwd_pipe_kernel<M, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             kPipeSmemBytes);                                                              \
-        decoder_bwd_pipe_kernel<M, LS><<<grid, kPipeThreads, kPipeSmemBytes, s>>>(a);                      \
+#define PWR_LAUNCH_PIPE(M, LS, TZ)                                                                             \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(decoder_bwd_pipe_kernel<M, LS, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             kPipeSmemBytes);                                                                  \
+        decoder_bwd_pipe_kernel<M, LS, TZ><<<grid, kPipeThreads, kPipeSmemBytes, s>>>(a);                      \
     } while (0)
-        if (method == PWR_METHOD_SOFTMAX)  { if (loss) PWR_LAUNCH_PIPE(PWR_METHOD_SOFTMAX, true); else PWR_LAUNCH_PIPE(PWR_METHOD_SOFTMAX, false); }
-        else if (method == PWR_METHOD_SUM) { if (loss) PWR_LAUNCH_PIPE(PWR_METHOD_SUM, true);     else PWR_LAUNCH_PIPE(PWR_METHOD_SUM, false); }
-        else                               { if (loss) PWR_LAUNCH_PIPE(PWR_METHOD_GIVEN, true);   else PWR_LAUNCH_PIPE(PWR_METHOD_GIVEN, false); }
+        PWR_DISPATCH(PWR_LAUNCH_PIPE);
 #undef PWR_LAUNCH_PIPE
         return launch_status();
     }
-#define PWR_LAUNCH_BWD(M, LS)                                                                              \
-    decoder_bwd_kernel<M, LS><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up,    \
-                                                         heat_gt, dmap_gt, uvd_gt, coef, gz, gD, gw_partial, \
-                                                         loss_partial, J)
-    if (method == PWR_METHOD_SOFTMAX)  { if (loss) PWR_LAUNCH_BWD(PWR_METHOD_SOFTMAX, true); else PWR_LAUNCH_BWD(PWR_METHOD_SOFTMAX, false); }
-    else if (method == PWR_METHOD_SUM) { if (loss) PWR_LAUNCH_BWD(PWR_METHOD_SUM, true);     else PWR_LAUNCH_BWD(PWR_METHOD_SUM, false); }
-    else                               { if (loss) PWR_LAUNCH_BWD(PWR_METHOD_GIVEN, true);   else PWR_LAUNCH_BWD(PWR_METHOD_GIVEN, false); }
+#define PWR_LAUNCH_BWD(M, LS, TZ)                                                                              \
+    decoder_bwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up,    \
+                                                             heat_gt, dmap_gt, uvd_gt, coef, gz, gD, gw_partial, \
+                                                             loss_partial, J)
+    PWR_DISPATCH(PWR_LAUNCH_BWD);
 #undef PWR_LAUNCH_BWD
     return launch_status();
 }
 
-extern "C" int pwr_decoder_bwd(const float* z, const float* w, const float* D, const float* L, const float* m,
+extern "C" int pwr_decoder_bwd(const void* z, const float* w, const void* D, const float* L, const float* m,
                                const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
-                               const float* gD_up, float* gz, float* gD, float* gw_partial, int B, int J,
-                               int method, void* stream) {
+                               const void* gD_up, void* gz, void* gD, float* gw_partial, int B, int J,
+                               int method, int map_dtype, void* stream) {
     LossCoef coef = {0.f, 0.f, 0.f, nullptr};
     return launch_bwd(false, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, nullptr, nullptr, nullptr, coef, gz,
-                      gD, gw_partial, nullptr, B, J, method, stream);
+                      gD, gw_partial, nullptr, B, J, method, map_dtype, stream);
 }
 
-extern "C" int pwr_decoder_bwd_loss(const float* z, const float* w, const float* D, const float* L, const float* m,
+extern "C" int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D, const float* L, const float* m,
                                     const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
-                                    const float* gD_up, const float* heat_gt, const float* dmap_gt,
+                                    const void* gD_up, const float* heat_gt, const float* dmap_gt,
                                     const float* uvd_gt, float alpha, float lambda_h, float lambda_d,
-                                    float loss_scale, const float* loss_scale_dev, int n_mean, float* gz,
-                                    float* gD, float* gw_partial,
-                                    float* loss_partial, int B, int J, int method, void* stream) {
+                                    float loss_scale, const float* loss_scale_dev, int n_mean, void* gz,
+                                    void* gD, float* gw_partial, float* loss_partial, int B, int J, int method,
+                                    int map_dtype, void* stream) {
     const double n = n_mean > 0 ? static_cast<double>(n_mean) : static_cast<double>(B) * J;
     LossCoef coef;
     coef.cu = static_cast<float>(loss_scale * 2.0 * alpha / n);
@@ -793,7 +871,7 @@ extern "C" int pwr_decoder_bwd_loss(const float* z, const float* w, const float*
     coef.cd = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_d / n);
     coef.scale_dev = loss_scale_dev;
     return launch_bwd(true, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, heat_gt, dmap_gt, uvd_gt, coef, gz, gD,
-                      gw_partial, loss_partial, B, J, method, stream);
+                      gw_partial, loss_partial, B, J, method, map_dtype, stream);
 }
 
 extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, int C, void* stream) {
@@ -814,17 +892,20 @@ extern "C" int pwr_stage_loss(const float* loss_partial, int B, int J, float lam
     return launch_status();
 }
 
-extern "C" int pwr_scale_inplace(float* x, const float* scale_dev, long long n, void* stream) {
+extern "C" int pwr_scale_inplace(void* x, const float* scale_dev, long long n, int map_dtype, void* stream) {
+    if (n < 0 || (n & 3) != 0) return PWR_E_SHAPE;            // whole maps only: n is a multiple of 4096
+    if (n == 0) return 0;
     PWR_REQUIRE_PTR(x);
     if (scale_dev == nullptr) return PWR_E_NULL;
-    if (n < 0) return PWR_E_SHAPE;
-    if (n == 0) return 0;
     const long long n4 = n / 4;
     long long blocks = (n4 + kThreads - 1) / kThreads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    scale_inplace_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, scale_dev, n4, n);
+    const unsigned g = static_cast<unsigned>(blocks);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (map_dtype == PWR_DTYPE_F32)       scale_inplace_kernel<float><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
+    else if (map_dtype == PWR_DTYPE_F16)  scale_inplace_kernel<__half><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
+    else if (map_dtype == PWR_DTYPE_BF16) scale_inplace_kernel<__nv_bfloat16><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
+    else return PWR_E_METHOD;
     return launch_status();
 }
 

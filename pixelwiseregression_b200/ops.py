@@ -26,20 +26,32 @@ def _check_maps(z, label_img, mask):
             raise _lib.PwrError("%s must be [B, 1, 64, 64], got %s" % (name, tuple(t.shape)))
 
 
+def _conv_maps(z, D, method):
+    """z and D as contiguous tensors of ONE kernel-supported element type: float32, or the
+    float16 / bfloat16 conv outputs of autocast, read by the kernels as they are (the arithmetic
+    is float32 either way, which is what autocast does for these ops)."""
+    dt = z.dtype
+    if dt not in _lib.MAP_DTYPES or method == "given" or (D is not None and D.dtype != dt):
+        dt = torch.float32
+    z = z.to(dt).contiguous()
+    D = D.to(dt).contiguous() if D is not None else None
+    return z, D, _lib.MAP_DTYPES[dt]
+
+
 def decoder_forward_raw(z, w, D, label_img, mask, method="softmax", store_heat=True, want_stats=True,
                         targets=None):
     """One launch of pwr_decoder_fwd.  Returns (H or None, uvd, stats or None,
-    loss_partial or None); all inputs float32 CUDA tensors."""
+    loss_partial or None).  z, D: float32 / float16 / bfloat16 CUDA tensors (same dtype);
+    everything else float32; H, uvd are float32."""
     require_cuda(z, w, D, label_img, mask)
     lib = _lib.load()
-    z = as_f32(z)
-    D = as_f32(D)
+    z, D, map_dtype = _conv_maps(z, D, method)
     label_img = as_f32(label_img)
     mask = as_f32(mask)
     _check_maps(z, label_img if D is not None else None, mask if D is not None else None)
     B, J = z.shape[0], z.shape[1]
     wv = as_f32(w).reshape(-1) if w is not None else None
-    H = torch.empty_like(z) if store_heat else None
+    H = torch.empty(z.shape, device=z.device, dtype=torch.float32) if store_heat else None
     uvd = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
     stats = torch.empty(B, J, 4, device=z.device, dtype=torch.float32) if want_stats else None
     heat_gt = dmap_gt = uvd_gt = loss_partial = None
@@ -49,7 +61,7 @@ def decoder_forward_raw(z, w, D, label_img, mask, method="softmax", store_heat=T
     with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd"):
         rc = lib.pwr_decoder_fwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
                                  ptr(uvd_gt), ptr(H), ptr(uvd), ptr(stats), ptr(loss_partial), B, J,
-                                 METHODS[method], stream_ptr(z.device))
+                                 METHODS[method], map_dtype, stream_ptr(z.device))
     check(rc, "pwr_decoder_fwd")
     return H, uvd, stats, loss_partial
 
@@ -59,11 +71,11 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
                          loss_scale=1.0, loss_scale_dev=None, n_mean=0, want_loss=False, want_gz=True,
                          want_gD=True):
     """One launch of pwr_decoder_bwd (targets None) or pwr_decoder_bwd_loss.
-    Returns (gz, gD, gw_partial [B,J] or None, loss_partial [B,J,3] or None)."""
+    Returns (gz, gD, gw_partial [B,J] or None, loss_partial [B,J,3] or None); gz, gD (and
+    gD_up) carry the element type of z, D."""
     require_cuda(z, w, D, label_img, mask, stats, uvd, g_uvd, gH_up, gD_up)
     lib = _lib.load()
-    z = as_f32(z)
-    D = as_f32(D)
+    z, D, map_dtype = _conv_maps(z, D, method)
     B, J = z.shape[0], z.shape[1]
     wv = as_f32(w).reshape(-1) if w is not None else None
     gz = torch.empty_like(z) if want_gz else None
@@ -71,13 +83,13 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
     gw_partial = torch.empty(B, J, device=z.device, dtype=torch.float32) if method == "softmax" else None
     g_uvd = as_f32(g_uvd)
     gH_up = as_f32(gH_up)
-    gD_up = as_f32(gD_up)
+    gD_up = gD_up.to(z.dtype).contiguous() if gD_up is not None else None
     s = stream_ptr(z.device)
     with torch.cuda.device(z.device), _lib.timed("pwr_decoder_bwd" if targets is None else "pwr_decoder_bwd_loss"):
         if targets is None:
             rc = lib.pwr_decoder_bwd(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
                                      ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(gz), ptr(gD),
-                                     ptr(gw_partial), B, J, METHODS[method], s)
+                                     ptr(gw_partial), B, J, METHODS[method], map_dtype, s)
             check(rc, "pwr_decoder_bwd")
             return gz, gD, gw_partial, None
         heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
@@ -87,7 +99,7 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
                                       ptr(dmap_gt), ptr(uvd_gt), float(alpha), float(lambda_h), float(lambda_d),
                                       float(loss_scale), ptr(as_f32(loss_scale_dev)), int(n_mean), ptr(gz),
                                       ptr(gD), ptr(gw_partial),
-                                      ptr(loss_partial), B, J, METHODS[method], s)
+                                      ptr(loss_partial), B, J, METHODS[method], map_dtype, s)
     check(rc, "pwr_decoder_bwd_loss")
     return gz, gD, gw_partial, loss_partial
 
@@ -110,7 +122,8 @@ def scale_inplace_(x, scale):
     """x *= scale, with `scale` a 0-dim CUDA tensor (no host sync; a no-op launch when scale == 1)."""
     require_cuda(x, scale)
     with torch.cuda.device(x.device):
-        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(as_f32(scale)), x.numel(), stream_ptr(x.device))
+        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(as_f32(scale)), x.numel(), _lib.MAP_DTYPES[x.dtype],
+                                           stream_ptr(x.device))
     check(rc, "pwr_scale_inplace")
     return x
 
@@ -155,7 +168,8 @@ class DecoderFunction(torch.autograd.Function):
         ctx.in_dtypes = (z.dtype, D.dtype)
         ctx.loss_cfg = (alpha, lambda_h, lambda_d) if targets is not None else None
         ctx.save_for_backward(z, w, D, label_img, mask, stats, uvd, heat_gt, dmap_gt, uvd_gt)
-        outs = (H.to(z.dtype), D.view_as(D), uvd.to(z.dtype))
+        # heat maps and coordinates are float32 even for half-precision logits, as under autocast
+        outs = (H, D.view_as(D), uvd)
         if targets is None:
             return outs
         out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
@@ -186,7 +200,7 @@ def fused_decoder(z, w, D, label_img, mask, method="softmax"):
     if torch.is_grad_enabled() and (z.requires_grad or D.requires_grad or (w is not None and w.requires_grad)):
         return DecoderFunction.apply(z, w, D, label_img, mask, method)
     H, uvd, _, _ = decoder_forward_raw(z, w, D, label_img, mask, method, want_stats=False)
-    return H.to(z.dtype), D, uvd.to(z.dtype)
+    return H, D, uvd
 
 
 def fused_decoder_with_loss(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method="softmax", alpha=1.0,
@@ -206,7 +220,7 @@ class PlaneFunction(torch.autograd.Function):
         H, uvd, stats, _ = decoder_forward_raw(z, w, None, None, None, method)
         ctx.method = method
         ctx.save_for_backward(z, w, stats, uvd)
-        return H.to(z.dtype), uvd[:, :, :2].contiguous().to(z.dtype)
+        return H, uvd[:, :, :2].contiguous()
 
     @staticmethod
     def backward(ctx, gH, g_uv):

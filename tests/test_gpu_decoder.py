@@ -282,3 +282,63 @@ def test_recover_uvd_and_joint_error_match_oracle():
     assert_close("xyz", xyz.cpu().numpy(), so.uvd2xyz(ref_px, *intr))
     err = ops.joint_error(cu(pred), cu(true), cu(box), cu(com), cu(cube), intr)
     assert_close("joint error", err.cpu().numpy(), so.joint_error(pred, true, box, com, cube, *intr))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("method", ["softmax", "sum"])
+def test_half_precision_conv_outputs_equal_upcast_path(dtype, method):
+    """fp16 / bf16 logits (autocast, train.py:170-172) read directly by the kernels give
+    exactly what the float32 kernels give on the up-cast values (autocast's own semantics), with the
+    gradients rounded once to the conv dtype."""
+    B, J = 5, 14
+    d, tg, ups = oracle_case(B, J, method, 0.5, True, seed=21)
+    z16, D16 = cu(d["z"]).to(dtype), cu(d["D"]).to(dtype)
+    w = cu(d["w"]) if method == "softmax" else None
+    L, m = cu(d["label"]), cu(d["mask"])
+    targets = tuple(cu(a) for a in tg)
+    gH_up, gD_up16 = cu(ups[1]), cu(ups[2]).to(dtype)
+    H16, uvd16, st16, lp16 = ops.decoder_forward_raw(z16, w, D16, L, m, method, targets=targets)
+    H32, uvd32, st32, lp32 = ops.decoder_forward_raw(z16.float(), w, D16.float(), L, m, method, targets=targets)
+    assert H16.dtype == torch.float32 and torch.equal(H16, H32) and torch.equal(uvd16, uvd32) and torch.equal(lp16, lp32)
+    for kw in (dict(targets=targets, alpha=0.5, want_loss=True),                 # pipelined, targets in the slots
+               dict(gH_up=gH_up, gD_up=gD_up16),                                 # pipelined, upstream maps in the slots
+               dict(gH_up=gH_up, gD_up=gD_up16, targets=targets, alpha=0.5)):    # direct-load kernel (both pairs)
+        kw32 = dict(kw)
+        if "gD_up" in kw32:
+            kw32["gD_up"] = kw32["gD_up"].float()
+        a = ops.decoder_backward_raw(z16, w, D16, L, m, st16, uvd16, cu(ups[0]), method=method, **kw)
+        b = ops.decoder_backward_raw(z16.float(), w, D16.float(), L, m, st32, uvd32, cu(ups[0]), method=method, **kw32)
+        assert a[0].dtype == dtype and a[1].dtype == dtype
+        assert torch.equal(a[0], b[0].to(dtype)) and torch.equal(a[1], b[1].to(dtype))
+        if method == "softmax":
+            assert torch.equal(a[2], b[2])
+        if a[3] is not None:
+            assert torch.equal(a[3], b[3])
+
+
+def test_autocast_training_step_through_the_fused_decoder():
+    """fp16 logits inside an autograd graph with a GradScaler-like upstream scale."""
+    B, J = 3, 14
+    d, tg, _ = oracle_case(B, J, "softmax", 0.5, False, seed=22)
+    z = cu(d["z"]).half().requires_grad_(True)
+    D = cu(d["D"]).half().requires_grad_(True)
+    w = cu(d["w"]).requires_grad_(True)
+    total, terms, uvd, H = ops.fused_decoder_loss(z, w, D, cu(d["label"]), cu(d["mask"]), *[cu(a) for a in tg], alpha=0.5)
+    (total * 1024.0).backward()
+    assert z.grad.dtype == torch.float16 and D.grad.dtype == torch.float16 and H.dtype == torch.float32
+    zf = z.detach().float().requires_grad_(True)
+    Df = D.detach().float().requires_grad_(True)
+    wf = w.detach().clone().requires_grad_(True)
+    total2, *_ = ops.fused_decoder_loss(zf, wf, Df, cu(d["label"]), cu(d["mask"]), *[cu(a) for a in tg], alpha=0.5)
+    (total2 * 1024.0).backward()
+    assert torch.equal(total, total2)
+    assert_close("gz", z.grad.float().cpu().numpy(), zf.grad.cpu().numpy(), 2e-3)     # two fp16 roundings (eager, then scale)
+    assert_close("gD", D.grad.float().cpu().numpy(), Df.grad.cpu().numpy(), 2e-3)
+    assert_close("gw", w.grad.cpu().numpy(), wf.grad.cpu().numpy(), 1e-6)
+    # drop-in autograd node with half inputs
+    z2 = cu(d["z"]).half().requires_grad_(True)
+    D2 = cu(d["D"]).half().requires_grad_(True)
+    H2, Dm, uvd2 = ops.fused_decoder(z2, w, D2, cu(d["label"]), cu(d["mask"]))
+    assert H2.dtype == torch.float32 and Dm.dtype == torch.float16 and uvd2.dtype == torch.float32
+    ((H2 ** 2).sum() + (Dm.float() ** 2).sum() * 1e-3 + (uvd2 ** 2).sum()).backward()
+    assert z2.grad.dtype == torch.float16 and D2.grad.dtype == torch.float16

@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--augment", action="store_true",
                     help="build the SFR targets through the augmented branch (datasets.py:216-299, train.py defaults)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the compact-target variant of the step")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager decoder baseline on the GPU")
     return ap.parse_args()
 
@@ -247,7 +248,8 @@ def run_b200(args):
     def step(frames_, com_, cube_, uvd_, z_, D_, kw=None):
         """The public-API call sequence a training loop makes for this path."""
         batch = sfr.build_sfr(frames_, com_, cube_, uvd_, **(kw or sfr_kw))
-        total, terms, uvd_out, _ = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, batch.heatmaps,
+        heat_t = batch.heatmaps if batch.heatmaps is not None else batch.taps     # dense maps, or compact taps
+        total, terms, uvd_out, _ = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, heat_t,
                                                           batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
                                                           lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)
         z_.grad = D_.grad = w.grad = None
@@ -311,6 +313,42 @@ def run_b200(args):
                          "achieved_gbs": gbs, "frac": gbs / peak}
     dominant = max(kernels, key=lambda k: kernels[k]["avg_ms"])
     step_kernel_ms = sum(k["avg_ms"] for k in kernels.values())
+
+    # ---- the same step with compact targets ("report the elided variant separately"):
+    # the SFR builder emits 64 B of taps per joint instead of two dense maps and the loss kernel
+    # evaluates heat-map / depth-map targets on the fly; identical loss terms and gradients
+    # (tests/test_gpu_decoder.py::test_sparse_targets_equal_dense_targets), 33 % fewer bytes ----
+    sparse = None
+    if not args.no_sparse:
+        kw_sparse = dict(sfr_kw, targets="sparse")
+        for _ in range(3):
+            step(frames, com, cube, uvd, z, D, kw_sparse)
+        barrier()
+        _lib.PROFILE = []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step(frames, com, cube, uvd, z, D, kw_sparse)
+        s1.record()
+        barrier()
+        prof_s, _lib.PROFILE = _lib.PROFILE, None
+        ts = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item()) / args.steps
+        bytes_s = {"pwr_sfr_build": roofline.sfr_build_sparse_bytes(J) * B,
+                   "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J) * B,
+                   "pwr_decoder_bwd_loss": roofline.decoder_bwd_sparse_bytes(J) * B}
+        kms = {}
+        for name, s_, e_ in prof_s:
+            kms.setdefault(name, []).append(s_.elapsed_time(e_))
+        sparse = {"value": B * world / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
+                  "algorithmic_bytes_per_sample": roofline.step_sparse_bytes(J),
+                  "step_roofline_frac": roofline.step_sparse_bytes(J) * B / (ms_s * 1e-3) / 1e9 / peak,
+                  "kernels": {k: {"avg_ms": sum(v) / len(v), "algorithmic_bytes": bytes_s[k],
+                                  "frac": bytes_s[k] / (sum(v) / len(v) * 1e-3) / 1e9 / peak} for k, v in kms.items()},
+                  "note": "same step, same results; targets handed to the loss kernel as 64-byte taps per joint "
+                          "instead of two dense 16 KiB maps (sfr.build_sfr(targets='sparse'))"}
 
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region ----
     def run_e2e(frames_dev, kw, what):
@@ -400,6 +438,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": e2e,
             "e2e_raw_frames": e2e_raw,
+            "sparse_targets": sparse,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
                          "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,

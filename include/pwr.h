@@ -82,6 +82,20 @@ int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com /*[B,3]*/,
 #define PWR_FRAME_U16   2   /* 16-bit grey PNG (ICVL :632, HAND17 :940):
                                (v/65535)*65535                              */
 
+/* Compact ("sparse") form of one joint's heat map + depth map target: a heat map is the 7x7
+ * sigma-1.5 Gaussian (BORDER_REFLECT_101) of four taps (utils.py:37-65), so 64 bytes describe
+ * what the dense 2 x 16 KiB planes hold.  The loss kernels can evaluate both targets on the fly
+ * from this (see `taps` of pwr_decoder_fwd / pwr_decoder_bwd_loss), which removes the write and
+ * the re-read of 2J dense maps per sample. */
+typedef struct {
+    double tap[4];              /* a, b, c, d at (ty0,tx0) (ty0,tx1) (ty1,tx0) (ty1,tx1)      */
+    double cd;                  /* centred joint depth uvd_z - com_z (x scale if augmented)   */
+    double cd_norm;             /* cd / cube: Dmap = (cd_norm - label_img) * [heat>0] * mask  */
+    int16_t tx0, tx1, ty0, ty1; /* wrapped heat-map indices of the taps                       */
+    int32_t ok;                 /* 0: the joint was rejected (maps are all zero)              */
+    int32_t pad;
+} pwr_joint_taps;
+
 /* Bytes of caller-allocated device scratch pwr_sfr_crop (J = 0) / pwr_sfr_build
  * need: per-sample crop geometry and per-joint splat taps prepared once per
  * sample, plus the counter of the per-sample reject gate.  Contents need no
@@ -129,7 +143,9 @@ int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf,
  *   scaled with cv2.warpAffine's fixed-point bilinear recipe; a sample whose
  *   augmented branch would raise falls back to the plain branch, as the
  *   reference's try/except does.
- * extra outputs: uvd_norm [B,J,3], heatmaps [B,J,64,64], dmap [B,J,64,64] f32;
+ * extra outputs: uvd_norm [B,J,3], heatmaps [B,J,64,64], dmap [B,J,64,64] f32
+ *   (both NULL = do not render the dense maps), joint_taps [B,J] (NULL = not
+ *   wanted; at least one of the two target forms must be requested);
  *   valid [B] u8 = 0 where the reference raises (empty crop, heat-map index
  *   out of range, NaN, sum(mask) < 10).
  *   workspace: >= pwr_sfr_workspace_bytes(B, J) bytes, 16-byte aligned. */
@@ -142,6 +158,7 @@ int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
                   float* img, float* label_img, float* mask,
                   float* box_size, float* cube_size, float* com_out,
                   float* uvd_norm, float* heatmaps, float* dmap,
+                  pwr_joint_taps* joint_taps,
                   uint8_t* valid, void* workspace, size_t workspace_size,
                   int B, int J, void* stream);
 
@@ -157,7 +174,8 @@ int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
  *   read) evaluates the plane branch alone and returns d = 0.
  *   heat_gt, dmap_gt [B,J,64,64], uvd_gt [B,J,3]: only read when
  *   loss_partial != NULL (an inner stage whose loss VALUE is needed at forward
- *   time, train.py:197-199).
+ *   time, train.py:197-199).  taps [B,J] != NULL replaces the dense heat_gt /
+ *   dmap_gt (which may then be NULL): the targets are evaluated on the fly.
  * outputs: H [B,J,64,64] normalised heat maps (NULL = do not store, e.g. the
  *   last stage at inference); uvd [B,J,3]; stats [B,J,4] = (softmax offset in
  *   log2 units, 1/sum, masked-heat sum + 1e-14, d) saved for the backward
@@ -166,7 +184,7 @@ int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
 int pwr_decoder_fwd(const void* z, const float* w, const void* D,
                     const float* L, const float* m,
                     const float* heat_gt, const float* dmap_gt,
-                    const float* uvd_gt,
+                    const float* uvd_gt, const pwr_joint_taps* taps,
                     float* H, float* uvd, float* stats, float* loss_partial,
                     int B, int J, int method, int map_dtype, void* stream);
 
@@ -201,7 +219,7 @@ int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D,
                          const float* uvd, const float* g_uvd,
                          const float* gH_up, const void* gD_up,
                          const float* heat_gt, const float* dmap_gt,
-                         const float* uvd_gt,
+                         const float* uvd_gt, const pwr_joint_taps* taps,
                          float alpha, float lambda_h, float lambda_d,
                          float loss_scale, const float* loss_scale_dev,
                          int n_mean,

@@ -33,10 +33,10 @@ SIGNATURES = {
     "pwr_sfr_workspace_bytes": [_I, _I],
     "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
     "pwr_sfr_build": [_P, _I, _I, _I, _P, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                      _P, _SZ, _I, _I, _P],
-    "pwr_decoder_fwd": [_P] * 12 + [_I, _I, _I, _I, _P],
+                      _P, _P, _SZ, _I, _I, _P],
+    "pwr_decoder_fwd": [_P] * 13 + [_I, _I, _I, _I, _P],
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _I, _P],
-    "pwr_decoder_bwd_loss": [_P] * 13 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _I, _P],
+    "pwr_decoder_bwd_loss": [_P] * 14 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _I, _P],
     "pwr_reduce_partials": [_P, _P, _I, _I, _I, _P],
     "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P],
     "pwr_scale_inplace": [_P, _P, _LL, _I, _P],

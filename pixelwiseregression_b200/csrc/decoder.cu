@@ -140,6 +140,58 @@ __device__ __forceinline__ float heat_raw(float z, float c, float off) {
 }
 
 // ---------------------------------------------------------------------------
+// sparse targets: heat-map / depth-map targets evaluated on the fly from pwr_joint_taps
+// ---------------------------------------------------------------------------
+// cv::getGaussianKernel(7, 1.5) rounded to float32 (the dense targets are float32 roundings of the
+// float64 blur; evaluating in float32 here differs by < 4e-7 relative, far inside the 1e-5 bound)
+__constant__ float kGauss7f[7] = {0x1.2c18a51a3e5e7p-5, 0x1.c7ce552574441p-4, 0x1.bbe4f897eb627p-3,
+                                  0x1.152db38ecae3ep-2, 0x1.bbe4f897eb627p-3, 0x1.c7ce552574441p-4,
+                                  0x1.2c18a51a3e5e7p-5};
+
+// weight with which a unit impulse at index t reaches output x through the 7-tap Gaussian with
+// BORDER_REFLECT_101 on a 64-long axis (same decomposition as gauss_reach in sfr.cu)
+__device__ __forceinline__ float gauss_reach_f(int x, int t) {
+    float wgt = 0.f;
+    const int k0 = t - x + 3;
+    if (k0 >= 0 && k0 <= 6) wgt += kGauss7f[k0];
+    const int k1 = 3 - x - t;
+    if (t >= 1 && k1 >= 0 && k1 <= 6) wgt += kGauss7f[k1];
+    const int k2 = 2 * kLabel + 1 - x - t;
+    if (t <= kLabel - 2 && k2 >= 0 && k2 <= 6) wgt += kGauss7f[k2];
+    return wgt;
+}
+
+struct TapsF { float a, b, c, d, cdn; int tx0, tx1, ty0, ty1, ok; };
+
+__device__ __forceinline__ TapsF load_taps(const pwr_joint_taps* __restrict__ p) {
+    const double4 t = *reinterpret_cast<const double4*>(p->tap);
+    TapsF f;
+    f.a = static_cast<float>(t.x); f.b = static_cast<float>(t.y); f.c = static_cast<float>(t.z); f.d = static_cast<float>(t.w);
+    f.cdn = static_cast<float>(p->cd_norm);
+    f.tx0 = p->tx0; f.tx1 = p->tx1; f.ty0 = p->ty0; f.ty1 = p->ty1; f.ok = p->ok;
+    return f;
+}
+
+// targets of the 4 pixels (row y, columns x0..x0+3): heat = blur of the four taps, Dmap =
+// (cd/cube - label_img) * [heat > 0] * mask (datasets.py:372-374, 380); zero outside the footprint
+__device__ __forceinline__ void sparse_targets(const TapsF& t, int y, int x0, const float4& l4, const float4& m4,
+                                               float4& hg, float4& dg) {
+    hg = make_float4(0.f, 0.f, 0.f, 0.f);
+    dg = hg;
+    if (!t.ok) return;
+    if (abs(y - t.ty0) > 3 && abs(y - t.ty1) > 3) return;
+    if (!((x0 + 3 >= t.tx0 - 3 && x0 <= t.tx0 + 3) || (x0 + 3 >= t.tx1 - 3 && x0 <= t.tx1 + 3))) return;
+    const float wy0 = gauss_reach_f(y, t.ty0), wy1 = gauss_reach_f(y, t.ty1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float wx0 = gauss_reach_f(x0 + k, t.tx0), wx1 = gauss_reach_f(x0 + k, t.tx1);
+        const float h = wy0 * (t.a * wx0 + t.b * wx1) + wy1 * (t.c * wx0 + t.d * wx1);
+        set_comp(hg, k, h);
+        set_comp(dg, k, (h > 0.f && comp(m4, k) != 0.f) ? t.cdn - comp(l4, k) : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
 template <int METHOD, bool LOSS, typename TZ>
@@ -147,7 +199,7 @@ __global__ void __launch_bounds__(kThreads)
 decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, const void* __restrict__ D,
                    const float* __restrict__ L, const float* __restrict__ m,
                    const float* __restrict__ heat_gt, const float* __restrict__ dmap_gt,
-                   const float* __restrict__ uvd_gt, float* __restrict__ H,
+                   const float* __restrict__ uvd_gt, const pwr_joint_taps* __restrict__ taps, float* __restrict__ H,
                    float* __restrict__ uvd, float* __restrict__ stats, float* __restrict__ loss_partial, int J) {
     __shared__ float scratch[kWarps * 5];
     const int bj = blockIdx.x;
@@ -179,6 +231,10 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
     }
 
     const PixelCoords pc = pixel_coords();
+    const bool sparse = LOSS && taps != nullptr;
+    TapsF tp;
+    if (sparse) tp = load_taps(taps + bj);
+    float4 hgs[kVec];                           // sparse heat targets, kept for the second loop
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum e, e*(x-32), e*(y-32), e*m, e*m*m*(D+L)
     float ld2 = 0.f;                            // sum (D - Dgt)^2
 #pragma unroll
@@ -186,7 +242,11 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         const float ys = pc.ys0 + 16.f * i;
         float rowsum = 0.f;
         float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (LOSS) dg = ld_stream(dmap_gt + off + i * (kThreads * 4));
+        if (LOSS) {
+            if (sparse) sparse_targets(tp, static_cast<int>(threadIdx.x >> 4) + 16 * i, static_cast<int>(threadIdx.x & 15) * 4,
+                                       lv[i], mv[i], hgs[i], dg);
+            else dg = ld_stream(dmap_gt + off + i * (kThreads * 4));
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float e = heat_raw<METHOD>(comp(zv[i], k), c, shift);
@@ -211,7 +271,7 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         float4 h = zv[i];
         h.x *= inv_s; h.y *= inv_s; h.z *= inv_s; h.w *= inv_s;
         if (LOSS) {
-            const float4 hg = ld_stream(heat_gt + off + i * (kThreads * 4));
+            const float4 hg = sparse ? hgs[i] : ld_stream(heat_gt + off + i * (kThreads * 4));
             const float e0 = h.x - hg.x, e1 = h.y - hg.y, e2 = h.z - hg.z, e3 = h.w - hg.w;
             lh2[0] += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
         }
@@ -257,7 +317,7 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
                    const float* __restrict__ uvd, const float* __restrict__ g_uvd,
                    const float* __restrict__ gH_up, const void* __restrict__ gD_up,
                    const float* __restrict__ heat_gt, const float* __restrict__ dmap_gt,
-                   const float* __restrict__ uvd_gt, LossCoef coef,
+                   const float* __restrict__ uvd_gt, const pwr_joint_taps* __restrict__ taps, LossCoef coef,
                    void* __restrict__ gz, void* __restrict__ gD, float* __restrict__ gw_partial,
                    float* __restrict__ loss_partial, int J) {
     __shared__ float scratch[kWarps * 3];
@@ -272,6 +332,9 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
     const size_t offb = static_cast<size_t>(b) * kMap + threadIdx.x * 4;
     const bool depth = (D != nullptr);
     const bool map_loss = LOSS && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
+    const bool sparse = map_loss && taps != nullptr;
+    TapsF tp;
+    if (sparse) tp = load_taps(taps + bj);
 
     float4 zv[kVec], pv[kVec], gv[kVec];   // logits, heat p, dL/dp
 #pragma unroll
@@ -302,7 +365,8 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         const size_t ob = offb + i * (kThreads * 4);
         float4 d4 = zero4, l4 = zero4, m4 = zero4, hg = zero4, dg = zero4, uh = zero4, ud = zero4;
         if (depth) { d4 = MapIO<TZ>::ld(D, o); l4 = ld_keep(L + ob); m4 = ld_keep(m + ob); }
-        if (map_loss) { hg = ld_stream(heat_gt + o); if (depth) dg = ld_stream(dmap_gt + o); }
+        if (sparse) sparse_targets(tp, static_cast<int>(threadIdx.x >> 4) + 16 * i, static_cast<int>(threadIdx.x & 15) * 4, l4, m4, hg, dg);
+        else if (map_loss) { hg = ld_stream(heat_gt + o); if (depth) dg = ld_stream(dmap_gt + o); }
         if (gH_up != nullptr) uh = ld_stream(gH_up + o);
         if (gD_up != nullptr) ud = MapIO<TZ>::ld(gD_up, o);
         const float gyrow = gv63 * (pc.ys0 + 16.f * i);
@@ -446,6 +510,7 @@ struct PipeArgs {
     const float* stats; const float* uvd; const float* g_uvd;
     const float* slot2; const void* slot3;     // (heat_gt, dmap_gt) or (gH_up, gD_up); either may be NULL
     const float* uvd_gt;
+    const pwr_joint_taps* taps;                // sparse targets (then slot2/slot3 carry no targets)
     LossCoef coef;
     void* gz; void* gD; float* gw_partial; float* loss_partial;
     int J; int items;
@@ -539,6 +604,9 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
         const float gu63 = gu / 63.f, gv63 = gvv / 63.f;
         const float gdd = gd / st.z;
         const float dcoord = st.w;
+        const bool sparse = LOSS && a.taps != nullptr;
+        TapsF tp;
+        if (sparse) tp = load_taps(a.taps + bj);
 
         const float* sz = stage_base + s * 4 * kMap;          // slot bases (each slot is 16 KiB apart)
         const float* sD = sz + kMap;
@@ -556,8 +624,13 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
             const int cidx = tid + i * kPipeThreads;
             const float4 z4 = MapIO<TZ>::smem(sz, cidx), d4 = MapIO<TZ>::smem(sD, cidx), l4 = sL[cidx], m4 = sM[cidx];
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            // slot 2 / 3 hold either dense targets (tg) or dense upstream gradients
             const float4 q2 = has2 ? s2[cidx] : zero4;
             const float4 q3 = has3 ? (tg ? MapIO<float>::smem(s3, cidx) : MapIO<TZ>::smem(s3, cidx)) : zero4;
+            float4 t2 = tg ? q2 : zero4, t3 = tg ? q3 : zero4;          // targets
+            const float4 u2 = tg ? zero4 : q2, u3 = tg ? zero4 : q3;    // upstream gradients
+            if (sparse) sparse_targets(tp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
+            const bool have_h = sparse || (tg && has2), have_d = sparse || (tg && has3);
             const float gyrow = gv63 * (ys0 + 32.f * i);
             float4 gd4;
 #pragma unroll
@@ -568,15 +641,16 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
                 float gp = fmaf(gu63, xs + static_cast<float>(kk), gyrow);
                 gp = fmaf(gdd * mk, rec - dcoord, gp);
                 float gdk = gdd * p * mk * mk;
-                if (LOSS && tg) {
-                    const float eh = has2 ? p - comp(q2, kk) : 0.f;
-                    const float ed = has3 ? dk - comp(q3, kk) : 0.f;
+                if (LOSS) {
+                    const float eh = have_h ? p - comp(t2, kk) : 0.f;
+                    const float ed = have_d ? dk - comp(t3, kk) : 0.f;
                     gp = fmaf(a.coef.ch, eh, gp);
                     gdk = fmaf(a.coef.cd, ed, gdk);
                     acc[1] = fmaf(eh, eh, acc[1]);
                     acc[2] = fmaf(ed, ed, acc[2]);
                 }
-                if (!tg) { gp += comp(q2, kk); gdk += comp(q3, kk); }
+                gp += comp(u2, kk);
+                gdk += comp(u3, kk);
                 acc[0] = fmaf(gp, p, acc[0]);
                 set_comp(pv[i], kk, p);
                 set_comp(gv[i], kk, gp);
@@ -771,7 +845,7 @@ static bool bad_dtype(int method, int map_dtype) {
 
 extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, const float* L, const float* m,
                                const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
-                               float* H, float* uvd, float* stats, float* loss_partial,
+                               const pwr_joint_taps* taps, float* H, float* uvd, float* stats, float* loss_partial,
                                int B, int J, int method, int map_dtype, void* stream) {
     if (bad_method(method) || bad_dtype(method, map_dtype)) return PWR_E_METHOD;
     if (int rc = check_bj(B, J)) return rc;
@@ -783,13 +857,14 @@ extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, con
     if (method == PWR_METHOD_SOFTMAX && w == nullptr) return PWR_E_NULL;
     const bool loss = loss_partial != nullptr;
     if (loss) {
-        PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt);
+        if (taps == nullptr) { PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt); }
+        else PWR_REQUIRE_PTR(taps);
         if (uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define PWR_LAUNCH_FWD(M, LS, TZ)                                                                            \
-    decoder_fwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, H, uvd, \
-                                                             stats, loss_partial, J)
+    decoder_fwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, taps, H, \
+                                                             uvd, stats, loss_partial, J)
     PWR_DISPATCH(PWR_LAUNCH_FWD);
 #undef PWR_LAUNCH_FWD
     return launch_status();
@@ -798,8 +873,8 @@ extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, con
 static int launch_bwd(bool loss, const void* z, const float* w, const void* D, const float* L, const float* m,
                       const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
                       const void* gD_up, const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
-                      LossCoef coef, void* gz, void* gD, float* gw_partial, float* loss_partial, int B, int J,
-                      int method, int map_dtype, void* stream) {
+                      const pwr_joint_taps* taps, LossCoef coef, void* gz, void* gD, float* gw_partial,
+                      float* loss_partial, int B, int J, int method, int map_dtype, void* stream) {
     if (bad_method(method) || bad_dtype(method, map_dtype)) return PWR_E_METHOD;
     if (int rc = check_bj(B, J)) return rc;
     if (B == 0) return 0;
@@ -809,20 +884,23 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
     if (D == nullptr && (gD != nullptr || gD_up != nullptr)) return PWR_E_NULL;
     if (method == PWR_METHOD_SOFTMAX && w == nullptr) return PWR_E_NULL;
     if (loss) {
-        PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt);
+        if (taps == nullptr) { PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt); }
+        else PWR_REQUIRE_PTR(taps);
         if (uvd == nullptr || uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // Hot configurations -> persistent TMA-pipelined kernel: depth branch present, and at most one
-    // pair of extra maps (targets XOR dense upstream gradients).
-    const bool need_targets = loss && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
+    // pair of extra DENSE maps (targets XOR upstream gradients); sparse targets need no slot.
+    const bool map_terms = loss && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
+    const bool need_targets = map_terms && taps == nullptr;
+    if (!map_terms) taps = nullptr;
     const bool need_up = gH_up != nullptr || gD_up != nullptr;
     if (D != nullptr && !(need_targets && need_up) && !force_direct_bwd()) {
         PipeArgs a;
         a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.stats = stats; a.uvd = uvd; a.g_uvd = g_uvd;
         a.slot2 = need_targets ? heat_gt : gH_up;
         a.slot3 = need_targets ? static_cast<const void*>(dmap_gt) : gD_up;
-        a.uvd_gt = uvd_gt; a.coef = coef; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial;
+        a.uvd_gt = uvd_gt; a.taps = taps; a.coef = coef; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial;
         a.loss_partial = loss_partial; a.J = J; a.items = B * J;
         a.slots_are_targets = need_targets ? 1 : 0;
         int dev = 0, sms = 0;
@@ -841,8 +919,8 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
     }
 #define PWR_LAUNCH_BWD(M, LS, TZ)                                                                              \
     decoder_bwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up,    \
-                                                             heat_gt, dmap_gt, uvd_gt, coef, gz, gD, gw_partial, \
-                                                             loss_partial, J)
+                                                             heat_gt, dmap_gt, uvd_gt, taps, coef, gz, gD,      \
+                                                             gw_partial, loss_partial, J)
     PWR_DISPATCH(PWR_LAUNCH_BWD);
 #undef PWR_LAUNCH_BWD
     return launch_status();
@@ -853,14 +931,15 @@ extern "C" int pwr_decoder_bwd(const void* z, const float* w, const void* D, con
                                const void* gD_up, void* gz, void* gD, float* gw_partial, int B, int J,
                                int method, int map_dtype, void* stream) {
     LossCoef coef = {0.f, 0.f, 0.f, nullptr};
-    return launch_bwd(false, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, nullptr, nullptr, nullptr, coef, gz,
-                      gD, gw_partial, nullptr, B, J, method, map_dtype, stream);
+    return launch_bwd(false, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, nullptr, nullptr, nullptr, nullptr, coef,
+                      gz, gD, gw_partial, nullptr, B, J, method, map_dtype, stream);
 }
 
 extern "C" int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D, const float* L, const float* m,
                                     const float* stats, const float* uvd, const float* g_uvd, const float* gH_up,
                                     const void* gD_up, const float* heat_gt, const float* dmap_gt,
-                                    const float* uvd_gt, float alpha, float lambda_h, float lambda_d,
+                                    const float* uvd_gt, const pwr_joint_taps* taps, float alpha, float lambda_h,
+                                    float lambda_d,
                                     float loss_scale, const float* loss_scale_dev, int n_mean, void* gz,
                                     void* gD, float* gw_partial, float* loss_partial, int B, int J, int method,
                                     int map_dtype, void* stream) {
@@ -870,8 +949,8 @@ extern "C" int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D
     coef.ch = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_h / n);
     coef.cd = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_d / n);
     coef.scale_dev = loss_scale_dev;
-    return launch_bwd(true, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, heat_gt, dmap_gt, uvd_gt, coef, gz, gD,
-                      gw_partial, loss_partial, B, J, method, map_dtype, stream);
+    return launch_bwd(true, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, heat_gt, dmap_gt, uvd_gt, taps, coef, gz,
+                      gD, gw_partial, loss_partial, B, J, method, map_dtype, stream);
 }
 
 extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, int C, void* stream) {

@@ -276,6 +276,7 @@ struct SfrArgs {
     int* prep_flags;            // workspace: [B] joints_bad
     unsigned int* gate;         // workspace: [B] packed (bands arrived << 24 | NaN << 16 | mask count)
     double pf_margin, pf_umax, pf_vmax;   // load_from_text prefilter: margin < 0 = off; 2*halfu, 2*halfv
+    pwr_joint_taps* taps_out;   // [B,J] compact ("sparse") targets, or NULL
     const double* aug;          // [B,8] (scale, shift_u, shift_v, cos a, sin a, cos a', sin a', -) or NULL
     WarpParam* prep_warp;       // workspace: [B] (augmentation only)
 };
@@ -397,6 +398,16 @@ __device__ bool prep_joints(const SfrArgs& a, int b, int lane, const SampleGeom&
         }
         bad |= jp.ok ? 0 : 1;
         a.prep_joints[static_cast<size_t>(b) * a.J + j] = jp;
+        if (a.taps_out != nullptr) {
+            pwr_joint_taps t;
+            t.tap[0] = jp.tap[0]; t.tap[1] = jp.tap[1]; t.tap[2] = jp.tap[2]; t.tap[3] = jp.tap[3];
+            t.cd = jp.cd;
+            t.cd_norm = g.ok ? __ddiv_rn(jp.cd, g.cube) : 0.0;
+            t.tx0 = static_cast<int16_t>(jp.tx0); t.tx1 = static_cast<int16_t>(jp.tx1);
+            t.ty0 = static_cast<int16_t>(jp.ty0); t.ty1 = static_cast<int16_t>(jp.ty1);
+            t.ok = jp.ok; t.pad = 0;
+            a.taps_out[static_cast<size_t>(b) * a.J + j] = t;
+        }
     }
     return __any_sync(0xffffffffu, bad) != 0;
 }
@@ -497,7 +508,8 @@ sfr_build_kernel(SfrArgs a) {
     // ... while pass A of phase 2 streams the zeros: a heat map is zero outside the <= 8x8
     // footprint of the blurred 4-tap splat, and so is the depth map, so every map band is
     // zero-filled with 128-bit stores here and patched after phase 1.
-    if (TRAIN) {
+    const bool dense = TRAIN && a.heatmaps != nullptr;      // dense maps wanted (else: compact taps only)
+    if (dense) {
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const size_t band_off = static_cast<size_t>(b) * a.J * kMap + y_lo * kLabel + (tid & 31) * 4;
         for (int j = tid >> 5; j < a.J; j += kWarps) {
@@ -516,7 +528,7 @@ sfr_build_kernel(SfrArgs a) {
         if (tid < kImage) xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);
         else if (tid < kImage + 2 * kBandRows)
             ytap[tid - kImage] = linear_tap(band * 2 * kBandRows + (tid - kImage), g.nrows, g.scale_y);
-        if (TRAIN && tid < a.J) {
+        if (dense && tid < a.J) {
             const JointParam& jp = joints[tid];                     // rows ty0-3..ty0+3 or ty1..ty1+3 hit the band?
             if (jp.ok && ((jp.ty0 + 3 >= y_lo && jp.ty0 - 3 < y_hi) || (jp.ty1 + 3 >= y_lo && jp.ty1 < y_hi)))
                 band_list[atomicAdd(&band_list_n, 1)] = tid;
@@ -589,7 +601,7 @@ sfr_build_kernel(SfrArgs a) {
 
     // ---- phase 2, pass B: the <= 8x8 footprint of every joint that touches this band
     // (pass A zero-filled the maps before the barriers above, so CTA-scope order holds)
-    if (TRAIN && g.ok)
+    if (dense && g.ok)
         patch_footprints<T>(a, g, joints, band_list, band_list_n, label_s, b, y_lo, y_hi, tid, kThreads);
 }
 
@@ -652,7 +664,8 @@ sfr_aug_kernel(SfrArgs a) {
         for (int i = tid; i < words; i += kAugThreads) reinterpret_cast<uint32_t*>(sm.joints)[i] = __ldcg(js + i);
         if (tid == 0) { sm.list_n = 0; sm.count = 0; sm.nan_seen = 0; }
     }
-    {   // pass A of phase 2: zero every map of the sample
+    const bool dense = a.heatmaps != nullptr;
+    if (dense) {   // pass A of phase 2: zero every map of the sample
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float* hp = a.heatmaps + static_cast<size_t>(b) * a.J * kMap;
         float* dp = a.dmap + static_cast<size_t>(b) * a.J * kMap;
@@ -755,7 +768,7 @@ sfr_aug_kernel(SfrArgs a) {
         a.valid[b] = (g.ok && !a.prep_flags[b] && !sm.nan_seen && sm.count >= 10) ? 1 : 0;
 
     // ---- phase 2, pass B
-    if (g.ok) patch_footprints<T>(a, g, sm.joints, sm.list, sm.list_n, sm.label, b, 0, kLabel, tid, kAugThreads);
+    if (dense && g.ok) patch_footprints<T>(a, g, sm.joints, sm.list, sm.list_n, sm.label, b, 0, kLabel, tid, kAugThreads);
 }
 
 // ---------------------------------------------------------------------------
@@ -891,7 +904,7 @@ extern "C" int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf
     if (workspace_size < workspace_bytes(B, 0)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  nullptr, nullptr, nullptr, valid, B, 0, nullptr, nullptr, nullptr, nullptr,
-                 prefilter_margin, prefilter_umax, prefilter_vmax, nullptr, nullptr};
+                 prefilter_margin, prefilter_umax, prefilter_vmax, nullptr, nullptr, nullptr};
     carve_workspace(a, workspace);
     return launch_sfr<false>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }
@@ -902,7 +915,8 @@ extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int W
                              float* img,
                              float* label_img,
                              float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
-                             float* heatmaps, float* dmap, uint8_t* valid, void* workspace, size_t workspace_size,
+                             float* heatmaps, float* dmap, pwr_joint_taps* joint_taps, uint8_t* valid,
+                             void* workspace, size_t workspace_size,
                              int B, int J, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
     if (J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
@@ -911,11 +925,13 @@ extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int W
         cube_size == nullptr || com_out == nullptr || uvd_norm == nullptr || valid == nullptr)
         return PWR_E_NULL;
     PWR_REQUIRE_PTR(img); PWR_REQUIRE_PTR(label_img); PWR_REQUIRE_PTR(mask);
-    PWR_REQUIRE_PTR(heatmaps); PWR_REQUIRE_PTR(dmap); PWR_REQUIRE_PTR(workspace);
+    PWR_OPTIONAL_PTR(heatmaps); PWR_OPTIONAL_PTR(dmap); PWR_OPTIONAL_PTR(joint_taps); PWR_REQUIRE_PTR(workspace);
+    if ((heatmaps == nullptr) != (dmap == nullptr)) return PWR_E_NULL;          // both dense maps or neither
+    if (heatmaps == nullptr && joint_taps == nullptr) return PWR_E_NULL;        // some form of targets is required
     if (workspace_size < workspace_bytes(B, J)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  uvd_norm, heatmaps, dmap, valid, B, J, nullptr, nullptr, nullptr, nullptr,
-                 prefilter_margin, prefilter_umax, prefilter_vmax, aug, nullptr};
+                 prefilter_margin, prefilter_umax, prefilter_vmax, joint_taps, aug, nullptr};
     carve_workspace(a, workspace);
     return launch_sfr<true>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }

@@ -189,7 +189,9 @@ class PixelwiseRegression(torch.nn.Module):
         the loss arithmetic inside the decoder kernels.  Returns (loss, every_loss, uvds):
         `every_loss[i]` is a [3] tensor (heatmap_loss, depthmap_loss, uvd_loss) of stage i
         (what train.py logs, :296-310) and `uvds[i]` the decoded coordinates.  The last
-        stage runs forward and backward+loss back to back (ops.fused_decoder_loss)."""
+        stage runs forward and backward+loss back to back (ops.fused_decoder_loss).
+        `heatmaps` may be the sparse `taps` tensor of sfr.build_sfr(targets="sparse")
+        (`depthmaps` is then ignored): the loss kernels evaluate the targets on the fly."""
         f = self.conv(img)
         loss = 0
         every_loss, uvds = [], []

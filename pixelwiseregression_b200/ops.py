@@ -8,6 +8,8 @@ Reference lines replaced: model.py:79-97, 123-132, 151 (decoder forward),
 what autograd derives from them plus train.py:197-207 (backward + loss),
 utils.py:332-337 + datasets.py:100-111 (recover_uvd / uvd2xyz).
 """
+from collections import namedtuple
+
 import torch
 
 from . import _lib
@@ -24,6 +26,24 @@ def _check_maps(z, label_img, mask):
     for name, t in (("label_img", label_img), ("mask", mask)):
         if t is not None and tuple(t.shape) != (B, 1, HW, HW):
             raise _lib.PwrError("%s must be [B, 1, 64, 64], got %s" % (name, tuple(t.shape)))
+
+
+SparseTargets = namedtuple("SparseTargets", ["taps", "uvd"])
+SparseTargets.__doc__ = """Compact targets of a batch: `taps` [B,J,64] uint8 (pwr_joint_taps records written by
+sfr.build_sfr(targets="sparse")) from which the loss kernels evaluate the heat-map and depth-map targets on
+the fly, and the normalised joint coordinates `uvd` [B,J,3]."""
+
+
+def _unpack_targets(targets, B, J):
+    """(heat_gt, dmap_gt, uvd_gt) dense maps, or SparseTargets -> (heat, dmap, uvd, taps) for the C ABI."""
+    if isinstance(targets, SparseTargets):
+        taps = targets.taps
+        require_cuda(taps)
+        if taps.dtype != torch.uint8 or tuple(taps.shape) != (B, J, 64) or not taps.is_contiguous():
+            raise _lib.PwrError("sparse targets must be a contiguous [B, J, 64] uint8 tensor of pwr_joint_taps")
+        return None, None, as_f32(targets.uvd), taps
+    heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
+    return heat_gt, dmap_gt, uvd_gt, None
 
 
 def _conv_maps(z, D, method):
@@ -54,13 +74,13 @@ def decoder_forward_raw(z, w, D, label_img, mask, method="softmax", store_heat=T
     H = torch.empty(z.shape, device=z.device, dtype=torch.float32) if store_heat else None
     uvd = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
     stats = torch.empty(B, J, 4, device=z.device, dtype=torch.float32) if want_stats else None
-    heat_gt = dmap_gt = uvd_gt = loss_partial = None
+    heat_gt = dmap_gt = uvd_gt = taps = loss_partial = None
     if targets is not None:
-        heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
+        heat_gt, dmap_gt, uvd_gt, taps = _unpack_targets(targets, B, J)
         loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
     with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd"):
         rc = lib.pwr_decoder_fwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
-                                 ptr(uvd_gt), ptr(H), ptr(uvd), ptr(stats), ptr(loss_partial), B, J,
+                                 ptr(uvd_gt), ptr(taps), ptr(H), ptr(uvd), ptr(stats), ptr(loss_partial), B, J,
                                  METHODS[method], map_dtype, stream_ptr(z.device))
     check(rc, "pwr_decoder_fwd")
     return H, uvd, stats, loss_partial
@@ -92,11 +112,12 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
                                      ptr(gw_partial), B, J, METHODS[method], map_dtype, s)
             check(rc, "pwr_decoder_bwd")
             return gz, gD, gw_partial, None
-        heat_gt, dmap_gt, uvd_gt = (as_f32(t) for t in targets)
+        heat_gt, dmap_gt, uvd_gt, taps = _unpack_targets(targets, B, J)
         loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32) if want_loss else None
         rc = lib.pwr_decoder_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
                                       ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(heat_gt),
-                                      ptr(dmap_gt), ptr(uvd_gt), float(alpha), float(lambda_h), float(lambda_d),
+                                      ptr(dmap_gt), ptr(uvd_gt), ptr(taps), float(alpha), float(lambda_h),
+                                      float(lambda_d),
                                       float(loss_scale), ptr(as_f32(loss_scale_dev)), int(n_mean), ptr(gz),
                                       ptr(gD), ptr(gw_partial),
                                       ptr(loss_partial), B, J, METHODS[method], map_dtype, s)
@@ -146,6 +167,15 @@ def stage_loss_from_partials(loss_partial, lambda_h, lambda_d, n_mean=0):
     return stage_loss(loss_partial, lambda_h, lambda_d, 1.0, n_mean)[:3]
 
 
+def _make_targets(heat_gt, dmap_gt, uvd_gt):
+    """The autograd functions receive plain tensors: a uint8 `heat_gt` IS the sparse taps tensor."""
+    if heat_gt is None:
+        return None
+    if heat_gt.dtype == torch.uint8:
+        return SparseTargets(heat_gt, uvd_gt)
+    return (heat_gt, dmap_gt, uvd_gt)
+
+
 class DecoderFunction(torch.autograd.Function):
     """Differentiable fused decoder: (z, w, D, label_img, mask) -> (heatmaps,
     depthmaps, uvd), model.py:147-151 without the two conv stacks.  `depthmaps`
@@ -162,7 +192,7 @@ class DecoderFunction(torch.autograd.Function):
     def forward(ctx, z, w, D, label_img, mask, method, heat_gt=None, dmap_gt=None, uvd_gt=None, alpha=1.0,
                 lambda_h=1.0, lambda_d=0.01):
         ctx.set_materialize_grads(False)
-        targets = (heat_gt, dmap_gt, uvd_gt) if heat_gt is not None else None
+        targets = _make_targets(heat_gt, dmap_gt, uvd_gt)
         H, uvd, stats, loss_partial = decoder_forward_raw(z, w, D, label_img, mask, method, targets=targets)
         ctx.method = method
         ctx.in_dtypes = (z.dtype, D.dtype)
@@ -184,7 +214,7 @@ class DecoderFunction(torch.autograd.Function):
             alpha, lambda_h, lambda_d = ctx.loss_cfg
             gz, gD, gw_partial, _ = decoder_backward_raw(
                 z, w, D, label_img, mask, stats, uvd, g_uvd, gH, gD_up, ctx.method,
-                targets=(heat_gt, dmap_gt, uvd_gt), alpha=alpha, lambda_h=lambda_h, lambda_d=lambda_d,
+                targets=_make_targets(heat_gt, dmap_gt, uvd_gt), alpha=alpha, lambda_h=lambda_h, lambda_d=lambda_d,
                 loss_scale_dev=g_total)
         else:
             gz, gD, gw_partial, _ = decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd, gH, gD_up,
@@ -276,7 +306,7 @@ class DecoderLossFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)       # no zero-filled gradient tensors for the detached outputs
         need_grad = any(ctx.needs_input_grad[:3])
         H, uvd, stats, _ = decoder_forward_raw(z, w, D, label_img, mask, method, store_heat=store_heat)
-        targets = (heat_gt, dmap_gt, uvd_gt)
+        targets = _make_targets(heat_gt, dmap_gt, uvd_gt)
         gz, gD, gw_partial, loss_partial = decoder_backward_raw(
             z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
             want_loss=True, want_gz=need_grad, want_gD=need_grad)
@@ -306,7 +336,9 @@ class DecoderLossFunction(torch.autograd.Function):
 
 def fused_decoder_loss(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method="softmax", alpha=1.0,
                        lambda_h=1.0, lambda_d=0.01, store_heat=True):
-    """Returns (total_loss, loss_terms[3] = (heatmap, depthmap, uvd), uvd[, heatmaps])."""
+    """Returns (total_loss, loss_terms[3] = (heatmap, depthmap, uvd), uvd[, heatmaps]).
+    `heat_gt` may be the uint8 taps tensor of sfr.build_sfr(targets="sparse") (then `dmap_gt` is
+    ignored / None): the targets are evaluated inside the loss kernel."""
     return DecoderLossFunction.apply(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method, float(alpha),
                                      float(lambda_h), float(lambda_d), bool(store_heat))
 

@@ -30,6 +30,23 @@ def decoder_bwd_bytes(J, with_targets=True, upstream_maps=False):
     return maps * MAP + 2 * MAP
 
 
+TAPS = 64    # sizeof(pwr_joint_taps)
+
+
+def sfr_build_sparse_bytes(J):
+    """train mode with compact targets: no dense heat / depth maps, 64 B of taps per joint."""
+    return 65536 + (65536 + 2 * MAP) + TAPS * J + 12 * J + 20
+
+
+def decoder_bwd_sparse_bytes(J):
+    """read z, D + L, m + 64 B of taps per joint; write gz, gD."""
+    return 4 * J * MAP + 2 * MAP + TAPS * J
+
+
+def step_sparse_bytes(J):
+    return sfr_build_sparse_bytes(J) + decoder_fwd_bytes(J) + decoder_bwd_sparse_bytes(J)
+
+
 def step_bytes(J):
     """SFR build + decoder forward + last-stage backward+loss (BASELINE config 2)."""
     return sfr_build_bytes(J) + decoder_fwd_bytes(J) + decoder_bwd_bytes(J)

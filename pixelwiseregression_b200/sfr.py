@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import check, ptr, require_cuda, stream_ptr
 
 SFRBatch = namedtuple("SFRBatch", ["img", "label_img", "mask", "box_size", "cube_size", "com", "uvd", "heatmaps",
-                                   "depthmaps", "valid"])
+                                   "depthmaps", "valid", "taps"], defaults=(None,))
 SFRTestBatch = namedtuple("SFRTestBatch", ["img", "label_img", "mask", "box_size", "cube_size", "com", "valid"])
 
 
@@ -77,13 +77,17 @@ def _aug_device_params(aug, B, device):
 
 
 def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only=False, frame_format="f32",
-              prefilter=None, augment=None):
+              prefilter=None, augment=None, targets="dense"):
     """frames [B,Hf,Wf] CUDA depth frames: float32 mm (`frame_format="f32"`, what
     process_single_data receives), or raw sensor samples decoded on the fly exactly as
     the reference's loaders do: "nyu_gb16" = uint16 G<<8|B of the NYU PNG
     (datasets.py:810), "u16" = 16-bit grey PNG (ICVL :632, HAND17 :940).
     `prefilter=(margin, halfu, halfv)` applies the hand rectangle of load_from_text
     (NYU/HAND17 margin 40, ICVL 30; datasets.py:841-853) inside the crop taps.
+    `targets`: "dense" renders heatmaps / depthmaps [B,J,64,64] like the reference; "sparse" returns
+    them as `taps` [B,J,64] uint8 (one 64-byte pwr_joint_taps per joint) for the loss kernels to
+    evaluate on the fly (ops.fused_decoder_loss / model.forward_loss accept it in place of the
+    dense heat maps), which removes the write and re-read of 2J maps per sample; "both" does both.
     `augment` = [B,4] (scale, shift_u, shift_v, angle_deg), e.g. from `draw_augmentation`: the
     reference's augmented branch (datasets.py:216-299, train.py's default flags) with these
     draws; samples whose augmented branch would raise fall back to the plain branch.
@@ -146,14 +150,17 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     if uvd.dim() != 3 or uvd.shape[0] != B or uvd.shape[2] != 3:
         raise _lib.PwrError("uvd must be [B, J, 3]")
     J = uvd.shape[1]
+    if targets not in ("dense", "sparse", "both"):
+        raise _lib.PwrError("targets must be 'dense', 'sparse' or 'both'")
     uvd_norm = torch.empty(B, J, 3, **f32)
-    heatmaps = torch.empty(B, J, 64, 64, **f32)
-    dmap = torch.empty(B, J, 64, 64, **f32)
+    heatmaps = torch.empty(B, J, 64, 64, **f32) if targets != "sparse" else None
+    dmap = torch.empty(B, J, 64, 64, **f32) if targets != "sparse" else None
+    taps = torch.empty(B, J, 64, device=dev, dtype=torch.uint8) if targets != "dense" else None
     aug_dev = _aug_device_params(augment, B, dev) if augment is not None else None
     with torch.cuda.device(dev), _lib.timed("pwr_sfr_build"):
         rc = lib.pwr_sfr_build(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), ptr(uvd), ptr(aug_dev), float(fx), float(fy),
                                int(frame_f64), pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
-                               ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(valid), ptr(workspace),
-                               ws_bytes, B, J, s)
+                               ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(taps), ptr(valid),
+                               ptr(workspace), ws_bytes, B, J, s)
     check(rc, "pwr_sfr_build")
-    return SFRBatch(img, label_img, mask, box_size, cube_size, com_out, uvd_norm, heatmaps, dmap, valid)
+    return SFRBatch(img, label_img, mask, box_size, cube_size, com_out, uvd_norm, heatmaps, dmap, valid, taps)

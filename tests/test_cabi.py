@@ -53,21 +53,21 @@ def test_argument_errors_without_a_gpu(lib):
     fake = ctypes.c_void_p(0x1000)          # aligned, never dereferenced: validation fails first
     odd = ctypes.c_void_p(0x1004)           # misaligned
     # NULL required pointer
-    assert lib.pwr_decoder_fwd(null, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 0, 0, null) == -1
+    assert lib.pwr_decoder_fwd(null, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 1, 14, 0, 0, null) == -1
     # misaligned map pointer
-    assert lib.pwr_decoder_fwd(odd, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 0, 0, null) == -3
+    assert lib.pwr_decoder_fwd(odd, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 1, 14, 0, 0, null) == -3
     # unknown method / bad shapes
-    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 7, 0, null) == -4
-    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 0, 0, 0, null) == -2
-    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, -1, 14, 0, 0, null) == -2
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 1, 14, 7, 0, null) == -4
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 1, 0, 0, 0, null) == -2
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, -1, 14, 0, 0, null) == -2
     # unknown conv dtype, and caller-supplied heat maps exist in float32 only
-    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 0, 5, null) == -4
-    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 1, 14, 2, 1, null) == -4
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 1, 14, 0, 5, null) == -4
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 1, 14, 2, 1, null) == -4
     assert lib.pwr_sfr_com(null, 480, 640, fake, 1, null) == -1
     assert lib.pwr_sfr_com(fake, 0, 640, fake, 1, null) == -2
     assert lib.pwr_reduce_partials(null, fake, 1, 1, 1, null) == -1
     # B == 0 is a successful no-op
-    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, fake, fake, fake, null, 0, 14, 0, 0, null) == 0
+    assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 0, 14, 0, 0, null) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -342,3 +342,50 @@ def test_autocast_training_step_through_the_fused_decoder():
     assert H2.dtype == torch.float32 and Dm.dtype == torch.float16 and uvd2.dtype == torch.float32
     ((H2 ** 2).sum() + (Dm.float() ** 2).sum() * 1e-3 + (uvd2 ** 2).sum()).backward()
     assert z2.grad.dtype == torch.float16 and D2.grad.dtype == torch.float16
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5])
+def test_sparse_targets_equal_dense_targets(alpha):
+    """sfr.build_sfr(targets="both"): the loss kernels evaluating heat-map / depth-map targets on the
+    fly from the 64-byte taps give the same loss terms and gradients as reading the dense maps."""
+    from pixelwiseregression_b200 import sfr
+    shape = synth.NYU
+    B, J = 12, shape.joints
+    d = synth.make_frames(shape, B, seed=51)
+    uvd_np = d["uvd"].copy()
+    uvd_np[0, 0, :2] = d["com"][0, :2] + np.array([-0.97, 0.3]) * 100      # a joint on the map border (reflection)
+    batch = sfr.build_sfr(torch.from_numpy(d["frames"]).cuda(), d["com"], d["cube"], uvd_np, fx=shape.fx, fy=shape.fy,
+                          targets="both")
+    assert batch.taps.shape == (B, J, 64) and batch.taps.dtype == torch.uint8
+    g = torch.Generator(device=DEV).manual_seed(3)
+    z = torch.randn(B, J, 64, 64, device=DEV, generator=g) * 3
+    D = torch.randn(B, J, 64, 64, device=DEV, generator=g)
+    w = torch.rand(J, 1, device=DEV, generator=g) + 0.5
+    gH = torch.randn(B, J, 64, 64, device=DEV, generator=g) * 1e-3
+    gDu = torch.randn(B, J, 64, 64, device=DEV, generator=g) * 1e-3
+    dense = (batch.heatmaps, batch.depthmaps, batch.uvd)
+    sparse = ops.SparseTargets(batch.taps, batch.uvd)
+    # forward with loss (inner stage)
+    _, uvd_d, st, lp_d = ops.decoder_forward_raw(z, w, D, batch.label_img, batch.mask, targets=dense)
+    _, uvd_s, _, lp_s = ops.decoder_forward_raw(z, w, D, batch.label_img, batch.mask, targets=sparse)
+    assert torch.equal(uvd_d, uvd_s)
+    assert_close("fwd loss partials", lp_s.cpu().numpy(), lp_d.cpu().numpy(), 1e-5)
+    # backward + loss: pipelined (no upstream), pipelined with upstream maps (only possible with sparse
+    # targets), and the direct kernel
+    for up in (dict(), dict(gH_up=gH, gD_up=gDu)):
+        a = ops.decoder_backward_raw(z, w, D, batch.label_img, batch.mask, st, uvd_d, targets=dense, alpha=alpha,
+                                     want_loss=True, **up)
+        b = ops.decoder_backward_raw(z, w, D, batch.label_img, batch.mask, st, uvd_d, targets=sparse, alpha=alpha,
+                                     want_loss=True, **up)
+        assert_close("gz", b[0].cpu().numpy(), a[0].cpu().numpy(), 1e-5)
+        assert_close("gD", b[1].cpu().numpy(), a[1].cpu().numpy(), 1e-5)
+        assert_close("gw", b[2].cpu().numpy(), a[2].cpu().numpy(), 1e-5)
+        assert_close("loss partials", b[3].cpu().numpy(), a[3].cpu().numpy(), 1e-5)
+    # through the public fused criterion
+    zz = z.clone().requires_grad_(True)
+    total_d, terms_d, *_ = ops.fused_decoder_loss(zz, w, D, batch.label_img, batch.mask, batch.heatmaps,
+                                                  batch.depthmaps, batch.uvd, alpha=alpha)
+    total_s, terms_s, *_ = ops.fused_decoder_loss(zz, w, D, batch.label_img, batch.mask, batch.taps, None, batch.uvd,
+                                                  alpha=alpha)
+    assert_close("terms", terms_s.cpu().numpy(), terms_d.cpu().numpy(), 1e-5)
+    assert abs(total_s.item() - total_d.item()) <= 1e-5 * abs(total_d.item())

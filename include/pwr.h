@@ -177,8 +177,8 @@ int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
  *   time, train.py:197-199).  taps [B,J] != NULL replaces the dense heat_gt /
  *   dmap_gt (which may then be NULL): the targets are evaluated on the fly.
  * outputs: H [B,J,64,64] normalised heat maps (NULL = do not store, e.g. the
- *   last stage at inference); uvd [B,J,3]; stats [B,J,4] = (softmax offset in
- *   log2 units, 1/sum, masked-heat sum + 1e-14, d) saved for the backward
+ *   last stage at inference); uvd [B,J,3]; stats [B,J,4] = (extremum of z
+ *   in the direction of sign(w), 1/sum, masked-heat sum + 1e-14, d) saved for the backward
  *   (NULL = do not store); loss_partial [B,J,3] per-(b,j) sums of squares
  *   (heat, dmap, uvd) before lambda/mean scaling (NULL = no loss). */
 int pwr_decoder_fwd(const void* z, const float* w, const void* D,

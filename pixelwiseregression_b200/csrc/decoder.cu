@@ -161,40 +161,71 @@ __device__ __forceinline__ float gauss_reach_f(int x, int t) {
     return wgt;
 }
 
-struct TapsF { float a, b, c, d, cdn; int tx0, tx1, ty0, ty1, ok; };
+// Footprint table: the blurred 4-tap splat is non-zero on <= 8x8 pixels.  Before a CTA walks the
+// 4096 pixels of a map, 121 threads evaluate the heat target on the 11 x 11 candidate grid
+// (rows ty0-3..ty0+3 then ty1..ty1+3, same for columns; entries that fall outside the map or
+// repeat an earlier row/column stay 0 and are never looked up) into shared memory; the hot loop
+// then only does an integer range test per 4-pixel chunk and, inside the footprint, a table lookup.
+constexpr int kCand = 11;
+constexpr int kFootprint = kCand * kCand;
 
-__device__ __forceinline__ TapsF load_taps(const pwr_joint_taps* __restrict__ p) {
-    const double4 t = *reinterpret_cast<const double4*>(p->tap);
-    TapsF f;
-    f.a = static_cast<float>(t.x); f.b = static_cast<float>(t.y); f.c = static_cast<float>(t.z); f.d = static_cast<float>(t.w);
-    f.cdn = static_cast<float>(p->cd_norm);
-    f.tx0 = p->tx0; f.tx1 = p->tx1; f.ty0 = p->ty0; f.ty1 = p->ty1; f.ok = p->ok;
-    return f;
+struct TapsIdx { int tx0, tx1, ty0, ty1, ok; float cdn; };
+
+// `raw` = the 16 words of a pwr_joint_taps record (global or shared memory)
+__device__ __forceinline__ TapsIdx taps_index(const uint32_t* raw) {
+    const pwr_joint_taps* p = reinterpret_cast<const pwr_joint_taps*>(raw);
+    TapsIdx t;
+    t.tx0 = p->tx0; t.tx1 = p->tx1; t.ty0 = p->ty0; t.ty1 = p->ty1; t.ok = p->ok;
+    t.cdn = static_cast<float>(p->cd_norm);
+    return t;
 }
 
-// targets of the 4 pixels (row y, columns x0..x0+3): heat = blur of the four taps, Dmap =
+// one candidate of the footprint table (thread `c` of the first kFootprint threads)
+__device__ __forceinline__ float footprint_entry(const uint32_t* raw, int c) {
+    const pwr_joint_taps* p = reinterpret_cast<const pwr_joint_taps*>(raw);
+    const int sy = c / kCand, sx = c - sy * kCand;
+    const int ty0 = p->ty0, ty1 = p->ty1, tx0 = p->tx0, tx1 = p->tx1;
+    const int y = sy < 7 ? ty0 + sy - 3 : ty1 + sy - 7;
+    const int x = sx < 7 ? tx0 + sx - 3 : tx1 + sx - 7;
+    if (!p->ok || y < 0 || y >= kLabel || x < 0 || x >= kLabel) return 0.f;
+    if ((sy >= 7 && abs(y - ty0) <= 3) || (sx >= 7 && abs(x - tx0) <= 3)) return 0.f;
+    const float a = static_cast<float>(p->tap[0]), b = static_cast<float>(p->tap[1]);
+    const float cc = static_cast<float>(p->tap[2]), d = static_cast<float>(p->tap[3]);
+    const float wy0 = gauss_reach_f(y, ty0), wy1 = gauss_reach_f(y, ty1);
+    const float wx0 = gauss_reach_f(x, tx0), wx1 = gauss_reach_f(x, tx1);
+    return wy0 * (a * wx0 + b * wx1) + wy1 * (cc * wx0 + d * wx1);
+}
+
+// targets of the 4 pixels (row y, columns x0..x0+3): heat from the table, Dmap =
 // (cd/cube - label_img) * [heat > 0] * mask (datasets.py:372-374, 380); zero outside the footprint
-__device__ __forceinline__ void sparse_targets(const TapsF& t, int y, int x0, const float4& l4, const float4& m4,
-                                               float4& hg, float4& dg) {
+__device__ __forceinline__ void sparse_lookup(const TapsIdx& t, const float* fp, int y, int x0, const float4& l4,
+                                              const float4& m4, float4& hg, float4& dg) {
     hg = make_float4(0.f, 0.f, 0.f, 0.f);
     dg = hg;
-    if (!t.ok) return;
-    if (abs(y - t.ty0) > 3 && abs(y - t.ty1) > 3) return;
-    if (!((x0 + 3 >= t.tx0 - 3 && x0 <= t.tx0 + 3) || (x0 + 3 >= t.tx1 - 3 && x0 <= t.tx1 + 3))) return;
-    const float wy0 = gauss_reach_f(y, t.ty0), wy1 = gauss_reach_f(y, t.ty1);
+    int sy = -1;
+    if (abs(y - t.ty0) <= 3) sy = y - t.ty0 + 3;
+    else if (y - t.ty1 >= 0 && y - t.ty1 <= 3) sy = 7 + y - t.ty1;
+    if (!t.ok || sy < 0) return;
+    if (!((x0 + 3 >= t.tx0 - 3 && x0 <= t.tx0 + 3) || (x0 + 3 >= t.tx1 && x0 <= t.tx1 + 3))) return;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float wx0 = gauss_reach_f(x0 + k, t.tx0), wx1 = gauss_reach_f(x0 + k, t.tx1);
-        const float h = wy0 * (t.a * wx0 + t.b * wx1) + wy1 * (t.c * wx0 + t.d * wx1);
+        const int x = x0 + k;
+        int sx = -1;
+        if (abs(x - t.tx0) <= 3) sx = x - t.tx0 + 3;
+        else if (x - t.tx1 >= 0 && x - t.tx1 <= 3) sx = 7 + x - t.tx1;
+        const float h = sx >= 0 ? fp[sy * kCand + sx] : 0.f;
         set_comp(hg, k, h);
         set_comp(dg, k, (h > 0.f && comp(m4, k) != 0.f) ? t.cdn - comp(l4, k) : 0.f);
     }
 }
 
+// LOSS template parameter of the kernels below
+enum { LOSS_NONE = 0, LOSS_DENSE = 1, LOSS_SPARSE = 2 };   // no loss | dense target maps | pwr_joint_taps
+
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int METHOD, bool LOSS, typename TZ>
+template <int METHOD, int LOSS, typename TZ>
 __global__ void __launch_bounds__(kThreads)
 decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, const void* __restrict__ D,
                    const float* __restrict__ L, const float* __restrict__ m,
@@ -224,17 +255,24 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         for (int i = 0; i < kVec; ++i) mv[i] = lv[i] = dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    float c = 0.f, shift = 0.f;
+    float c = 0.f, shift = 0.f, zext = 0.f;
     if (METHOD == PWR_METHOD_SOFTMAX) {
         c = w[j] * kLog2e;
-        shift = block_extremum(zv, c >= 0.f, scratch) * c;
+        zext = block_extremum(zv, c >= 0.f, scratch);
+        shift = zext * c;                          // the backward recomputes exactly this product
     }
 
     const PixelCoords pc = pixel_coords();
-    const bool sparse = LOSS && taps != nullptr;
-    TapsF tp;
-    if (sparse) tp = load_taps(taps + bj);
-    float4 hgs[kVec];                           // sparse heat targets, kept for the second loop
+    constexpr bool sparse = (LOSS == LOSS_SPARSE);
+    __shared__ float fp[sparse ? kFootprint : 1];
+    TapsIdx tp;
+    if (sparse) {
+        const uint32_t* raw = reinterpret_cast<const uint32_t*>(taps + bj);
+        tp = taps_index(raw);
+        if (threadIdx.x < kFootprint) fp[threadIdx.x] = footprint_entry(raw, threadIdx.x);
+        __syncthreads();
+    }
+    float4 hgs[sparse ? kVec : 1];              // sparse heat targets, kept for the second loop
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum e, e*(x-32), e*(y-32), e*m, e*m*m*(D+L)
     float ld2 = 0.f;                            // sum (D - Dgt)^2
 #pragma unroll
@@ -243,8 +281,8 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         float rowsum = 0.f;
         float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
         if (LOSS) {
-            if (sparse) sparse_targets(tp, static_cast<int>(threadIdx.x >> 4) + 16 * i, static_cast<int>(threadIdx.x & 15) * 4,
-                                       lv[i], mv[i], hgs[i], dg);
+            if (sparse) sparse_lookup(tp, fp, static_cast<int>(threadIdx.x >> 4) + 16 * i, static_cast<int>(threadIdx.x & 15) * 4,
+                                      lv[i], mv[i], hgs[sparse ? i : 0], dg);
             else dg = ld_stream(dmap_gt + off + i * (kThreads * 4));
         }
 #pragma unroll
@@ -271,7 +309,7 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         float4 h = zv[i];
         h.x *= inv_s; h.y *= inv_s; h.z *= inv_s; h.w *= inv_s;
         if (LOSS) {
-            const float4 hg = sparse ? hgs[i] : ld_stream(heat_gt + off + i * (kThreads * 4));
+            const float4 hg = sparse ? hgs[sparse ? i : 0] : ld_stream(heat_gt + off + i * (kThreads * 4));
             const float e0 = h.x - hg.x, e1 = h.y - hg.y, e2 = h.z - hg.z, e3 = h.w - hg.w;
             lh2[0] += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
         }
@@ -286,7 +324,7 @@ decoder_fwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         uvd[bj * 3 + 1] = v;
         uvd[bj * 3 + 2] = d;
         if (stats != nullptr)
-            reinterpret_cast<float4*>(stats)[bj] = make_float4(shift, inv_s, den, d);
+            reinterpret_cast<float4*>(stats)[bj] = make_float4(zext, inv_s, den, d);
         if (LOSS) {
             const float eu = u - uvd_gt[bj * 3 + 0], ev = v - uvd_gt[bj * 3 + 1], ed = d - uvd_gt[bj * 3 + 2];
             loss_partial[bj * 3 + 0] = lh2[0];
@@ -310,7 +348,7 @@ struct LossCoef {
 // the target maps are only read when they matter (non-zero map weights or
 // loss_partial requested), so the default alpha = 1 costs no extra traffic
 // unless the caller wants the logged loss values.
-template <int METHOD, bool LOSS, typename TZ>
+template <int METHOD, int LOSS, typename TZ>
 __global__ void __launch_bounds__(kThreads)
 decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, const void* __restrict__ D,
                    const float* __restrict__ L, const float* __restrict__ m, const float* __restrict__ stats,
@@ -332,17 +370,24 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
     const size_t offb = static_cast<size_t>(b) * kMap + threadIdx.x * 4;
     const bool depth = (D != nullptr);
     const bool map_loss = LOSS && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
-    const bool sparse = map_loss && taps != nullptr;
-    TapsF tp;
-    if (sparse) tp = load_taps(taps + bj);
+    const bool sparse = (LOSS == LOSS_SPARSE) && map_loss;
+    __shared__ float fp[LOSS == LOSS_SPARSE ? kFootprint : 1];
+    TapsIdx tp;
+    if (LOSS == LOSS_SPARSE) {
+        const uint32_t* raw = reinterpret_cast<const uint32_t*>(taps + bj);
+        tp = taps_index(raw);
+        if (threadIdx.x < kFootprint) fp[threadIdx.x] = footprint_entry(raw, threadIdx.x);
+        __syncthreads();
+    }
 
     float4 zv[kVec], pv[kVec], gv[kVec];   // logits, heat p, dL/dp
 #pragma unroll
     for (int i = 0; i < kVec; ++i) zv[i] = MapIO<TZ>::ld(z, off + i * (kThreads * 4));
 
-    const float4 st = reinterpret_cast<const float4*>(stats)[bj];   // (shift, 1/sum, den, d)
+    const float4 st = reinterpret_cast<const float4*>(stats)[bj];   // (z extremum, 1/sum, den, d)
     const float wj = (METHOD == PWR_METHOD_SOFTMAX) ? w[j] : 1.f;
     const float c = wj * kLog2e;
+    const float shift = st.x * c;
     float gu = 0.f, gvv = 0.f, gd = 0.f, lu = 0.f;
     if (g_uvd != nullptr) { gu = g_uvd[bj * 3 + 0]; gvv = g_uvd[bj * 3 + 1]; gd = g_uvd[bj * 3 + 2]; }
     if (LOSS) {
@@ -365,15 +410,16 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         const size_t ob = offb + i * (kThreads * 4);
         float4 d4 = zero4, l4 = zero4, m4 = zero4, hg = zero4, dg = zero4, uh = zero4, ud = zero4;
         if (depth) { d4 = MapIO<TZ>::ld(D, o); l4 = ld_keep(L + ob); m4 = ld_keep(m + ob); }
-        if (sparse) sparse_targets(tp, static_cast<int>(threadIdx.x >> 4) + 16 * i, static_cast<int>(threadIdx.x & 15) * 4, l4, m4, hg, dg);
-        else if (map_loss) { hg = ld_stream(heat_gt + o); if (depth) dg = ld_stream(dmap_gt + o); }
+        if (LOSS == LOSS_SPARSE) {
+            if (sparse) sparse_lookup(tp, fp, static_cast<int>(threadIdx.x >> 4) + 16 * i, static_cast<int>(threadIdx.x & 15) * 4, l4, m4, hg, dg);
+        } else if (map_loss) { hg = ld_stream(heat_gt + o); if (depth) dg = ld_stream(dmap_gt + o); }
         if (gH_up != nullptr) uh = ld_stream(gH_up + o);
         if (gD_up != nullptr) ud = MapIO<TZ>::ld(gD_up, o);
         const float gyrow = gv63 * (pc.ys0 + 16.f * i);
         float4 gd4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float p = heat_raw<METHOD>(comp(zv[i], k), c, st.x) * st.y;
+            const float p = heat_raw<METHOD>(comp(zv[i], k), c, shift) * st.y;
             const float mk = comp(m4, k), dk = comp(d4, k);
             const float rec = mk * (dk + comp(l4, k));
             float gp = fmaf(gu63, pc.xs + static_cast<float>(k), gyrow);
@@ -485,24 +531,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Block-wide sums for the persistent kernel.  The caller alternates between two scratch buffers,
+// so the usual trailing barrier (scratch reuse) is not needed: the next writer of this buffer is two
+// items away and every item ends with a __syncthreads.
 template <int N>
 __device__ __forceinline__ void pipe_block_sum(float (&v)[N], float* scratch) {
+    static_assert(kPipeWarps == 16, "second level reduces 16 per-warp partials with a 4-step shuffle tree");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) scratch[warp * N + i] = v[i];
+        for (int i = 0; i < N; ++i) scratch[i * kPipeWarps + warp] = v[i];
     }
     __syncthreads();
+    // every warp reduces the 16 partials of each value itself: one shared load per lane and four
+    // shuffles instead of 16 loads + adds per thread
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        float s = 0.f;
+        float s = scratch[i * kPipeWarps + (lane & (kPipeWarps - 1))];
 #pragma unroll
-        for (int wv = 0; wv < kPipeWarps; ++wv) s += scratch[wv * N + i];
+        for (int o = kPipeWarps / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         v[i] = s;
     }
-    __syncthreads();
 }
 
 struct PipeArgs {
@@ -517,14 +568,20 @@ struct PipeArgs {
     int slots_are_targets;                     // 1: slot2/3 = heat_gt/dmap_gt, 0: = gH_up/gD_up
 };
 
-template <int METHOD, bool LOSS, typename TZ>
+template <int METHOD, int LOSS, typename TZ>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 decoder_bwd_pipe_kernel(PipeArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_base = reinterpret_cast<float*>(smem_raw);                               // [stages][4][4096]
     float* lm_base = stage_base + kPipeStages * 4 * kMap;                                 // [2][2][4096]
     uint64_t* full = reinterpret_cast<uint64_t*>(lm_base + 2 * 2 * kMap);                 // [stages]
-    __shared__ float scratch[kPipeWarps * 3];
+    __shared__ float scratch[2][kPipeWarps * 5];      // double-buffered: one barrier per reduction
+    // Per-item scalars (stats, upstream / predicted / target uvd, the 64-byte taps record) are
+    // prefetched one item ahead by the first 32 threads: the global loads are issued at the top of
+    // iteration k and parked in shared memory at its end, so no item starts with an exposed
+    // L2 / HBM round trip.  Word layout: 0-3 stats, 4-6 g_uvd, 7-9 uvd, 10-12 uvd_gt, 16-31 taps.
+    __shared__ __align__(16) uint32_t scal[2][32];
+    __shared__ float fp[LOSS == LOSS_SPARSE ? kFootprint : 1];
 
     const int tid = threadIdx.x;
     const long long first = static_cast<long long>(a.items) * blockIdx.x / gridDim.x;
@@ -548,8 +605,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
     const uint32_t stage_tx = 2 * kZBytes + (has2 ? kSlotBytes : 0) + (has3 ? slot3_bytes : 0);
 
     // producer (thread 0): stream item `it` into stage `s`; fetch L, m when the sample changes
-    auto issue = [&](long long it, int s, int prev_b, int lm_buf) {
-        const int b = static_cast<int>(it / a.J);
+    auto issue = [&](long long it, int b, int s, int prev_b, int lm_buf) {
         const size_t off = static_cast<size_t>(it) * kMap;
         float* st = stage_base + s * 4 * kMap;
         const bool new_lm = (b != prev_b);
@@ -568,10 +624,23 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
         }
     };
 
+    auto scalar_word = [&](long long it, int wd) -> uint32_t {
+        const size_t bj = static_cast<size_t>(it);
+        if (wd < 4) return __float_as_uint(a.stats[bj * 4 + wd]);
+        if (wd < 7) return a.g_uvd != nullptr ? __float_as_uint(a.g_uvd[bj * 3 + wd - 4]) : 0u;
+        if (wd < 10) return (LOSS && a.uvd != nullptr) ? __float_as_uint(a.uvd[bj * 3 + wd - 7]) : 0u;
+        if (wd < 13) return LOSS ? __float_as_uint(a.uvd_gt[bj * 3 + wd - 10]) : 0u;
+        if (wd >= 16 && LOSS == LOSS_SPARSE) return reinterpret_cast<const uint32_t*>(a.taps + bj)[wd - 16];
+        return 0u;
+    };
+
     // lm_cur: buffer holding the current item's L/m; toggles whenever the sample changes
     int lm_cur = 0;
     int b_cur = static_cast<int>(first / a.J);
-    if (tid == 0) issue(first, 0, -1, 0);
+    int j_cur = static_cast<int>(first - static_cast<long long>(b_cur) * a.J);
+    if (tid == 0) issue(first, b_cur, 0, -1, 0);
+    if (tid < 32) scal[0][tid] = scalar_word(first, tid);
+    __syncthreads();
 
     const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
     const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + 32*i
@@ -583,30 +652,37 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
         // prefetch the next item into the other stage (its readers finished before the barrier
         // that ended the previous iteration)
         const long long nxt = it + 1;
-        const int b_next = nxt < last ? static_cast<int>(nxt / a.J) : b_cur;
+        const int j_next = (j_cur + 1 == a.J) ? 0 : j_cur + 1;
+        const int b_next = (nxt < last && j_next == 0) ? b_cur + 1 : b_cur;
         const int lm_next = (b_next != b_cur) ? (lm_cur ^ 1) : lm_cur;
-        if (tid == 0 && nxt < last) issue(nxt, (k + 1) % kPipeStages, b_cur, lm_next);
+        if (tid == 0 && nxt < last) issue(nxt, b_next, (k + 1) % kPipeStages, b_cur, lm_next);
+        const uint32_t next_word = (tid < 32 && nxt < last) ? scalar_word(nxt, tid) : 0u;   // lands during the compute
 
         const int bj = static_cast<int>(it);
-        const int j = bj - b_cur * a.J;
-        const float4 st = reinterpret_cast<const float4*>(a.stats)[bj];   // (shift, 1/sum, den, d)
+        const int j = j_cur;
+        const float* sc = reinterpret_cast<const float*>(scal[k & 1]);
+        const float4 st = *reinterpret_cast<const float4*>(sc);           // (z extremum, 1/sum, den, d)
         const float wj = (METHOD == PWR_METHOD_SOFTMAX) ? a.w[j] : 1.f;
         const float c = wj * kLog2e;
-        float gu = 0.f, gvv = 0.f, gd = 0.f, lu = 0.f;
-        if (a.g_uvd != nullptr) { gu = a.g_uvd[bj * 3 + 0]; gvv = a.g_uvd[bj * 3 + 1]; gd = a.g_uvd[bj * 3 + 2]; }
+        const float shift = st.x * c, zref = st.x;
+        float gu = sc[4], gvv = sc[5], gd = sc[6], lu = 0.f;
         if (LOSS) {
-            const float eu = a.uvd[bj * 3 + 0] - a.uvd_gt[bj * 3 + 0];
-            const float ev = a.uvd[bj * 3 + 1] - a.uvd_gt[bj * 3 + 1];
-            const float ed = a.uvd[bj * 3 + 2] - a.uvd_gt[bj * 3 + 2];
+            const float eu = sc[7] - sc[10], ev = sc[8] - sc[11], ed = sc[9] - sc[12];
             gu = fmaf(a.coef.cu, eu, gu); gvv = fmaf(a.coef.cu, ev, gvv); gd = fmaf(a.coef.cu, ed, gd);
             lu = eu * eu + ev * ev + ed * ed;
         }
-        const float gu63 = gu / 63.f, gv63 = gvv / 63.f;
-        const float gdd = gd / st.z;
+        const float gu63 = gu * (1.f / 63.f), gv63 = gvv * (1.f / 63.f);
+        const float gdd = __fdividef(gd, st.z);
         const float dcoord = st.w;
-        const bool sparse = LOSS && a.taps != nullptr;
-        TapsF tp;
-        if (sparse) tp = load_taps(a.taps + bj);
+        constexpr bool sparse = (LOSS == LOSS_SPARSE);
+        TapsIdx tp;
+        if (sparse) {
+            // footprint table of this item from the prefetched taps record (fp's previous readers
+            // finished before the barrier that ended the previous iteration)
+            tp = taps_index(scal[k & 1] + 16);
+            if (tid < kFootprint) fp[tid] = footprint_entry(scal[k & 1] + 16, tid);
+            __syncthreads();
+        }
 
         const float* sz = stage_base + s * 4 * kMap;          // slot bases (each slot is 16 KiB apart)
         const float* sD = sz + kMap;
@@ -617,8 +693,12 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
 
         mbar_wait(&full[s], parity);
 
+        // acc: sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2, and for dL/dw = sum_px gy*z with gy = p*(gp - S1):
+        // T1 = sum p*gp*(z - zref), T2 = sum p*(z - zref)  =>  sum gy*z = T1 - S1*T2 (sum gy = 0 makes the
+        // reference point free; zref = the extremum, where p peaks, keeps both sums small), so dL/dw
+        // needs no second pass over z and no second block reduction.
         float4 pv[kPipeVec], gv[kPipeVec];
-        float acc[3] = {0.f, 0.f, 0.f};
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < kPipeVec; ++i) {
             const int cidx = tid + i * kPipeThreads;
@@ -629,13 +709,13 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
             const float4 q3 = has3 ? (tg ? MapIO<float>::smem(s3, cidx) : MapIO<TZ>::smem(s3, cidx)) : zero4;
             float4 t2 = tg ? q2 : zero4, t3 = tg ? q3 : zero4;          // targets
             const float4 u2 = tg ? zero4 : q2, u3 = tg ? zero4 : q3;    // upstream gradients
-            if (sparse) sparse_targets(tp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
+            if (sparse) sparse_lookup(tp, fp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
             const bool have_h = sparse || (tg && has2), have_d = sparse || (tg && has3);
             const float gyrow = gv63 * (ys0 + 32.f * i);
             float4 gd4;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const float p = heat_raw<METHOD>(comp(z4, kk), c, st.x) * st.y;
+                const float p = heat_raw<METHOD>(comp(z4, kk), c, shift) * st.y;
                 const float mk = comp(m4, kk), dk = comp(d4, kk);
                 const float rec = mk * (dk + comp(l4, kk));
                 float gp = fmaf(gu63, xs + static_cast<float>(kk), gyrow);
@@ -651,33 +731,35 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
                 }
                 gp += comp(u2, kk);
                 gdk += comp(u3, kk);
-                acc[0] = fmaf(gp, p, acc[0]);
+                const float pg = gp * p;
+                acc[0] += pg;
+                if (METHOD == PWR_METHOD_SOFTMAX) {
+                    const float dz = comp(z4, kk) - zref;
+                    acc[3] = fmaf(pg, dz, acc[3]);
+                    acc[4] = fmaf(p, dz, acc[4]);
+                }
                 set_comp(pv[i], kk, p);
                 set_comp(gv[i], kk, gp);
                 set_comp(gd4, kk, gdk);
             }
             if (a.gD != nullptr) MapIO<TZ>::st(a.gD, static_cast<size_t>(bj) * kMap + cidx * 4, gd4);
         }
-        if (METHOD != PWR_METHOD_GIVEN || LOSS) pipe_block_sum<3>(acc, scratch);
+        if (METHOD != PWR_METHOD_GIVEN || LOSS) pipe_block_sum<5>(acc, scratch[k & 1]);
 
         const float s1 = acc[0];
-        float sw[1] = {0.f};
         if (a.gz != nullptr) {
 #pragma unroll
             for (int i = 0; i < kPipeVec; ++i) {
                 const int cidx = tid + i * kPipeThreads;
-                const float4 z4 = MapIO<TZ>::smem(sz, cidx);
                 float4 g4;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const float zk = comp(z4, kk);
                     float g;
                     if (METHOD == PWR_METHOD_SOFTMAX) {
-                        const float gy = comp(pv[i], kk) * (comp(gv[i], kk) - s1);
-                        sw[0] = fmaf(gy, zk, sw[0]);
-                        g = wj * gy;
+                        g = wj * (comp(pv[i], kk) * (comp(gv[i], kk) - s1));       // w * dL/d(w z)
                     } else if (METHOD == PWR_METHOD_SUM) {
-                        g = zk > 0.f ? (comp(gv[i], kk) - s1) * st.y : 0.f;
+                        // p > eps/S  <=>  z > 0: through relu and 1/sum
+                        g = comp(MapIO<TZ>::smem(sz, cidx), kk) > 0.f ? (comp(gv[i], kk) - s1) * st.y : 0.f;
                     } else {
                         g = comp(gv[i], kk);
                     }
@@ -686,18 +768,18 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
                 MapIO<TZ>::st(a.gz, static_cast<size_t>(bj) * kMap + cidx * 4, g4);
             }
         }
-        if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr) {
-            pipe_block_sum<1>(sw, scratch);
-            if (tid == 0) a.gw_partial[bj] = sw[0];
-        }
+        if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr && tid == 0)
+            a.gw_partial[bj] = acc[3] - s1 * acc[4];
         if (LOSS && a.loss_partial != nullptr && tid == 0) {
             a.loss_partial[bj * 3 + 0] = acc[1];
             a.loss_partial[bj * 3 + 1] = acc[2];
             a.loss_partial[bj * 3 + 2] = lu;
         }
+        if (tid < 32 && nxt < last) scal[(k + 1) & 1][tid] = next_word;
         // every thread is done with stage s and (if the sample changes) with the old L/m buffer
         __syncthreads();
         b_cur = b_next;
+        j_cur = j_next;
         lm_cur = lm_next;
     }
 }
@@ -829,17 +911,23 @@ static bool bad_dtype(int method, int map_dtype) {
     if (map_dtype != PWR_DTYPE_F32 && map_dtype != PWR_DTYPE_F16 && map_dtype != PWR_DTYPE_BF16) return true;
     return method == PWR_METHOD_GIVEN && map_dtype != PWR_DTYPE_F32;
 }
+#define PWR_DISPATCH_LOSS(LAUNCH, M, TZ)                                                              \
+    do {                                                                                              \
+        if (loss_mode == LOSS_NONE) LAUNCH(M, LOSS_NONE, TZ);                                         \
+        else if (loss_mode == LOSS_DENSE) LAUNCH(M, LOSS_DENSE, TZ);                                  \
+        else LAUNCH(M, LOSS_SPARSE, TZ);                                                              \
+    } while (0)
 #define PWR_DISPATCH(LAUNCH)                                                                          \
     do {                                                                                              \
-        if (method == PWR_METHOD_GIVEN)        { if (loss) LAUNCH(PWR_METHOD_GIVEN, true, float);  else LAUNCH(PWR_METHOD_GIVEN, false, float); }    \
+        if (method == PWR_METHOD_GIVEN) PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_GIVEN, float);           \
         else if (method == PWR_METHOD_SOFTMAX) {                                                      \
-            if (map_dtype == PWR_DTYPE_F32)      { if (loss) LAUNCH(PWR_METHOD_SOFTMAX, true, float);  else LAUNCH(PWR_METHOD_SOFTMAX, false, float); }  \
-            else if (map_dtype == PWR_DTYPE_F16) { if (loss) LAUNCH(PWR_METHOD_SOFTMAX, true, __half); else LAUNCH(PWR_METHOD_SOFTMAX, false, __half); } \
-            else                                 { if (loss) LAUNCH(PWR_METHOD_SOFTMAX, true, __nv_bfloat16); else LAUNCH(PWR_METHOD_SOFTMAX, false, __nv_bfloat16); } \
+            if (map_dtype == PWR_DTYPE_F32)      PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_SOFTMAX, float);          \
+            else if (map_dtype == PWR_DTYPE_F16) PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_SOFTMAX, __half);         \
+            else                                 PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_SOFTMAX, __nv_bfloat16);  \
         } else {                                                                                      \
-            if (map_dtype == PWR_DTYPE_F32)      { if (loss) LAUNCH(PWR_METHOD_SUM, true, float);  else LAUNCH(PWR_METHOD_SUM, false, float); }  \
-            else if (map_dtype == PWR_DTYPE_F16) { if (loss) LAUNCH(PWR_METHOD_SUM, true, __half); else LAUNCH(PWR_METHOD_SUM, false, __half); } \
-            else                                 { if (loss) LAUNCH(PWR_METHOD_SUM, true, __nv_bfloat16); else LAUNCH(PWR_METHOD_SUM, false, __nv_bfloat16); } \
+            if (map_dtype == PWR_DTYPE_F32)      PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_SUM, float);              \
+            else if (map_dtype == PWR_DTYPE_F16) PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_SUM, __half);             \
+            else                                 PWR_DISPATCH_LOSS(LAUNCH, PWR_METHOD_SUM, __nv_bfloat16);      \
         }                                                                                             \
     } while (0)
 
@@ -861,6 +949,7 @@ extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, con
         else PWR_REQUIRE_PTR(taps);
         if (uvd_gt == nullptr || D == nullptr) return PWR_E_NULL;
     }
+    const int loss_mode = !loss ? LOSS_NONE : (taps != nullptr ? LOSS_SPARSE : LOSS_DENSE);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define PWR_LAUNCH_FWD(M, LS, TZ)                                                                            \
     decoder_fwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, taps, H, \
@@ -894,6 +983,7 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
     const bool map_terms = loss && (loss_partial != nullptr || coef.ch != 0.f || coef.cd != 0.f);
     const bool need_targets = map_terms && taps == nullptr;
     if (!map_terms) taps = nullptr;
+    const int loss_mode = !loss ? LOSS_NONE : (taps != nullptr ? LOSS_SPARSE : LOSS_DENSE);
     const bool need_up = gH_up != nullptr || gD_up != nullptr;
     if (D != nullptr && !(need_targets && need_up) && !force_direct_bwd()) {
         PipeArgs a;

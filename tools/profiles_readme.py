@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Regenerate profiles/README.md from profiles/{tag}_launches.csv, {tag}_bench_n1.json and traffic.json."""
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+
+rows = list(csv.reader(open(os.path.join(P, "%s_launches.csv" % tag))))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+hdr, data = rows[hi], rows[hi + 1:]
+ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+seq = [(r[ki], float(r[vi].replace(",", "")) / (1e3 if r[ui] == "ns" else 1)) for r in data if len(r) > vi]
+idx = [i for i, (n, _) in enumerate(seq) if "sfr_prep" in n]
+step = seq[idx[-1]:]
+tot = sum(t for _, t in step)
+agg = {}
+for n, t in step:
+    k = n.split("(")[0].replace("void ", "")[:70]
+    agg[k] = agg.get(k, 0) + t
+bench = json.load(open(os.path.join(P, "%s_bench_n1.json" % tag)))
+ev, evtot = bench["kernels"], bench["ms_per_step"]
+
+
+def entry(k):
+    if "sfr_build_kernel" in k or "sfr_prep" in k:
+        return "pwr_sfr_build"
+    if "decoder_fwd_kernel" in k:
+        return "pwr_decoder_fwd"
+    if "decoder_bwd" in k:
+        return "pwr_decoder_bwd_loss"
+    return None
+
+
+L = ["# profiles/ — round 1\n",
+     "All captured under `gpurun` on one B200 (sm_100a), `bench.py` at its default workload (NYU shape, B = 4096, "
+     "J = 14, float32 frames, dense targets).\n",
+     "| file | what |", "|---|---|",
+     "| `%s_bench_n1.json`, `%s_bench_n2.json`, `%s_bench_n8.json` | the JSON line of `bench.py` at N = 1 / 2 / 8 (torchrun) |" % (tag, tag, tag),
+     "| `%s_bench_reference.json` | the JSON line of `bench.py --impl reference` (CPU oracle port) on the same box |" % tag,
+     "| `%s_launches.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `bench.py --steps 3 --warmup 3` (includes the synthetic-input generation kernels before the first step) |" % tag,
+     "| `%s_ncu_summary.md` | key metrics of one `ncu --set full` capture of the hot kernels (`tools/ncu_summary.py`) |" % tag,
+     "| `traffic.json` | DRAM bytes per launch from that capture (read by `bench.py` -> `roofline.traffic`) |",
+     "| `%s_sanitizer_*.log` | `compute-sanitizer` memcheck / racecheck over the GPU parity tests: 0 errors, 0 hazards |" % tag,
+     "",
+     "## Share of the step: ncu launch list (cold, serialised) vs CUDA events inside bench.py\n",
+     "| kernel | ncu us | ncu share | bench events ms (entry point) | bench share |", "|---|---|---|---|---|"]
+seen = set()
+for k, t in sorted(agg.items(), key=lambda kv: -kv[1]):
+    e = entry(k)
+    show = e and e not in seen and "prep" not in k
+    if show:
+        seen.add(e)
+    L.append("| `%s` | %.1f | %.1f %% | %s | %s |" % (k, t, 100 * t / tot, ("%.3f" % ev[e]["avg_ms"]) if show else "-",
+                                                 ("%.1f %%" % (100 * ev[e]["avg_ms"] / evtot)) if show else "-"))
+L.append("| **step total** | %.1f | 100 %% | %.3f (`ms_per_step`) | |" % (tot, evtot))
+hot = sum(t for k, t in agg.items() if entry(k))
+L += ["",
+      "The hand-written hot kernels account for %.1f %% of the ncu step and %.1f %% of the event-timed step "
+      "(`pwr_sfr_build` is two launches: `sfr_prep_kernel` + `sfr_build_kernel`); the rest is `pwr_stage_loss`, "
+      "`pwr_reduce_partials`, two early-exit `pwr_scale_inplace` launches and a few tiny ATen kernels from autograd."
+      % (100 * hot / tot, 100 * sum(ev[e]["avg_ms"] for e in ev) / evtot),
+      "",
+      "## Roofline (measured peak %.1f GB/s, MEASURED_PEAKS.json)\n" % bench["roofline"]["peak"],
+      "| entry point | algorithmic bytes / launch | event-timed ms | achieved GB/s | frac of measured peak | DRAM traffic / algorithmic (ncu) |",
+      "|---|---|---|---|---|---|"]
+tr = json.load(open(os.path.join(P, "traffic.json")))
+for e in ("pwr_sfr_build", "pwr_decoder_fwd", "pwr_decoder_bwd_loss"):
+    L.append("| `%s` | %d | %.3f | %.0f | %.3f | %.2f |" % (e, ev[e]["algorithmic_bytes"], ev[e]["avg_ms"], ev[e]["achieved_gbs"],
+                                                        ev[e]["frac"], tr[e]["traffic_over_algorithmic"]))
+L += ["",
+      "Whole step: %d B/sample x 4096 / %.3f ms = %.0f GB/s = %.3f of measured peak (`step_roofline_frac`), %.2f M samples/s."
+      % (bench["config"]["algorithmic_bytes_per_sample"], evtot, bench["config"]["algorithmic_bytes_per_sample"] * 4096 / evtot / 1e6,
+         bench["step_roofline_frac"], bench["value"] / 1e6),
+      "The measured peak is a torch device-to-device copy; the pipelined backward (1-D bulk TMA into a shared-memory ring, "
+      "one persistent CTA per SM) moves its bytes slightly faster than that copy.",
+      "`pwr_sfr_build` moves %.2fx its algorithmic bytes: the formula counts a 128x128 crop (0.27 GB) where the "
+      "non-antialiased bilinear taps of a 176-352 px box touch every source pixel (1.0 GB); writes match the formula. "
+      "Against its real DRAM traffic it runs at %.0f GB/s." % (tr["pwr_sfr_build"]["traffic_over_algorithmic"],
+                                                              tr["pwr_sfr_build"]["dram_bytes_per_launch"] / ev["pwr_sfr_build"]["avg_ms"] / 1e6),
+      "",
+      "## Other numbers in `%s_bench_n1.json`\n" % tag,
+      "* `e2e` (float32 frames + logits from pinned host memory every step): %.0f samples/s, %.2f GB H2D per step (PCIe-bound); "
+      "`e2e_raw_frames` (raw uint16 sensor frames, PNG decode + hand rectangle inside the kernel): %.0f samples/s."
+      % (bench["e2e"]["value"], bench["e2e"]["h2d_bytes_per_step"] / 1e9, bench["e2e_raw_frames"]["value"]),
+      "* `cpu_baseline` (oracle port, %d host cores): %.0f samples/s." % (bench["cpu_baseline"]["cores"], bench["cpu_baseline"]["value"]),
+      "* `gpu_eager_decoder` (the reference's decoder + loss lines as eager PyTorch on the same GPU): %.2f ms vs %.2f ms fused = %.1fx."
+      % (bench["gpu_eager_decoder"]["ms"], bench["gpu_eager_decoder"]["fused_ms"], bench["gpu_eager_decoder"]["speedup"]),
+      "* `sparse_targets` (compact 64-byte targets evaluated inside the loss kernel, reported separately as SURVEY 8d asks): "
+      "%.2f M samples/s, %d B/sample." % (bench["sparse_targets"]["value"] / 1e6, bench["sparse_targets"]["algorithmic_bytes_per_sample"])]
+for n in (2, 8):
+    f = os.path.join(P, "%s_bench_n%d.json" % (tag, n))
+    if os.path.isfile(f):
+        b = json.load(open(f))
+        L.append("* N = %d (weak scaling, torchrun + NCCL): %.2f M samples/s, %.3f ms/step -> %.1f %% of N x the N = 1 value."
+                 % (n, b["value"] / 1e6, b["ms_per_step"], 100 * b["value"] / (n * bench["value"])))
+open(os.path.join(P, "README.md"), "w").write("\n".join(L) + "\n")
+print("\n".join(L[12:]))

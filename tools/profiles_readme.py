@@ -39,7 +39,7 @@ L = ["# profiles/ — round 1\n",
      "All captured under `gpurun` on one B200 (sm_100a), `bench.py` at its default workload (NYU shape, B = 4096, "
      "J = 14, float32 frames, dense targets).\n",
      "| file | what |", "|---|---|",
-     "| `%s_bench_n1.json`, `%s_bench_n2.json`, `%s_bench_n8.json` | the JSON line of `bench.py` at N = 1 / 2 / 8 (torchrun) |" % (tag, tag, tag),
+     "| `%s_bench_n1.json`, `%s_bench_n2.json`, `%s_bench_n4.json`, `%s_bench_n8.json` | the JSON line of `bench.py` at N = 1 / 2 / 4 / 8 (torchrun) |" % (tag, tag, tag, tag),
      "| `%s_bench_reference.json` | the JSON line of `bench.py --impl reference` (CPU oracle port) on the same box |" % tag,
      "| `%s_launches.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `bench.py --steps 3 --warmup 3` (includes the synthetic-input generation kernels before the first step) |" % tag,
      "| `%s_ncu_summary.md` | key metrics of one `ncu --set full` capture of the hot kernels (`tools/ncu_summary.py`) |" % tag,
@@ -91,7 +91,7 @@ L += ["",
       % (bench["gpu_eager_decoder"]["ms"], bench["gpu_eager_decoder"]["fused_ms"], bench["gpu_eager_decoder"]["speedup"]),
       "* `sparse_targets` (compact 64-byte targets evaluated inside the loss kernel, reported separately as SURVEY 8d asks): "
       "%.2f M samples/s, %d B/sample." % (bench["sparse_targets"]["value"] / 1e6, bench["sparse_targets"]["algorithmic_bytes_per_sample"])]
-for n in (2, 8):
+for n in (2, 4, 8):
     f = os.path.join(P, "%s_bench_n%d.json" % (tag, n))
     if os.path.isfile(f):
         b = json.load(open(f))

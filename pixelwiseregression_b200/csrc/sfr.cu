@@ -27,6 +27,11 @@
 //                     NaN; datasets.py:385-390) is one packed atomicAdd per
 //                     CTA on the sample's counter; the CTA that arrives last
 //                     writes `valid`.
+//   sfr_aug_kernel    the augmented branch (datasets.py:216-299): one CTA per
+//                     sample, resized crop staged in shared memory, rotation +
+//                     scale through cv2.warpAffine's fixed-point bilinear map.
+// Frames may be decoded float32 or raw PNG samples (NYU G/B, 16-bit grey)
+// decoded per tap; the hand rectangle of load_from_text tightens the tap bounds.
 //
 // Arithmetic contract (bit-level where the result is discontinuous):
 //   * crop box, int CoM, slice extents: float64 with explicit _rn intrinsics
@@ -230,7 +235,6 @@ template <typename T> struct Arith;
 template <> struct Arith<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
     static __device__ __forceinline__ float rcp(float b) { return __frcp_rn(b); }
     // a / b, correctly rounded, from rb = RN(1/b): q = RN(a*rb) is within 1 ulp, the FMA residual is
     // exact, and one correction step lands on RN(a/b) (Markstein).  |a| < cube-ish and b = cube, so no
@@ -251,7 +255,6 @@ template <> struct Arith<float> {
 template <> struct Arith<double> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
     static __device__ __forceinline__ double rcp(double b) { return b; }
     static __device__ __forceinline__ double div_by(double a, double b, double) { return __ddiv_rn(a, b); }
     static __device__ __forceinline__ double window(double v, const SampleGeom& g) {

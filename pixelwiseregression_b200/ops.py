@@ -313,7 +313,7 @@ class DecoderLossFunction(torch.autograd.Function):
         out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
         terms, total = out4[:3], out4[3]
         gw = reduce_partials(gw_partial).view_as(w) if (need_grad and w is not None) else None
-        ctx.has_w = w is not None
+        # the eager gradients live on the node until its (single) backward consumes them
         ctx.grads = (gz, gD, gw)
         outs = (total, terms, uvd) + ((H,) if store_heat else ())
         ctx.mark_non_differentiable(*outs[1:])
@@ -321,10 +321,13 @@ class DecoderLossFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, *unused):
+        if ctx.grads is None:
+            raise _lib.PwrError("fused_decoder_loss: backward through the same node twice (the eager gradients are "
+                                "rescaled in place and handed over once; retain_graph is not supported here)")
         gz, gD, gw = ctx.grads
         ctx.grads = None
         if gz is None:
-            raise _lib.PwrError("DecoderLossFunction: forward ran without gradient tracking")
+            raise _lib.PwrError("fused_decoder_loss: forward ran without gradient tracking")
         if g_total is None:
             return (None,) * 13
         scale_inplace_(gz, g_total)

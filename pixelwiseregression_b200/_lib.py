@@ -56,6 +56,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.isfile(LIB_PATH) and "PWR_LIB_PATH" not in os.environ:
+        try:                                   # a fresh checkout: compile once (needs nvcc), never fall back
+            from . import build as _build
+            _build.build()
+        except Exception as exc:
+            raise PwrError("libpwr_b200.so not found at %s and building it failed (%s): run `python -m "
+                           "pixelwiseregression_b200.build` (there is no CPU fallback)" % (LIB_PATH, exc))
     if not os.path.isfile(LIB_PATH):
         raise PwrError(
             "libpwr_b200.so not found at %s: build it with `python -m pixelwiseregression_b200.build` "

@@ -358,7 +358,7 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
                    const float* __restrict__ uvd_gt, const pwr_joint_taps* __restrict__ taps, LossCoef coef,
                    void* __restrict__ gz, void* __restrict__ gD, float* __restrict__ gw_partial,
                    float* __restrict__ loss_partial, int J) {
-    __shared__ float scratch[kWarps * 3];
+    __shared__ float scratch[kWarps * 5];
     if (LOSS && coef.scale_dev != nullptr) {
         const float up = *coef.scale_dev;
         coef.cu *= up; coef.ch *= up; coef.cd *= up;
@@ -397,13 +397,17 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         gu = fmaf(coef.cu, eu, gu); gvv = fmaf(coef.cu, ev, gvv); gd = fmaf(coef.cu, ed, gd);
         lu = eu * eu + ev * ev + ed * ed;
     }
-    const float gu63 = gu / 63.f, gv63 = gvv / 63.f;
-    const float gdd = depth ? gd / st.z : 0.f;        // g_d / den
-    const float dcoord = st.w;
+    const float gu63 = gu * (1.f / 63.f), gv63 = gvv * (1.f / 63.f);
+    const float gdd = depth ? __fdividef(gd, st.z) : 0.f;        // g_d / den
+    const float dcoord = st.w, zref = st.x;
     const PixelCoords pc = pixel_coords();
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float acc[3] = {0.f, 0.f, 0.f};      // sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2
+    // acc: sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2, T1 = sum p*gp*(z-zref), T2 = sum p*(z-zref):
+    // dL/dw = sum_px p*(gp - S1)*z = T1 - S1*T2 (sum_px p*(gp - S1) = 0 frees the reference point),
+    // so one block reduction serves everything and z is dead after this loop
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned int zpos = 0;               // PWR_METHOD_SUM: bit (4*i+k) = z > 0
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
         const size_t o = off + i * (kThreads * 4);
@@ -419,7 +423,8 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
         float4 gd4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float p = heat_raw<METHOD>(comp(zv[i], k), c, shift) * st.y;
+            const float zk = comp(zv[i], k);
+            const float p = heat_raw<METHOD>(zk, c, shift) * st.y;
             const float mk = comp(m4, k), dk = comp(d4, k);
             const float rec = mk * (dk + comp(l4, k));
             float gp = fmaf(gu63, pc.xs + static_cast<float>(k), gyrow);
@@ -435,31 +440,33 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
             }
             gp += comp(uh, k);
             gdk += comp(ud, k);
-            acc[0] = fmaf(gp, p, acc[0]);
+            const float pg = gp * p;
+            acc[0] += pg;
+            if (METHOD == PWR_METHOD_SOFTMAX) {
+                acc[3] = fmaf(pg, zk - zref, acc[3]);
+                acc[4] = fmaf(p, zk - zref, acc[4]);
+            }
+            if (METHOD == PWR_METHOD_SUM && zk > 0.f) zpos |= 1u << (4 * i + k);
             set_comp(pv[i], k, p);
             set_comp(gv[i], k, gp);
             set_comp(gd4, k, gdk);
         }
         if (gD != nullptr) MapIO<TZ>::st(gD, o, gd4);
     }
-    if (METHOD != PWR_METHOD_GIVEN || LOSS) block_sum<3>(acc, scratch);
+    if (METHOD != PWR_METHOD_GIVEN || LOSS) block_sum<5>(acc, scratch);
 
     const float s1 = acc[0];
-    float s2[1] = {0.f};
     if (gz != nullptr) {
 #pragma unroll
         for (int i = 0; i < kVec; ++i) {
             float4 g4;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float zk = comp(zv[i], k);
                 float g;
                 if (METHOD == PWR_METHOD_SOFTMAX) {
-                    const float gy = comp(pv[i], k) * (comp(gv[i], k) - s1);   // dL/d(w z)
-                    s2[0] = fmaf(gy, zk, s2[0]);
-                    g = wj * gy;
+                    g = wj * (comp(pv[i], k) * (comp(gv[i], k) - s1));                 // w * dL/d(w z)
                 } else if (METHOD == PWR_METHOD_SUM) {
-                    g = zk > 0.f ? (comp(gv[i], k) - s1) * st.y : 0.f;         // through relu and 1/sum
+                    g = ((zpos >> (4 * i + k)) & 1u) ? (comp(gv[i], k) - s1) * st.y : 0.f;   // through relu and 1/sum
                 } else {
                     g = comp(gv[i], k);                                        // heat map given: dL/dp itself
                 }
@@ -468,10 +475,8 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
             MapIO<TZ>::st(gz, off + i * (kThreads * 4), g4);
         }
     }
-    if (METHOD == PWR_METHOD_SOFTMAX && gw_partial != nullptr) {
-        block_sum<1>(s2, scratch);
-        if (threadIdx.x == 0) gw_partial[bj] = s2[0];
-    }
+    if (METHOD == PWR_METHOD_SOFTMAX && gw_partial != nullptr && threadIdx.x == 0)
+        gw_partial[bj] = acc[3] - s1 * acc[4];
     if (LOSS && loss_partial != nullptr && threadIdx.x == 0) {
         loss_partial[bj * 3 + 0] = acc[1];
         loss_partial[bj * 3 + 1] = acc[2];

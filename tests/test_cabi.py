@@ -73,5 +73,6 @@ def test_argument_errors_without_a_gpu(lib):
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setenv("PWR_LIB_PATH", str(tmp_path / "nope.so"))      # an explicit path is never auto-built
     with pytest.raises(_lib.PwrError, match="no CPU fallback"):
         _lib.load()

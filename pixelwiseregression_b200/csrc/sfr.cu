@@ -45,7 +45,10 @@
 
 namespace pwr {
 
-constexpr int kBands = 4;                       // CTAs per sample
+#ifndef PWR_SFR_BANDS
+#define PWR_SFR_BANDS 8
+#endif
+constexpr int kBands = PWR_SFR_BANDS;           // CTAs per sample
 constexpr int kBandRows = kLabel / kBands;      // label rows per CTA
 constexpr int kLabelIters = kBandRows * kLabel / kThreads;
 

@@ -503,7 +503,10 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
 // host picks: (heat_gt, dmap_gt) for the fused loss, or (gH_up, gD_up) for
 // dense upstream gradients.  Configurations that need both pairs at once go
 // through the direct-load kernel.
-constexpr int kPipeThreads = 512;
+#ifndef PWR_PIPE_THREADS
+#define PWR_PIPE_THREADS 512
+#endif
+constexpr int kPipeThreads = PWR_PIPE_THREADS;
 constexpr int kPipeWarps = kPipeThreads / 32;
 constexpr int kPipeVec = kMap / 4 / kPipeThreads;     // float4 chunks per thread per map = 2
 constexpr int kPipeStages = 2;
@@ -541,7 +544,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // items away and every item ends with a __syncthreads.
 template <int N>
 __device__ __forceinline__ void pipe_block_sum(float (&v)[N], float* scratch) {
-    static_assert(kPipeWarps == 16, "second level reduces 16 per-warp partials with a 4-step shuffle tree");
+    static_assert(kPipeWarps == 8 || kPipeWarps == 16 || kPipeWarps == 32, "second level is a shuffle tree over the warps");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
@@ -648,7 +651,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
     __syncthreads();
 
     const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
-    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + 32*i
+    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + (kPipeThreads/16)*i
 
     int k = 0;
     for (long long it = first; it < last; ++it, ++k) {
@@ -716,7 +719,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
             const float4 u2 = tg ? zero4 : q2, u3 = tg ? zero4 : q3;    // upstream gradients
             if (sparse) sparse_lookup(tp, fp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
             const bool have_h = sparse || (tg && has2), have_d = sparse || (tg && has3);
-            const float gyrow = gv63 * (ys0 + 32.f * i);
+            const float gyrow = gv63 * (ys0 + static_cast<float>(kPipeThreads / 16) * i);
             float4 gd4;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {

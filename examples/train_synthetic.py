@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--level", type=int, default=4)
     ap.add_argument("--stages", type=int, default=2)
     ap.add_argument("--alpha", type=float, default=1.0)
+    ap.add_argument("--json", default="", help="also write the result as one JSON line to this file (rank 0)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -136,6 +137,19 @@ def main():
         print("decoder=%s shape=%s gpus=%d batch/gpu=%d: %.2f ms/step, %.0f samples/s, loss %.5f, peak mem %.1f GB" % (
             args.decoder, shape.name, world, args.batch, ms.item(), args.batch * world / ms.item() * 1e3, loss.item(),
             torch.cuda.max_memory_allocated() / 1e9))
+        if args.json:
+            import json
+            with open(args.json, "w") as f:
+                f.write(json.dumps({
+                    "metric": "end-to-end training samples/s", "value": args.batch * world / ms.item() * 1e3,
+                    "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": ms.item(), "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": "configs[2]: %s-shape end-to-end training step (on-GPU SFR build, cuDNN "
+                                           "hourglass backbone, fused decoder + loss, AdamW), batch %d/GPU, DDP over NCCL"
+                                           % (shape.name, args.batch),
+                               "decoder": args.decoder, "features": args.features, "stages": args.stages,
+                               "level": args.level, "joints": shape.joints},
+                    "loss": loss.item(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}) + "\n")
     if world > 1:
         dist.destroy_process_group()
 

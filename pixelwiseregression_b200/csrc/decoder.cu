@@ -564,6 +564,222 @@ __device__ __forceinline__ void pipe_block_sum(float (&v)[N], float* scratch) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// forward, persistent + TMA-pipelined variant (no fused loss: inference and the plain training forward)
+// ---------------------------------------------------------------------------
+// The one-CTA-per-(b,j) forward above is a chain load -> extremum -> sums -> store with three CTAs
+// per SM; when the heat maps are not stored (inference, last stage) nothing overlaps the load
+// latency and it reaches 79 % of the copy peak (ncu r1, HAND17 B=4096).  Here a few persistent CTAs
+// per SM each walk a contiguous range of items; the z / D maps of a CTA's next item(s) are always in
+// flight (ring of 32 KB stages filled by 1-D bulk TMA copies), the CTAs of an SM interleave their
+// reduction phases, and the five block sums cost 8 shuffles per warp instead of 25 (a forward
+// item moves only 32 KB, so the shuffle pipe - one warp instruction per clock per SM - is a
+// first-order cost: a lock-step 512-thread CTA with tree reductions was measured 40 % SLOWER than
+// the direct kernel).  L and m stay in registers across the J consecutive items of a sample (with
+// per-item cached loads instead the L1 thrashed - 0.5 % hit rate - and 30 % of the stall samples
+// sat on their first use).  Measured at HAND17 B=4096 without the heat-map store: direct 0.576 ms,
+// this kernel 0.452 ms (256 threads, 2 stages, 3 CTAs/SM) / 0.488 (3 stages, 2 CTAs/SM) / 0.528
+// (128 threads, 1 stage, 6 CTAs/SM, L/m not register-resident).
+#ifndef PWR_FWD_PIPE_THREADS
+#define PWR_FWD_PIPE_THREADS 256
+#endif
+#ifndef PWR_FWD_PIPE_STAGES
+#define PWR_FWD_PIPE_STAGES 2
+#endif
+constexpr int kFwdThreads = PWR_FWD_PIPE_THREADS;
+constexpr int kFwdWarps = kFwdThreads / 32;
+constexpr int kFwdVec = kMap / 4 / kFwdThreads;       // float4 chunks per thread per map
+constexpr int kFwdStages = PWR_FWD_PIPE_STAGES;
+constexpr int kFwdSmemBytes = kFwdStages * 2 * kSlotBytes + 64;
+constexpr int kFwdCtasPerSm = (227 * 1024 / (kFwdSmemBytes + 1024)) < (2048 / kFwdThreads)
+                                  ? (227 * 1024 / (kFwdSmemBytes + 1024)) : (2048 / kFwdThreads);
+static_assert(kFwdWarps == 4 || kFwdWarps == 8 || kFwdWarps == 16, "second level reads whole float4s of partials");
+
+// Warp totals of five values in 8 shuffles: at every butterfly step a lane keeps only the values its
+// half of the pair is responsible for, so the number of live values halves as the partner distance
+// does.  Totals end up in lane 0 (v0), 4 (v1), 8 (v2), 16 (v3), 20 (v4); fixed order => deterministic.
+__device__ __forceinline__ float warp_sum5_scattered(const float (&v)[5]) {
+    const int lane = threadIdx.x & 31;
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+    // xor 16: lower half keeps v0 v1 v2, upper half keeps v3 v4
+    float r = __shfl_xor_sync(0xffffffffu, b16 ? v[0] : v[3], 16);
+    const float x0 = (b16 ? v[3] : v[0]) + r;
+    r = __shfl_xor_sync(0xffffffffu, b16 ? v[1] : v[4], 16);
+    const float x1 = (b16 ? v[4] : v[1]) + r;
+    r = __shfl_xor_sync(0xffffffffu, b16 ? v[2] : 0.f, 16);
+    const float x2 = b16 ? 0.f : v[2] + r;
+    // xor 8: bit-3-clear lanes keep x0 x1, bit-3-set lanes keep x2
+    r = __shfl_xor_sync(0xffffffffu, b8 ? x0 : x2, 8);
+    const float p = (b8 ? x2 : x0) + r;
+    r = __shfl_xor_sync(0xffffffffu, b8 ? x1 : 0.f, 8);
+    const float q = x1 + r;                                   // meaningful on bit-3-clear lanes only
+    // xor 4: bit-3-clear lanes split (p | q); bit-3-set lanes keep reducing p
+    r = __shfl_xor_sync(0xffffffffu, b8 ? p : (b4 ? p : q), 4);
+    float wv = (b8 ? p : (b4 ? q : p)) + r;
+    wv += __shfl_xor_sync(0xffffffffu, wv, 2);
+    wv += __shfl_xor_sync(0xffffffffu, wv, 1);
+    return wv;
+}
+// scratch layout [5][kFwdWarps]; lanes 0, 4, 8, 16, 20 hold value 0..4
+__device__ __forceinline__ void store_scattered5(float wv, float* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int idx = -1;
+    if (lane == 0) idx = 0; else if (lane == 4) idx = 1; else if (lane == 8) idx = 2;
+    else if (lane == 16) idx = 3; else if (lane == 20) idx = 4;
+    if (idx >= 0) scratch[idx * kFwdWarps + warp] = wv;
+}
+__device__ __forceinline__ float sum_partials(const float* row) {      // kFwdWarps floats, fixed order
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFwdWarps / 4; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(row)[i];
+        s += (t.x + t.y) + (t.z + t.w);
+    }
+    return s;
+}
+
+struct FwdPipeArgs {
+    const void* z; const float* w; const void* D; const float* L; const float* m;
+    float* H; float* uvd; float* stats;
+    int J; int items;
+};
+
+template <int METHOD, typename TZ>
+__global__ void __launch_bounds__(kFwdThreads, kFwdCtasPerSm)
+decoder_fwd_pipe_kernel(FwdPipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_base = reinterpret_cast<float*>(smem_raw);                               // [stages][2][4096]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + kFwdStages * 2 * kMap);     // [stages]
+    __shared__ __align__(16) float scr_e[2][kFwdWarps];       // double-buffered: one barrier per reduction
+    __shared__ __align__(16) float scr_s[2][5 * kFwdWarps];
+
+    const int tid = threadIdx.x;
+    const long long first = static_cast<long long>(a.items) * blockIdx.x / gridDim.x;
+    const long long last = static_cast<long long>(a.items) * (blockIdx.x + 1) / gridDim.x;
+    if (first >= last) return;
+    if (tid == 0) {
+        for (int s = 0; s < kFwdStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr uint32_t kZBytes = kMap * sizeof(TZ);
+    // producer (thread 0): stream item `it` into the stage of its index
+    auto issue = [&](long long it, int kk) {
+        float* st = stage_base + (kk % kFwdStages) * 2 * kMap;
+        uint64_t* bar = &full[kk % kFwdStages];
+        const size_t off = static_cast<size_t>(it) * kMap;
+        mbar_expect_tx(bar, 2 * kZBytes);
+        bulk_g2s(st, static_cast<const TZ*>(a.z) + off, kZBytes, bar);
+        bulk_g2s(st + kMap, static_cast<const TZ*>(a.D) + off, kZBytes, bar);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < kFwdStages && first + i < last; ++i) issue(first + i, i);
+    }
+
+    int b_cur = static_cast<int>(first / a.J);
+    int j_cur = static_cast<int>(first - static_cast<long long>(b_cur) * a.J);
+    const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
+    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + (kFwdThreads/16)*i
+    constexpr bool kPreloadLM = kFwdVec <= 4;
+    float4 lv[kPreloadLM ? kFwdVec : 1], mv[kPreloadLM ? kFwdVec : 1];
+    int b_loaded = -1;
+    float c_next = (METHOD == PWR_METHOD_SOFTMAX) ? a.w[j_cur] * kLog2e : 0.f;     // fetched one item ahead
+    int k = 0;
+    for (long long it = first; it < last; ++it, ++k) {
+        const int s = k % kFwdStages;
+        const uint32_t parity = (k / kFwdStages) & 1;
+        const float* sz = stage_base + s * 2 * kMap;
+        const float* sD = sz + kMap;
+        const float c = c_next;
+        // label and mask of the sample stay in registers across its J items (with 32 pixels per
+        // thread the 64 registers are not there: cached loads inside pass 2 instead)
+        const size_t offb = static_cast<size_t>(b_cur) * kMap + tid * 4;
+        if (kPreloadLM && b_cur != b_loaded) {
+            b_loaded = b_cur;
+#pragma unroll
+            for (int i = 0; i < (kPreloadLM ? kFwdVec : 1); ++i) mv[i] = ld_keep(a.m + offb + i * (kFwdThreads * 4));
+#pragma unroll
+            for (int i = 0; i < (kPreloadLM ? kFwdVec : 1); ++i) lv[i] = ld_keep(a.L + offb + i * (kFwdThreads * 4));
+        }
+
+        mbar_wait(&full[s], parity);
+
+        float4 zv[kFwdVec];
+#pragma unroll
+        for (int i = 0; i < kFwdVec; ++i) zv[i] = MapIO<TZ>::smem(sz, tid + i * kFwdThreads);
+        float shift = 0.f, zext = 0.f;
+        if (METHOD == PWR_METHOD_SOFTMAX) {
+            const bool want_max = c >= 0.f;
+            float e = want_max ? -INFINITY : INFINITY;
+#pragma unroll
+            for (int i = 0; i < kFwdVec; ++i) {
+                if (want_max) e = fmaxf(fmaxf(fmaxf(e, zv[i].x), fmaxf(zv[i].y, zv[i].z)), zv[i].w);
+                else          e = fminf(fminf(fminf(e, zv[i].x), fminf(zv[i].y, zv[i].z)), zv[i].w);
+            }
+            e = want_max ? warp_max(e) : warp_min(e);
+            float* se = scr_e[k & 1];
+            if ((tid & 31) == 0) se[tid >> 5] = e;
+            __syncthreads();
+            zext = se[0];
+#pragma unroll
+            for (int wv = 1; wv < kFwdWarps; ++wv) zext = want_max ? fmaxf(zext, se[wv]) : fminf(zext, se[wv]);
+            shift = zext * c;                      // the backward recomputes exactly this product
+        }
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum e, e*(x-32), e*(y-32), e*m, e*m*m*(D+L)
+#pragma unroll
+        for (int i = 0; i < kFwdVec; ++i) {
+            const float4 d4 = MapIO<TZ>::smem(sD, tid + i * kFwdThreads);
+            const float4 m4 = kPreloadLM ? mv[kPreloadLM ? i : 0] : ld_keep(a.m + offb + i * (kFwdThreads * 4));
+            const float4 l4 = kPreloadLM ? lv[kPreloadLM ? i : 0] : ld_keep(a.L + offb + i * (kFwdThreads * 4));
+            const float ys = ys0 + static_cast<float>(kFwdThreads / 16) * i;
+            float rowsum = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float e = heat_raw<METHOD>(comp(zv[i], kk), c, shift);
+                set_comp(zv[i], kk, e);
+                const float mk = comp(m4, kk);
+                const float em = e * mk;
+                rowsum += e;
+                acc[1] = fmaf(e, xs + static_cast<float>(kk), acc[1]);
+                acc[3] += em;
+                acc[4] = fmaf(em, mk * (comp(d4, kk) + comp(l4, kk)), acc[4]);
+            }
+            acc[0] += rowsum;
+            acc[2] = fmaf(rowsum, ys, acc[2]);
+        }
+        float* ss = scr_s[k & 1];
+        store_scattered5(warp_sum5_scattered(acc), ss);
+        __syncthreads();
+        // every thread is past its shared-memory reads of this item: its stage can take item k + stages
+        if (tid == 0 && it + kFwdStages < last) issue(it + kFwdStages, k + kFwdStages);
+        if (++j_cur == a.J) { j_cur = 0; ++b_cur; }
+        if (METHOD == PWR_METHOD_SOFTMAX && it + 1 < last) c_next = a.w[j_cur] * kLog2e;
+
+        const float inv_s = (METHOD == PWR_METHOD_GIVEN) ? 1.f : 1.f / sum_partials(ss);
+        if (a.H != nullptr) {
+            float* Hp = a.H + static_cast<size_t>(it) * kMap;
+#pragma unroll
+            for (int i = 0; i < kFwdVec; ++i) {
+                float4 h = zv[i];
+                h.x *= inv_s; h.y *= inv_s; h.z *= inv_s; h.w *= inv_s;
+                st_stream(Hp + (tid + i * kFwdThreads) * 4, h);
+            }
+        }
+        if (tid == 0) {
+            const float su = sum_partials(ss + kFwdWarps), sv = sum_partials(ss + 2 * kFwdWarps);
+            const float sm = sum_partials(ss + 3 * kFwdWarps), sd = sum_partials(ss + 4 * kFwdWarps);
+            const float den = fmaf(sm, inv_s, kEps);
+            const float d = (sd * inv_s) / den;
+            float* o = a.uvd + static_cast<size_t>(it) * 3;
+            o[0] = su * inv_s / 63.f;
+            o[1] = sv * inv_s / 63.f;
+            o[2] = d;
+            if (a.stats != nullptr) reinterpret_cast<float4*>(a.stats)[it] = make_float4(zext, inv_s, den, d);
+        }
+    }
+}
+
 struct PipeArgs {
     const void* z; const float* w; const void* D; const float* L; const float* m;
     const float* stats; const float* uvd; const float* g_uvd;
@@ -905,6 +1121,16 @@ static bool force_direct_bwd() {
     const char* e = getenv("PWR_BWD_DIRECT");
     return e != nullptr && e[0] == '1';
 }
+// PWR_FWD_DIRECT=1 forces the one-CTA-per-item forward, PWR_FWD_PIPE=1 the pipelined one also when
+// the heat maps are stored (A/B measurements, tests of both paths).
+static bool force_direct_fwd() {
+    const char* e = getenv("PWR_FWD_DIRECT");
+    return e != nullptr && e[0] == '1';
+}
+static bool force_pipe_fwd() {
+    const char* e = getenv("PWR_FWD_PIPE");
+    return e != nullptr && e[0] == '1';
+}
 static bool bad_method(int method) {
     return method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM && method != PWR_METHOD_GIVEN;
 }
@@ -959,6 +1185,35 @@ extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, con
     }
     const int loss_mode = !loss ? LOSS_NONE : (taps != nullptr ? LOSS_SPARSE : LOSS_DENSE);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // No fused loss and the depth branch present -> persistent TMA-pipelined forward.
+    // Measured (B200, f32): without the heat-map store 0.452 vs 0.576 ms (HAND17 B=4096, 6.5 TB/s); with it
+    // the direct kernel below is already at 98 % of the copy peak and stays the default.
+    if (loss_mode == LOSS_NONE && D != nullptr && (H == nullptr || force_pipe_fwd()) && !force_direct_fwd()) {
+        FwdPipeArgs a;
+        a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.H = H; a.uvd = uvd; a.stats = stats; a.J = J; a.items = B * J;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = a.items < sms * kFwdCtasPerSm ? a.items : sms * kFwdCtasPerSm;
+#define PWR_LAUNCH_FWD_PIPE(M, TZ)                                                                            \
+    do {                                                                                                      \
+        cudaFuncSetAttribute(decoder_fwd_pipe_kernel<M, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                             kFwdSmemBytes);                                                                  \
+        decoder_fwd_pipe_kernel<M, TZ><<<grid, kFwdThreads, kFwdSmemBytes, s>>>(a);                            \
+    } while (0)
+        if (method == PWR_METHOD_GIVEN) PWR_LAUNCH_FWD_PIPE(PWR_METHOD_GIVEN, float);
+        else if (method == PWR_METHOD_SOFTMAX) {
+            if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_FWD_PIPE(PWR_METHOD_SOFTMAX, float);
+            else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_FWD_PIPE(PWR_METHOD_SOFTMAX, __half);
+            else                                 PWR_LAUNCH_FWD_PIPE(PWR_METHOD_SOFTMAX, __nv_bfloat16);
+        } else {
+            if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_FWD_PIPE(PWR_METHOD_SUM, float);
+            else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_FWD_PIPE(PWR_METHOD_SUM, __half);
+            else                                 PWR_LAUNCH_FWD_PIPE(PWR_METHOD_SUM, __nv_bfloat16);
+        }
+#undef PWR_LAUNCH_FWD_PIPE
+        return launch_status();
+    }
 #define PWR_LAUNCH_FWD(M, LS, TZ)                                                                            \
     decoder_fwd_kernel<M, LS, TZ><<<B * J, kThreads, 0, s>>>(z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, taps, H, \
                                                              uvd, stats, loss_partial, J)

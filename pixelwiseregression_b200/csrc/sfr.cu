@@ -15,7 +15,7 @@
 //                     division chains are latency-, not throughput-limited, so
 //                     they are done ONCE per sample here instead of stalling
 //                     every CTA of the main kernel.
-//   sfr_build_kernel  kBands CTAs per sample, one per horizontal band of the
+//   sfr_build_kernel  kBands (8 with dense maps, 2 without) CTAs per sample, one per horizontal band of the
 //                     label image.  Each CTA (a) streams zeros over its band
 //                     of all 2J maps with 128-bit stores while the prepared
 //                     geometry is fetched, (b) resamples its 2*R x 128 image
@@ -45,12 +45,19 @@
 
 namespace pwr {
 
+// CTAs (horizontal bands of the label image) per sample.  With dense maps a CTA's band of all 2J maps
+// is zero-filled while the taps are fetched, and 8 bands measured best (2/4/8/16: 0.60/0.59/0.54/0.55 ms
+// at B=4096 NYU); without them (test-only SFR, compact targets) nothing overlaps that prologue and
+// fewer, longer CTAs win (8/4/2: 0.289/0.258/0.250 ms HAND17 crop).
 #ifndef PWR_SFR_BANDS
 #define PWR_SFR_BANDS 8
 #endif
-constexpr int kBands = PWR_SFR_BANDS;           // CTAs per sample
-constexpr int kBandRows = kLabel / kBands;      // label rows per CTA
-constexpr int kLabelIters = kBandRows * kLabel / kThreads;
+#ifndef PWR_SFR_BANDS_LEAN
+#define PWR_SFR_BANDS_LEAN 2
+#endif
+constexpr int kBandsDense = PWR_SFR_BANDS;
+constexpr int kBandsLean = PWR_SFR_BANDS_LEAN;
+constexpr int kBandsMax = kBandsDense > kBandsLean ? kBandsDense : kBandsLean;
 
 // cv::getGaussianKernel(7, 1.5, CV_64F), OpenCV 4.13.0 (softdouble, exact bits)
 __constant__ double kGauss7[7] = {0x1.2c18a51a3e5e7p-5, 0x1.c7ce552574441p-4, 0x1.bbe4f897eb627p-3,
@@ -481,9 +488,12 @@ sfr_prep_kernel(SfrArgs a) {
 // ---------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------
-template <typename T, int FMT, bool TRAIN>
+template <typename T, int FMT, bool TRAIN, int kBands>
 __global__ void __launch_bounds__(kThreads)
 sfr_build_kernel(SfrArgs a) {
+    constexpr int kBandRows = kLabel / kBands;                    // label rows per CTA
+    constexpr int kLabelIters = kBandRows * kLabel / kThreads;
+    static_assert(kLabel % kBands == 0 && kImage + 2 * kBandRows <= kThreads, "tap tables are built by one thread each");
     __shared__ SampleGeom geom;
     __shared__ JointParam joints[TRAIN ? PWR_MAX_JOINTS : 1];
     __shared__ TapX xtap[kImage];
@@ -865,17 +875,28 @@ static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t str
     }
     sfr_prep_kernel<TRAIN, false><<<prep_grid, kPrepThreads, 0, stream>>>(a);
     if (int rc = launch_status()) return rc;
-    const unsigned grid = static_cast<unsigned>(a.B) * kBands;
-    if (frame_f64)            sfr_build_kernel<double, FMT_F32, TRAIN><<<grid, kThreads, 0, stream>>>(a);
-    else if (fmt == FMT_F32)  sfr_build_kernel<float, FMT_F32, TRAIN><<<grid, kThreads, 0, stream>>>(a);
-    else if (fmt == FMT_GB16) sfr_build_kernel<float, FMT_GB16, TRAIN><<<grid, kThreads, 0, stream>>>(a);
-    else                      sfr_build_kernel<float, FMT_U16, TRAIN><<<grid, kThreads, 0, stream>>>(a);
+#define PWR_LAUNCH_SFR(NB)                                                                                         \
+    do {                                                                                                           \
+        const unsigned grid = static_cast<unsigned>(a.B) * NB;                                                     \
+        if (frame_f64)            sfr_build_kernel<double, FMT_F32, TRAIN, NB><<<grid, kThreads, 0, stream>>>(a);  \
+        else if (fmt == FMT_F32)  sfr_build_kernel<float, FMT_F32, TRAIN, NB><<<grid, kThreads, 0, stream>>>(a);   \
+        else if (fmt == FMT_GB16) sfr_build_kernel<float, FMT_GB16, TRAIN, NB><<<grid, kThreads, 0, stream>>>(a);  \
+        else                      sfr_build_kernel<float, FMT_U16, TRAIN, NB><<<grid, kThreads, 0, stream>>>(a);   \
+    } while (0)
+    if constexpr (TRAIN) {
+        if (a.heatmaps != nullptr) {
+            PWR_LAUNCH_SFR(kBandsDense);
+            return launch_status();
+        }
+    }
+    PWR_LAUNCH_SFR(kBandsLean);
+#undef PWR_LAUNCH_SFR
     return launch_status();
 }
 
 static int check_frames(int Hf, int Wf, int B) {
     if (B < 0 || Hf < 1 || Wf < 1 || Hf > 16384 || Wf > 16384) return PWR_E_SHAPE;
-    if (static_cast<long long>(B) * kBands > 0x7fffffffLL) return PWR_E_SHAPE;
+    if (static_cast<long long>(B) * kBandsMax > 0x7fffffffLL) return PWR_E_SHAPE;
     return 0;
 }
 

@@ -389,3 +389,48 @@ def test_sparse_targets_equal_dense_targets(alpha):
                                                   alpha=alpha)
     assert_close("terms", terms_s.cpu().numpy(), terms_d.cpu().numpy(), 1e-5)
     assert abs(total_s.item() - total_d.item()) <= 1e-5 * abs(total_d.item())
+
+
+@pytest.mark.parametrize("method,dtype", [("softmax", torch.float32), ("sum", torch.float32),
+                                          ("softmax", torch.float16), ("sum", torch.bfloat16)])
+@pytest.mark.parametrize("B,J", [(1, 3), (7, 14), (41, 21), (300, 5)])
+def test_pipelined_forward_equals_direct_forward(method, dtype, B, J, monkeypatch):
+    """The persistent TMA-pipelined forward (no fused loss) and the one-CTA-per-item forward compute the
+    same heat maps bit for bit (same exp argument, same 1/sum up to the summation order) and the same
+    coordinates within float32 summation-order noise; ragged item ranges per CTA, sample boundaries
+    inside a range (L/m buffer switch) and negative temperatures included."""
+    rng = np.random.default_rng(B * 100 + J)
+    d = synth.make_decoder_inputs(B, J, seed=B + J)
+    z, D = cu(d["z"] * 3).to(dtype), cu(d["D"]).to(dtype)
+    L, m = cu(d["label"]), cu(d["mask"])
+    w = None
+    if method == "softmax":
+        wv = rng.uniform(0.5, 1.5, (J, 1)).astype(np.float32)
+        wv[::3] *= -1.0                                     # extremum = min for these joints
+        w = cu(wv)
+    for store_heat in (True, False):
+        monkeypatch.setenv("PWR_FWD_DIRECT", "1")
+        Hd, uvd_d, st_d, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
+        monkeypatch.setenv("PWR_FWD_DIRECT", "0")
+        monkeypatch.setenv("PWR_FWD_PIPE", "1")             # default: pipelined only without the heat-map store
+        Hp, uvd_p, st_p, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
+        monkeypatch.delenv("PWR_FWD_PIPE")
+        torch.cuda.synchronize()
+        assert torch.equal(st_d[..., 0], st_p[..., 0])      # extremum: exact
+        assert_close("1/sum", st_p[..., 1].cpu().numpy(), st_d[..., 1].cpu().numpy(), 1e-6)
+        assert_close("uvd", uvd_p.cpu().numpy(), uvd_d.cpu().numpy(), 2e-6)
+        assert_close("stats", st_p.cpu().numpy(), st_d.cpu().numpy(), 2e-6)
+        if store_heat:
+            assert_close("heat", Hp.cpu().numpy(), Hd.cpu().numpy(), 1e-6)
+        else:
+            assert Hp is None and Hd is None
+    # against the float64 oracle as well (the pipelined kernel is the default path)
+    t64 = lambda a: a.detach().cpu().to(torch.float64)
+    p_ref, _, uvd_ref = do.decoder_forward(t64(z), t64(w) if w is not None else None, t64(D), t64(L), t64(m), method)
+    monkeypatch.setenv("PWR_FWD_PIPE", "1")
+    Hp, uvd_p, _, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
+    monkeypatch.delenv("PWR_FWD_PIPE")
+    _, uvd_n, _, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=False, want_stats=False)   # default route
+    assert_close("heat vs oracle", Hp.cpu().numpy(), p_ref.numpy())
+    assert_close("uvd vs oracle", uvd_p.cpu().numpy(), uvd_ref.numpy())
+    assert torch.equal(uvd_n, uvd_p)

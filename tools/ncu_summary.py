@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--tag", default="r1")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--joints", type=int, default=14)
+    ap.add_argument("--print-only", action="store_true", help="exploratory capture: write nothing under profiles/")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -82,6 +83,9 @@ def main():
                               "batch": args.batch, "joints": args.joints, "report": os.path.basename(args.report)}
             out_md.append("| **DRAM traffic / algorithmic bytes** | %.3f GB / %.3f GB = %.2f |" % (
                 (rd + wr) / 1e9, alg[entry] / 1e9, (rd + wr) / alg[entry]))
+    if args.print_only:
+        print("\n".join(out_md))
+        return
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % args.tag), "w") as f:
         f.write("\n".join(out_md) + "\n")

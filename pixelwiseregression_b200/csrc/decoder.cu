@@ -1116,6 +1116,211 @@ static int check_bj(int B, int J) {
     if (static_cast<long long>(B) * J > 0x7fffffffLL / 4) return PWR_E_SHAPE;
     return 0;
 }
+// ---------------------------------------------------------------------------
+// backward, lean pipelined variant: no dense target / upstream-gradient maps
+// ---------------------------------------------------------------------------
+// With compact (pwr_joint_taps) targets, or with no map terms at all, an item moves only 32 KB in
+// and 32 KB out, and the one-CTA-per-SM kernel above stops being bandwidth-bound: its 512 threads walk
+// wait -> footprint table -> pass -> block sums -> store in lock step (1.01 ms vs 0.60 ms of traffic at
+// B=4096 J=14, ncu r1).  Same remedy as the pipelined forward: several independent CTAs per SM so the
+// phases of different items overlap, label / mask of the sample kept in registers across its J items,
+// and the five block sums in 8 shuffles per warp.
+#ifndef PWR_LEAN_THREADS
+#define PWR_LEAN_THREADS 256
+#endif
+#ifndef PWR_LEAN_STAGES
+#define PWR_LEAN_STAGES 3
+#endif
+#ifndef PWR_LEAN_CTAS
+#define PWR_LEAN_CTAS 2
+#endif
+constexpr int kLeanThreads = PWR_LEAN_THREADS;
+constexpr int kLeanWarps = kLeanThreads / 32;
+constexpr int kLeanVec = kMap / 4 / kLeanThreads;
+constexpr int kLeanStages = PWR_LEAN_STAGES;
+constexpr int kLeanCtasPerSm = PWR_LEAN_CTAS;
+constexpr int kLeanSmemBytes = kLeanStages * 2 * kSlotBytes + 64;
+static_assert(kLeanThreads == kFwdThreads, "the scattered block sums are laid out for kFwdWarps warps");
+static_assert(kLeanVec * 4 <= 32, "PWR_METHOD_SUM keeps one z > 0 bit per pixel of a thread");
+static_assert(kLeanCtasPerSm * (kLeanSmemBytes + 2048) <= 227 * 1024, "shared memory of the resident CTAs");
+
+template <int METHOD, int LOSS, typename TZ>
+__global__ void __launch_bounds__(kLeanThreads, kLeanCtasPerSm)
+decoder_bwd_lean_kernel(PipeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_base = reinterpret_cast<float*>(smem_raw);                               // [stages][2][4096]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + kLeanStages * 2 * kMap);    // [stages]
+    __shared__ __align__(16) float scr[2][5 * kLeanWarps];    // double-buffered: one barrier per reduction
+    __shared__ __align__(16) uint32_t scal[2][32];            // per-item scalars, fetched one item ahead
+    __shared__ float fp[LOSS == LOSS_SPARSE ? kFootprint : 1];
+
+    const int tid = threadIdx.x;
+    const long long first = static_cast<long long>(a.items) * blockIdx.x / gridDim.x;
+    const long long last = static_cast<long long>(a.items) * (blockIdx.x + 1) / gridDim.x;
+    if (first >= last) return;
+    if (LOSS && a.coef.scale_dev != nullptr) {
+        const float up = *a.coef.scale_dev;
+        a.coef.cu *= up; a.coef.ch *= up; a.coef.cd *= up;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kLeanStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    constexpr uint32_t kZBytes = kMap * sizeof(TZ);
+    auto issue = [&](long long it, int kk) {
+        float* st = stage_base + (kk % kLeanStages) * 2 * kMap;
+        uint64_t* bar = &full[kk % kLeanStages];
+        const size_t off = static_cast<size_t>(it) * kMap;
+        mbar_expect_tx(bar, 2 * kZBytes);
+        bulk_g2s(st, static_cast<const TZ*>(a.z) + off, kZBytes, bar);
+        bulk_g2s(st + kMap, static_cast<const TZ*>(a.D) + off, kZBytes, bar);
+    };
+    // word layout of scal: 0-3 stats, 4-6 g_uvd, 7-9 uvd, 10-12 uvd_gt, 16-31 taps
+    auto scalar_word = [&](long long it, int wd) -> uint32_t {
+        const size_t bj = static_cast<size_t>(it);
+        if (wd < 4) return __float_as_uint(a.stats[bj * 4 + wd]);
+        if (wd < 7) return a.g_uvd != nullptr ? __float_as_uint(a.g_uvd[bj * 3 + wd - 4]) : 0u;
+        if (wd < 10) return (LOSS && a.uvd != nullptr) ? __float_as_uint(a.uvd[bj * 3 + wd - 7]) : 0u;
+        if (wd < 13) return LOSS ? __float_as_uint(a.uvd_gt[bj * 3 + wd - 10]) : 0u;
+        if (wd >= 16 && LOSS == LOSS_SPARSE) return reinterpret_cast<const uint32_t*>(a.taps + bj)[wd - 16];
+        return 0u;
+    };
+    if (tid < 32) scal[0][tid] = scalar_word(first, tid);
+    __syncthreads();                                   // barriers initialised, first scalars visible
+    if (tid == 0) {
+        for (int i = 0; i < kLeanStages && first + i < last; ++i) issue(first + i, i);
+    }
+
+    int b_cur = static_cast<int>(first / a.J);
+    int j_cur = static_cast<int>(first - static_cast<long long>(b_cur) * a.J);
+    const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
+    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + (kLeanThreads/16)*i
+    float4 lv[kLeanVec], mv[kLeanVec];
+    int b_loaded = -1;
+    float w_next = (METHOD == PWR_METHOD_SOFTMAX) ? a.w[j_cur] : 1.f;
+    constexpr bool sparse = (LOSS == LOSS_SPARSE);
+    int k = 0;
+    for (long long it = first; it < last; ++it, ++k) {
+        const int s = k % kLeanStages;
+        const uint32_t parity = (k / kLeanStages) & 1;
+        const float* sz = stage_base + s * 2 * kMap;
+        const float* sD = sz + kMap;
+        const float wj = w_next;
+        if (b_cur != b_loaded) {                      // label and mask stay in registers for the J items of a sample
+            b_loaded = b_cur;
+            const size_t offb = static_cast<size_t>(b_cur) * kMap + tid * 4;
+#pragma unroll
+            for (int i = 0; i < kLeanVec; ++i) mv[i] = ld_keep(a.m + offb + i * (kLeanThreads * 4));
+#pragma unroll
+            for (int i = 0; i < kLeanVec; ++i) lv[i] = ld_keep(a.L + offb + i * (kLeanThreads * 4));
+        }
+        const uint32_t next_word = (tid < 32 && it + 1 < last) ? scalar_word(it + 1, tid) : 0u;   // lands during the pass
+
+        const float* sc = reinterpret_cast<const float*>(scal[k & 1]);
+        const float4 st = *reinterpret_cast<const float4*>(sc);           // (z extremum, 1/sum, den, d)
+        const float c = wj * kLog2e;
+        const float shift = st.x * c, zref = st.x;
+        float gu = sc[4], gvv = sc[5], gd = sc[6], lu = 0.f;
+        if (LOSS) {
+            const float eu = sc[7] - sc[10], ev = sc[8] - sc[11], ed = sc[9] - sc[12];
+            gu = fmaf(a.coef.cu, eu, gu); gvv = fmaf(a.coef.cu, ev, gvv); gd = fmaf(a.coef.cu, ed, gd);
+            lu = eu * eu + ev * ev + ed * ed;
+        }
+        const float gu63 = gu * (1.f / 63.f), gv63 = gvv * (1.f / 63.f);
+        const float gdd = __fdividef(gd, st.z);
+        const float dcoord = st.w;
+        TapsIdx tp;
+        if (sparse) {
+            // footprint table of this item (its previous readers finished before the barrier that
+            // ended the previous item's sums)
+            tp = taps_index(scal[k & 1] + 16);
+            if (tid < kFootprint) fp[tid] = footprint_entry(scal[k & 1] + 16, tid);
+            __syncthreads();
+        }
+
+        mbar_wait(&full[s], parity);
+
+        // acc: sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2, T1 = sum p*gp*(z - zref), T2 = sum p*(z - zref)
+        float4 pv[kLeanVec], gv[kLeanVec];
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        unsigned int zpos = 0;                          // PWR_METHOD_SUM: bit (4*i+kk) = z > 0
+#pragma unroll
+        for (int i = 0; i < kLeanVec; ++i) {
+            const int cidx = tid + i * kLeanThreads;
+            const float4 z4 = MapIO<TZ>::smem(sz, cidx), d4 = MapIO<TZ>::smem(sD, cidx);
+            const float4 l4 = lv[i], m4 = mv[i];
+            float4 t2 = make_float4(0.f, 0.f, 0.f, 0.f), t3 = t2;
+            if (sparse) sparse_lookup(tp, fp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
+            const float gyrow = gv63 * (ys0 + static_cast<float>(kLeanThreads / 16) * i);
+            float4 gd4;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float zk = comp(z4, kk);
+                const float p = heat_raw<METHOD>(zk, c, shift) * st.y;
+                const float mk = comp(m4, kk), dk = comp(d4, kk);
+                const float rec = mk * (dk + comp(l4, kk));
+                float gp = fmaf(gu63, xs + static_cast<float>(kk), gyrow);
+                gp = fmaf(gdd * mk, rec - dcoord, gp);
+                float gdk = gdd * p * mk * mk;
+                if (sparse) {
+                    const float eh = p - comp(t2, kk), ed = dk - comp(t3, kk);
+                    gp = fmaf(a.coef.ch, eh, gp);
+                    gdk = fmaf(a.coef.cd, ed, gdk);
+                    acc[1] = fmaf(eh, eh, acc[1]);
+                    acc[2] = fmaf(ed, ed, acc[2]);
+                }
+                const float pg = gp * p;
+                acc[0] += pg;
+                if (METHOD == PWR_METHOD_SOFTMAX) {
+                    const float dz = zk - zref;
+                    acc[3] = fmaf(pg, dz, acc[3]);
+                    acc[4] = fmaf(p, dz, acc[4]);
+                }
+                if (METHOD == PWR_METHOD_SUM && zk > 0.f) zpos |= 1u << (4 * i + kk);
+                set_comp(pv[i], kk, p);
+                set_comp(gv[i], kk, gp);
+                set_comp(gd4, kk, gdk);
+            }
+            if (a.gD != nullptr) MapIO<TZ>::st(a.gD, static_cast<size_t>(it) * kMap + cidx * 4, gd4);
+        }
+        // next item's scalars: parked before the barrier below, read after it
+        if (tid < 32 && it + 1 < last) scal[(k + 1) & 1][tid] = next_word;
+        float* ss = scr[k & 1];
+        store_scattered5(warp_sum5_scattered(acc), ss);
+        __syncthreads();
+        // every thread is past its shared-memory reads of this item: its stage can take item k + stages
+        if (tid == 0 && it + kLeanStages < last) issue(it + kLeanStages, k + kLeanStages);
+        if (++j_cur == a.J) { j_cur = 0; ++b_cur; }
+        if (METHOD == PWR_METHOD_SOFTMAX && it + 1 < last) w_next = a.w[j_cur];
+
+        const float s1 = (METHOD != PWR_METHOD_GIVEN || LOSS) ? sum_partials(ss) : 0.f;
+        if (a.gz != nullptr) {
+#pragma unroll
+            for (int i = 0; i < kLeanVec; ++i) {
+                float4 g4;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    float g;
+                    if (METHOD == PWR_METHOD_SOFTMAX) g = wj * (comp(pv[i], kk) * (comp(gv[i], kk) - s1));   // w * dL/d(w z)
+                    else if (METHOD == PWR_METHOD_SUM) g = ((zpos >> (4 * i + kk)) & 1u) ? (comp(gv[i], kk) - s1) * st.y : 0.f;
+                    else g = comp(gv[i], kk);
+                    set_comp(g4, kk, g);
+                }
+                MapIO<TZ>::st(a.gz, static_cast<size_t>(it) * kMap + (tid + i * kLeanThreads) * 4, g4);
+            }
+        }
+        if (tid == 0) {
+            if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr)
+                a.gw_partial[it] = sum_partials(ss + 3 * kLeanWarps) - s1 * sum_partials(ss + 4 * kLeanWarps);
+            if (LOSS && a.loss_partial != nullptr) {
+                a.loss_partial[it * 3 + 0] = sum_partials(ss + kLeanWarps);
+                a.loss_partial[it * 3 + 1] = sum_partials(ss + 2 * kLeanWarps);
+                a.loss_partial[it * 3 + 2] = lu;
+            }
+        }
+    }
+}
+
 // PWR_BWD_DIRECT=1 forces the direct-load backward (A/B measurements, tests of both paths).
 static bool force_direct_bwd() {
     const char* e = getenv("PWR_BWD_DIRECT");
@@ -1130,6 +1335,12 @@ static bool force_direct_fwd() {
 static bool force_pipe_fwd() {
     const char* e = getenv("PWR_FWD_PIPE");
     return e != nullptr && e[0] == '1';
+}
+// PWR_BWD_LEAN=0 sends the configurations without dense target / upstream maps through the
+// one-CTA-per-SM pipelined backward instead of the lean one.
+static bool no_lean_bwd() {
+    const char* e = getenv("PWR_BWD_LEAN");
+    return e != nullptr && e[0] == '0';
 }
 static bool bad_method(int method) {
     return method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM && method != PWR_METHOD_GIVEN;
@@ -1250,6 +1461,7 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
     const bool need_up = gH_up != nullptr || gD_up != nullptr;
     if (D != nullptr && !(need_targets && need_up) && !force_direct_bwd()) {
         PipeArgs a;
+        const bool lean = !need_targets && !need_up && !no_lean_bwd();      // no dense map beyond z, D
         a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.stats = stats; a.uvd = uvd; a.g_uvd = g_uvd;
         a.slot2 = need_targets ? heat_gt : gH_up;
         a.slot3 = need_targets ? static_cast<const void*>(dmap_gt) : gD_up;
@@ -1259,6 +1471,18 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (lean) {
+            const int lean_grid = a.items < sms * kLeanCtasPerSm ? a.items : sms * kLeanCtasPerSm;
+#define PWR_LAUNCH_LEAN(M, LS, TZ)                                                                             \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(decoder_bwd_lean_kernel<M, LS, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             kLeanSmemBytes);                                                                  \
+        decoder_bwd_lean_kernel<M, LS, TZ><<<lean_grid, kLeanThreads, kLeanSmemBytes, s>>>(a);                 \
+    } while (0)
+            PWR_DISPATCH(PWR_LAUNCH_LEAN);
+#undef PWR_LAUNCH_LEAN
+            return launch_status();
+        }
         const int grid = a.items < sms ? a.items : sms;
 #define PWR_LAUNCH_PIPE(M, LS, TZ)                                                                             \
     do {                                                                                                       \

@@ -434,3 +434,46 @@ def test_pipelined_forward_equals_direct_forward(method, dtype, B, J, monkeypatc
     assert_close("heat vs oracle", Hp.cpu().numpy(), p_ref.numpy())
     assert_close("uvd vs oracle", uvd_p.cpu().numpy(), uvd_ref.numpy())
     assert torch.equal(uvd_n, uvd_p)
+
+
+@pytest.mark.parametrize("method,dtype", [("softmax", torch.float32), ("sum", torch.float32),
+                                          ("softmax", torch.bfloat16), ("sum", torch.float16)])
+@pytest.mark.parametrize("B,J", [(1, 1), (9, 14), (301, 5)])
+def test_lean_backward_equals_pipelined_backward(method, dtype, B, J, monkeypatch):
+    """Configurations without dense target / upstream maps (compact targets, uvd-only loss, plain
+    backward) run in the lean multi-CTA-per-SM kernel; PWR_BWD_LEAN=0 sends them through the
+    one-CTA-per-SM pipelined kernel.  Same arithmetic per pixel, different summation order."""
+    from pixelwiseregression_b200 import sfr
+    shape = synth.NYU
+    rng = np.random.default_rng(B + 7 * J)
+    d = synth.make_frames(shape, B, seed=B + J)
+    uvd_j = d["uvd"][:, :J] if J <= shape.joints else None
+    batch = sfr.build_sfr(torch.from_numpy(d["frames"]).cuda(), d["com"], d["cube"], uvd_j, fx=shape.fx, fy=shape.fy,
+                          targets="sparse")
+    g = torch.Generator(device=DEV).manual_seed(B * J)
+    z = (torch.randn(B, J, 64, 64, device=DEV, generator=g) * 3).to(dtype)
+    D = torch.randn(B, J, 64, 64, device=DEV, generator=g).to(dtype)
+    w = None
+    if method == "softmax":
+        wv = rng.uniform(0.5, 1.5, (J, 1)).astype(np.float32)
+        wv[::4] *= -1.0
+        w = cu(wv)
+    L, m = batch.label_img, batch.mask
+    _, uvd, st, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
+    g_uvd = torch.randn(B, J, 3, device=DEV, generator=g) * 1e-2
+    sparse = ops.SparseTargets(batch.taps, batch.uvd)
+    cases = [dict(targets=sparse, alpha=0.5, want_loss=True, g_uvd=g_uvd),     # compact targets, all three terms
+             dict(targets=sparse, alpha=1.0, want_loss=False),                 # uvd term only, no map reads at all
+             dict(g_uvd=g_uvd),                                                # plain backward
+             dict(g_uvd=g_uvd, want_gD=False)]
+    for kw in cases:
+        monkeypatch.setenv("PWR_BWD_LEAN", "0")
+        a = ops.decoder_backward_raw(z, w, D, L, m, st, uvd, method=method, **kw)
+        monkeypatch.setenv("PWR_BWD_LEAN", "1")
+        b = ops.decoder_backward_raw(z, w, D, L, m, st, uvd, method=method, **kw)
+        torch.cuda.synchronize()
+        for name, x, y in zip(("gz", "gD", "gw_partial", "loss_partial"), b, a):
+            assert (x is None) == (y is None), name
+            if x is not None:
+                tol = 1e-5 if dtype == torch.float32 else 1e-2          # half outputs: one rounding of a ~1e-6-different value
+                assert_close(name, x.float().cpu().numpy(), y.float().cpu().numpy(), tol)

@@ -49,6 +49,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--joints", type=int, default=14)
     ap.add_argument("--print-only", action="store_true", help="exploratory capture: write nothing under profiles/")
+    ap.add_argument("--append", default="", metavar="TITLE",
+                    help="append the tables under this title to profiles/{tag}_ncu_summary.md; traffic.json is left alone")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -85,6 +87,14 @@ def main():
                 (rd + wr) / 1e9, alg[entry] / 1e9, (rd + wr) / alg[entry]))
     if args.print_only:
         print("\n".join(out_md))
+        return
+    if args.append:
+        out_md[0] = "\n# %s (`%s`, B=%d, J=%d)\n" % (args.append, os.path.basename(args.report), args.batch, args.joints)
+        del out_md[1]
+        out_md = [l for l in out_md if "DRAM traffic / algorithmic bytes" not in l]
+        with open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % args.tag), "a") as f:
+            f.write("\n".join(out_md) + "\n")
+        print("\n".join(out_md[-30:]))
         return
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % args.tag), "w") as f:

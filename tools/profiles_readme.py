@@ -44,6 +44,8 @@ L = ["# profiles/ — round 1\n",
      "| `%s_launches.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `bench.py --steps 3 --warmup 3` (includes the synthetic-input generation kernels before the first step) |" % tag,
      "| `%s_ncu_summary.md` | key metrics of one `ncu --set full` capture of the hot kernels (`tools/ncu_summary.py`) |" % tag,
      "| `traffic.json` | DRAM bytes per launch from that capture (read by `bench.py` -> `roofline.traffic`) |",
+     "| `%s_sweep_hand17_n1.txt` | `tools/sweep_inference.py`: BASELINE configs[4] inference sweep (HAND17 shape, batch 256 .. 16384) |" % tag,
+     "| `../tools/capture_profiles.sh` | the exact commands behind all of the above |",
      "| `%s_sanitizer_*.log` | `compute-sanitizer` memcheck / racecheck over the GPU parity tests: 0 errors, 0 hazards |" % tag,
      "",
      "## Share of the step: ncu launch list (cold, serialised) vs CUDA events inside bench.py\n",
@@ -91,11 +93,23 @@ L += ["",
       % (bench["gpu_eager_decoder"]["ms"], bench["gpu_eager_decoder"]["fused_ms"], bench["gpu_eager_decoder"]["speedup"]),
       "* `sparse_targets` (compact 64-byte targets evaluated inside the loss kernel, reported separately as SURVEY 8d asks): "
       "%.2f M samples/s, %d B/sample." % (bench["sparse_targets"]["value"] / 1e6, bench["sparse_targets"]["algorithmic_bytes_per_sample"])]
+sp = bench["sparse_targets"]["kernels"]
+L.append("  Its kernels: lean SFR build (2 bands, no dense maps) %.3f ms, forward %.3f ms, lean backward "
+         "(`decoder_bwd_lean_kernel`, 2 CTAs/SM) %.3f ms = %.0f %% of the measured peak on its own algorithmic bytes."
+         % (sp["pwr_sfr_build"]["avg_ms"], sp["pwr_decoder_fwd"]["avg_ms"], sp["pwr_decoder_bwd_loss"]["avg_ms"],
+            100 * sp["pwr_decoder_bwd_loss"]["frac"]))
 for n in (2, 4, 8):
     f = os.path.join(P, "%s_bench_n%d.json" % (tag, n))
     if os.path.isfile(f):
         b = json.load(open(f))
         L.append("* N = %d (weak scaling, torchrun + NCCL): %.2f M samples/s, %.3f ms/step -> %.1f %% of N x the N = 1 value."
                  % (n, b["value"] / 1e6, b["ms_per_step"], 100 * b["value"] / (n * bench["value"])))
+sweep = os.path.join(P, "%s_sweep_hand17_n1.txt" % tag)
+if os.path.isfile(sweep):
+    table = [l.rstrip() for l in open(sweep) if l.startswith("|")]
+    L += ["", "## Inference sweep (BASELINE configs[4]: HAND17 shape, J = 21, one B200)\n",
+          "One pass = test-only SFR (`pwr_sfr_crop`) + decoder forward without the heat-map store (`pwr_decoder_fwd`, "
+          "pipelined kernel) + `pwr_recover_uvd`; `calls` = launched from Python one by one, `graph` = the same pass "
+          "replayed as one CUDA graph; roofline against the SURVEY 8d byte formulas.\n"] + table
 open(os.path.join(P, "README.md"), "w").write("\n".join(L) + "\n")
 print("\n".join(L[12:]))

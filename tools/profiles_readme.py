@@ -104,6 +104,18 @@ for n in (2, 4, 8):
         b = json.load(open(f))
         L.append("* N = %d (weak scaling, torchrun + NCCL): %.2f M samples/s, %.3f ms/step -> %.1f %% of N x the N = 1 value."
                  % (n, b["value"] / 1e6, b["ms_per_step"], 100 * b["value"] / (n * bench["value"])))
+trains = {n: os.path.join(P, "%s_train_n%d.json" % (tag, n)) for n in (1, 2, 4, 8)}
+if all(os.path.isfile(f) for f in trains.values()):
+    t = {n: json.load(open(f)) for n, f in trains.items()}
+    L += ["", "## End-to-end training step (BASELINE configs[2]; `examples/train_synthetic.py`, `%s_train_n*.json`)\n" % tag,
+          "On-GPU SFR build -> PixelwiseRegression (cuDNN hourglass backbone, features %d, %d stages, float32) with the fused "
+          "decoder + loss -> backward -> AdamW, batch %d per GPU, DDP over NCCL for N > 1 (N = 8 alone on the box; "
+          "N = 4 / 2 / 1 side by side on disjoint GPUs of the same box).  The backbone is the unchanged reference on cuDNN "
+          "and bounds the step; the point of the table is the scaling.\n"
+          % (t[1]["config"]["features"], t[1]["config"]["stages"], 128),
+          "| GPUs | ms/step | samples/s | of N x the N = 1 value |", "|---|---|---|---|"]
+    for n in (1, 2, 4, 8):
+        L.append("| %d | %.2f | %.0f | %.1f %% |" % (n, t[n]["ms_per_step"], t[n]["value"], 100 * t[n]["value"] / (n * t[1]["value"])))
 sweep = os.path.join(P, "%s_sweep_hand17_n1.txt" % tag)
 if os.path.isfile(sweep):
     table = [l.rstrip() for l in open(sweep) if l.startswith("|")]

@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 METRIC = "SFR+decoder samples/s"
 UNIT = "samples/s"
+NOMINAL_HBM_GBS = 8000.0      # report against the nominal B200 figure as well as the measured copy peak
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 OUT = sys.stdout
 
@@ -40,8 +41,8 @@ OUT = sys.stdout
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)       # >= 50 timed iterations after 10 warm-ups
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--shape", default="NYU")
@@ -442,10 +443,13 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
                          "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,
+                         "nominal_peak": NOMINAL_HBM_GBS, "frac_of_nominal": dk["achieved_gbs"] / NOMINAL_HBM_GBS,
                          "avg_launch_ms": dk["avg_ms"], "algorithmic_bytes_per_launch": dk["algorithmic_bytes"],
                          "share_of_step": dk["avg_ms"] / step_kernel_ms if step_kernel_ms else None},
             "kernels": kernels,
             "step_roofline_frac": (roofline.step_bytes(J) * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
+            "step_roofline_frac_of_nominal": (roofline.step_bytes(J) * B / (elapsed_ms / args.steps * 1e-3) / 1e9)
+                                             / NOMINAL_HBM_GBS,
             "host_issue_ms_per_step": issue_ms,
             "between_kernels_ms_per_step": gap_ms,
             "cpu_baseline": cpu,

@@ -344,6 +344,35 @@ def golden_decoder(model_mod, name, method, B, J, seed, alpha, with_upstream):
     print(name, "losses", out["ref_losses"])
 
 
+def golden_model(model_mod, datasets, name, shape, B, seed, features=32, level=2, stages=2):
+    """BASELINE configs[0] (reference PixelwiseRegression, eval forward on the CPU, crops from the
+    reference's own SFR builder) at a width that keeps the fixture small: the reference's weights travel in
+    the file, so the drop-in model must load them (state_dict compatibility) and reproduce the outputs."""
+    torch.manual_seed(seed)
+    d = synth.make_frames(shape, B, seed)
+    ref = run_reference_sfr(datasets, shape, d["frames"], d["uvd"], d["com"], d["cube"], test_only=True)
+    assert ref["ref_valid"].all()
+    net = model_mod.PixelwiseRegression(shape.joints, stage=stages, features=features, level=level, norm_method="instance")
+    with torch.no_grad():
+        for st in net.stages:                      # trained temperatures are not all 1 (and can be negative)
+            st.plane_regression.w.uniform_(0.5, 1.5)
+        net.stages[-1].plane_regression.w[0] = -0.8
+    net.eval()
+    img, label, mask = (torch.from_numpy(ref["ref_" + n]) for n in ("img", "label_img", "mask"))
+    with torch.no_grad():
+        results = net(img, label, mask)
+    out = {"sd_" + k: v.numpy() for k, v in net.state_dict().items()}
+    out.update(img=img.numpy(), label_img=label.numpy(), mask=mask.numpy(), joints=np.int64(shape.joints),
+               features=np.int64(features), level=np.int64(level), stages=np.int64(stages), versions=versions())
+    for i, (heat, dm, uvd) in enumerate(results):
+        out["ref_uvd_%d" % i] = uvd.numpy()
+    out["ref_heat_last"] = results[-1][0][:1].numpy()       # one sample of maps is enough to pin the layout
+    out["ref_dmap_last"] = results[-1][1][:1].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    n_par = sum(p.numel() for p in net.parameters())
+    print(name, "params", n_par, "uvd[0,0]", results[-1][2][0, 0].tolist())
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     model_mod, _, datasets = ref_shim.load()
@@ -363,6 +392,7 @@ def main():
     golden_decoder(model_mod, "decoder_softmax_a1", "softmax", 2, 3, 10, 1.0, False)
     golden_decoder(model_mod, "decoder_softmax_a05_up", "softmax", 2, 3, 11, 0.5, True)
     golden_decoder(model_mod, "decoder_sum_a05_up", "sum", 2, 3, 12, 0.5, True)
+    golden_model(model_mod, datasets, "model_nyu_eval", synth.NYU, 6, 40)
 
 
 if __name__ == "__main__":

@@ -56,3 +56,17 @@ def assert_sfr_matches(got, ref, names, valid_ref, prefix=""):
         assert ((a > 0) == (b > 0)).all(), prefix + "heat-map support differs"
         a, b = np.asarray(got["dmap"])[sel], np.asarray(ref["dmap"])[sel]
         assert ((a != 0) == (b != 0)).all(), prefix + "Dmap support differs"
+
+
+def load_model_golden(name="model_nyu_eval"):
+    """Reference PixelwiseRegression weights + inputs + eval outputs (oracle/make_golden.py:golden_model).
+    Returns (golden dict, drop-in model with the reference's weights loaded, strict)."""
+    import torch
+    from pixelwiseregression_b200 import model as M
+    g = load_golden(name)
+    net = M.PixelwiseRegression(int(g["joints"]), stage=int(g["stages"]), features=int(g["features"]),
+                                level=int(g["level"]), norm_method="instance")
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")}
+    net.load_state_dict(sd, strict=True)          # the reference's own keys and shapes, nothing missing or extra
+    net.eval()
+    return g, net

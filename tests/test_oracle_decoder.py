@@ -83,3 +83,26 @@ def test_com_filter_matches_reference_definition():
     f = do.com_filter(64, torch.float64)
     assert f.shape == (2, 64, 64)
     assert f[0, 5, 40].item() == (40 - 32) / 63 and f[1, 5, 40].item() == (5 - 32) / 63
+
+
+def test_reference_model_weights_load_and_oracle_decoder_reproduces_reference_outputs():
+    """BASELINE configs[0] on the CPU: the unmodified reference model's state_dict loads into the drop-in
+    module tree (strict), and its backbone (plain PyTorch convs) + the oracle decoder reproduce the
+    reference's eval outputs on the reference's own SFR crops."""
+    import torch
+    from helpers import load_model_golden
+    g, net = load_model_golden()
+    img, label, mask = (torch.from_numpy(g[n]) for n in ("img", "label_img", "mask"))
+    with torch.no_grad():
+        f = net.conv(img)
+        results = []
+        for stage in net.stages:
+            f, z, d_raw = stage.features_and_logits(f)
+            plane = stage.plane_regression
+            H, D, uvd = do.decoder_forward(z, plane.temperature, d_raw, label, mask, plane.method)
+            results.append((H, D, uvd))
+            f = torch.cat([H, D, label], dim=1)
+    for i, (H, D, uvd) in enumerate(results):
+        assert_close("uvd stage %d" % i, uvd.numpy(), g["ref_uvd_%d" % i])
+    assert_close("heat", results[-1][0][:1].numpy(), g["ref_heat_last"])
+    assert_close("dmap", results[-1][1][:1].numpy(), g["ref_dmap_last"])

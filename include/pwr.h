@@ -227,6 +227,23 @@ int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D,
                          float* loss_partial,
                          int B, int J, int method, int map_dtype, void* stream);
 
+/* Last stage in one pass: pwr_decoder_fwd + pwr_decoder_bwd_loss without upstream gradients
+ * (train.py:192-207 when nothing but the loss consumes the stage's outputs).  z, D, heat_gt, dmap_gt
+ * are read once; `stats` never exists.  Arguments as in the two calls it replaces:
+ *   outputs H [B,J,64,64] (NULL = not wanted), uvd [B,J,3], gz, gD (either NULL = not wanted),
+ *   gw_partial [B,J] (PWR_METHOD_SOFTMAX), loss_partial [B,J,3] (NULL = not wanted).
+ * method is PWR_METHOD_SOFTMAX or PWR_METHOD_SUM; the depth branch is mandatory. */
+int pwr_decoder_fwd_bwd_loss(const void* z, const float* w, const void* D,
+                             const float* L, const float* m,
+                             const float* heat_gt, const float* dmap_gt,
+                             const float* uvd_gt, const pwr_joint_taps* taps,
+                             float alpha, float lambda_h, float lambda_d,
+                             float loss_scale, const float* loss_scale_dev,
+                             int n_mean,
+                             float* H, float* uvd, void* gz, void* gD,
+                             float* gw_partial, float* loss_partial,
+                             int B, int J, int method, int map_dtype, void* stream);
+
 /* Deterministic sum over the batch axis: out[j*C + c] = sum_b in[(b*J+j)*C+c]
  * (gw_partial -> gw: C=1; loss_partial -> per-joint sums: C=3). */
 int pwr_reduce_partials(const float* in, float* out, int B, int J, int C,

@@ -37,6 +37,7 @@ SIGNATURES = {
     "pwr_decoder_fwd": [_P] * 13 + [_I, _I, _I, _I, _P],
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _I, _P],
     "pwr_decoder_bwd_loss": [_P] * 14 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _I, _P],
+    "pwr_decoder_fwd_bwd_loss": [_P] * 9 + [_F, _F, _F, _F, _P, _I] + [_P] * 6 + [_I, _I, _I, _I, _P],
     "pwr_reduce_partials": [_P, _P, _I, _I, _I, _P],
     "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P],
     "pwr_scale_inplace": [_P, _P, _LL, _I, _P],

@@ -1117,6 +1117,284 @@ static int check_bj(int B, int J) {
     return 0;
 }
 // ---------------------------------------------------------------------------
+// last stage in ONE pass: forward + stage loss + backward (pwr_decoder_fwd_bwd_loss)
+// ---------------------------------------------------------------------------
+// train.py:192-207 for the last stage: nothing consumes its heat maps but the loss, so forward and
+// backward can share one visit of (z, D, heat_gt, dmap_gt): the logits are read once instead of
+// twice and `stats` never travels.  Per sample (7J + 2) maps move instead of (3J + 2) + (6J + 2)
+// (H stored; 6J + 2 without).
+// An item is a chain of three block reductions (extremum, forward sums, backward sums); one lock-step
+// 512-thread CTA per SM spent 6 750 cycles per item on it and LOST to the two-kernel route (1.36 vs
+// 1.32 ms, r1).  Hence two independent 256-thread CTAs per SM, each with its own ring of six 16 KB
+// slots (96 KB): the 2 or 4 maps of an item (z, D[, heat_gt, dmap_gt]) are bulk-TMA loads in one
+// FIFO, up to six in flight or resident, so while an item is in its backward pass the logits of the
+// next one (and with compact targets of the next two) are already landing.  L, m live in registers
+// across the J items of a sample; block sums cost 8 shuffles per warp.
+#ifndef PWR_FUSED_THREADS
+#define PWR_FUSED_THREADS 256
+#endif
+constexpr int kFusedThreads = PWR_FUSED_THREADS;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kFusedVec = kMap / 4 / kFusedThreads;
+constexpr int kFusedSlots = 6;
+constexpr int kFusedCtasPerSm = 2;
+constexpr int kFusedSmemBytes = kFusedSlots * kSlotBytes + 64;
+static_assert(kFusedThreads == kFwdThreads, "store_scattered5 / sum_partials are laid out for kFwdWarps warps");
+static_assert(kFusedVec * 4 <= 32, "one z > 0 bit per pixel of a thread");
+
+struct FusedArgs {
+    const void* z; const float* w; const void* D; const float* L; const float* m;
+    const float* heat_gt; const float* dmap_gt; const float* uvd_gt; const pwr_joint_taps* taps;
+    LossCoef coef;
+    float* H; float* uvd; void* gz; void* gD; float* gw_partial; float* loss_partial;
+    int J; int items;
+};
+
+template <int METHOD, int LOSS, typename TZ>
+__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm)
+decoder_fused_kernel(FusedArgs a) {
+    static_assert(LOSS != LOSS_NONE && METHOD != PWR_METHOD_GIVEN, "last stage with a loss");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slots = reinterpret_cast<float*>(smem_raw);                                    // [6][4096]
+    uint64_t* full = reinterpret_cast<uint64_t*>(slots + kFusedSlots * kMap);             // [6]
+    __shared__ __align__(16) float scr_e[2][kFusedWarps];
+    __shared__ __align__(16) float scr_f[2][5 * kFusedWarps];     // forward sums
+    __shared__ __align__(16) float scr_b[2][5 * kFusedWarps];     // backward sums
+    __shared__ __align__(16) uint32_t scal[2][32];                // 10-12 uvd_gt, 16-31 taps (one item ahead)
+    __shared__ float fp[LOSS == LOSS_SPARSE ? kFootprint : 1];
+    constexpr bool sparse = (LOSS == LOSS_SPARSE);
+
+    const int tid = threadIdx.x;
+    const long long first = static_cast<long long>(a.items) * blockIdx.x / gridDim.x;
+    const long long last = static_cast<long long>(a.items) * (blockIdx.x + 1) / gridDim.x;
+    if (first >= last) return;
+    if (a.coef.scale_dev != nullptr) {
+        const float up = *a.coef.scale_dev;
+        a.coef.cu *= up; a.coef.ch *= up; a.coef.cd *= up;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kFusedSlots; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool maps = !sparse && a.heat_gt != nullptr;        // dense target maps are visited (else: uvd term only)
+    const int lpi = maps ? 4 : 2;                             // loads per item: z, D[, heat_gt, dmap_gt]
+    constexpr uint32_t kZBytes = kMap * sizeof(TZ);
+    auto scalar_word = [&](long long it, int wd) -> uint32_t {
+        const size_t bj = static_cast<size_t>(it);
+        if (wd >= 10 && wd < 13) return __float_as_uint(a.uvd_gt[bj * 3 + wd - 10]);
+        if (wd >= 16 && sparse) return reinterpret_cast<const uint32_t*>(a.taps + bj)[wd - 16];
+        return 0u;
+    };
+    if (tid < 32) scal[0][tid] = scalar_word(first, tid);
+    __syncthreads();
+
+    // producer (thread 0): one FIFO of loads, load n -> slot n % 6
+    long long p_it = first;
+    int p_q = 0, n_issued = 0;
+    auto fill = [&](int limit) {
+        while (n_issued < limit && p_it < last) {
+            const int sl = n_issued % kFusedSlots;
+            float* dst = slots + sl * kMap;
+            const size_t off = static_cast<size_t>(p_it) * kMap;
+            if (p_q < 2) {
+                mbar_expect_tx(&full[sl], kZBytes);
+                bulk_g2s(dst, static_cast<const TZ*>(p_q == 0 ? a.z : a.D) + off, kZBytes, &full[sl]);
+            } else {
+                mbar_expect_tx(&full[sl], kSlotBytes);
+                bulk_g2s(dst, (p_q == 2 ? a.heat_gt : a.dmap_gt) + off, kSlotBytes, &full[sl]);
+            }
+            ++n_issued;
+            if (++p_q == lpi) { p_q = 0; ++p_it; }
+        }
+    };
+    if (tid == 0) fill(kFusedSlots);
+
+    int b_cur = static_cast<int>(first / a.J);
+    int j_cur = static_cast<int>(first - static_cast<long long>(b_cur) * a.J);
+    const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
+    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + (kFusedThreads/16)*i
+    float4 lv[kFusedVec], mv[kFusedVec];
+    int b_loaded = -1;
+    float w_next = (METHOD == PWR_METHOD_SOFTMAX) ? a.w[j_cur] : 1.f;
+    int k = 0;
+    for (long long it = first; it < last; ++it, ++k) {
+        const float wj = w_next;
+        const float c = wj * kLog2e;
+        if (b_cur != b_loaded) {                      // label and mask stay in registers for the J items of a sample
+            b_loaded = b_cur;
+            const size_t offb = static_cast<size_t>(b_cur) * kMap + tid * 4;
+#pragma unroll
+            for (int i = 0; i < kFusedVec; ++i) mv[i] = ld_keep(a.m + offb + i * (kFusedThreads * 4));
+#pragma unroll
+            for (int i = 0; i < kFusedVec; ++i) lv[i] = ld_keep(a.L + offb + i * (kFusedThreads * 4));
+        }
+        const uint32_t next_word = (tid < 32 && it + 1 < last) ? scalar_word(it + 1, tid) : 0u;
+        const float* sc = reinterpret_cast<const float*>(scal[k & 1]);
+        TapsIdx tp;
+        if (sparse) {
+            tp = taps_index(scal[k & 1] + 16);
+            if (tid < kFootprint) fp[tid] = footprint_entry(scal[k & 1] + 16, tid);
+        }
+        // slots and barrier phases of this item's loads
+        const int n0 = k * lpi;
+        const int sl_z = n0 % kFusedSlots, sl_d = (n0 + 1) % kFusedSlots;
+        const float* sz = slots + sl_z * kMap;
+        const float* sD = slots + sl_d * kMap;
+
+        // ---- forward: extremum, un-normalised heat, five sums (decoder_fwd_kernel's arithmetic) ----
+        mbar_wait(&full[sl_z], (n0 / kFusedSlots) & 1);
+        float4 zv[kFusedVec], pv[kFusedVec];
+#pragma unroll
+        for (int i = 0; i < kFusedVec; ++i) zv[i] = MapIO<TZ>::smem(sz, tid + i * kFusedThreads);
+        float shift = 0.f, zext = 0.f;
+        if (METHOD == PWR_METHOD_SOFTMAX) {
+            const bool want_max = c >= 0.f;
+            float e = want_max ? -INFINITY : INFINITY;
+#pragma unroll
+            for (int i = 0; i < kFusedVec; ++i) {
+                if (want_max) e = fmaxf(fmaxf(fmaxf(e, zv[i].x), fmaxf(zv[i].y, zv[i].z)), zv[i].w);
+                else          e = fminf(fminf(fminf(e, zv[i].x), fminf(zv[i].y, zv[i].z)), zv[i].w);
+            }
+            e = want_max ? warp_max(e) : warp_min(e);
+            float* se = scr_e[k & 1];
+            if ((tid & 31) == 0) se[tid >> 5] = e;
+            __syncthreads();                                             // (also publishes fp)
+            zext = se[0];
+#pragma unroll
+            for (int wv = 1; wv < kFusedWarps; ++wv) zext = want_max ? fmaxf(zext, se[wv]) : fminf(zext, se[wv]);
+            shift = zext * c;
+        } else if (sparse) {
+            __syncthreads();                                             // fp visible
+        }
+        mbar_wait(&full[sl_d], ((n0 + 1) / kFusedSlots) & 1);
+        float accf[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum e, e*(x-32), e*(y-32), e*m, e*m*m*(D+L)
+#pragma unroll
+        for (int i = 0; i < kFusedVec; ++i) {
+            const float4 d4 = MapIO<TZ>::smem(sD, tid + i * kFusedThreads);
+            const float ys = ys0 + static_cast<float>(kFusedThreads / 16) * i;
+            float rowsum = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float e = heat_raw<METHOD>(comp(zv[i], kk), c, shift);
+                set_comp(pv[i], kk, e);
+                const float mk = comp(mv[i], kk);
+                const float em = e * mk;
+                rowsum += e;
+                accf[1] = fmaf(e, xs + static_cast<float>(kk), accf[1]);
+                accf[3] += em;
+                accf[4] = fmaf(em, mk * (comp(d4, kk) + comp(lv[i], kk)), accf[4]);
+            }
+            accf[0] += rowsum;
+            accf[2] = fmaf(rowsum, ys, accf[2]);
+        }
+        float* sf = scr_f[k & 1];
+        store_scattered5(warp_sum5_scattered(accf), sf);
+        __syncthreads();
+        const float inv_s = 1.f / sum_partials(sf);
+        const float den = fmaf(sum_partials(sf + 3 * kFusedWarps), inv_s, kEps);
+        const float dcoord = (sum_partials(sf + 4 * kFusedWarps) * inv_s) / den;
+        const float u = sum_partials(sf + kFusedWarps) * inv_s / 63.f;
+        const float v = sum_partials(sf + 2 * kFusedWarps) * inv_s / 63.f;
+
+        // ---- loss on the coordinates: the upstream of the backward ----
+        const float eu = u - sc[10], ev = v - sc[11], ed = dcoord - sc[12];
+        const float gu = a.coef.cu * eu, gvv = a.coef.cu * ev, gd = a.coef.cu * ed;
+        const float lu = eu * eu + ev * ev + ed * ed;
+        const float gu63 = gu * (1.f / 63.f), gv63 = gvv * (1.f / 63.f);
+        const float gdd = __fdividef(gd, den);
+
+        // ---- backward pass (decoder_bwd_pipe_kernel's arithmetic), heat maps stored on the way ----
+        const float4* s2 = reinterpret_cast<const float4*>(slots + ((n0 + 2) % kFusedSlots) * kMap);
+        const float4* s3 = reinterpret_cast<const float4*>(slots + ((n0 + 3) % kFusedSlots) * kMap);
+        if (maps) {
+            mbar_wait(&full[(n0 + 2) % kFusedSlots], ((n0 + 2) / kFusedSlots) & 1);
+            mbar_wait(&full[(n0 + 3) % kFusedSlots], ((n0 + 3) / kFusedSlots) & 1);
+        }
+        float4 gv[kFusedVec];
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2, T1, T2
+        unsigned int zpos = 0;
+#pragma unroll
+        for (int i = 0; i < kFusedVec; ++i) {
+            const int cidx = tid + i * kFusedThreads;
+            const float4 d4 = MapIO<TZ>::smem(sD, cidx), l4 = lv[i], m4 = mv[i];
+            float4 t2 = make_float4(0.f, 0.f, 0.f, 0.f), t3 = t2;
+            if (sparse) sparse_lookup(tp, fp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
+            else if (maps) { t2 = s2[cidx]; t3 = s3[cidx]; }
+            const bool have_t = sparse || maps;
+            const float gyrow = gv63 * (ys0 + static_cast<float>(kFusedThreads / 16) * i);
+            float4 gd4, p4;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float zk = comp(zv[i], kk);
+                const float p = comp(pv[i], kk) * inv_s;
+                const float mk = comp(m4, kk), dk = comp(d4, kk);
+                const float rec = mk * (dk + comp(l4, kk));
+                float gp = fmaf(gu63, xs + static_cast<float>(kk), gyrow);
+                gp = fmaf(gdd * mk, rec - dcoord, gp);
+                float gdk = gdd * p * mk * mk;
+                if (have_t) {
+                    const float eh = p - comp(t2, kk), edm = dk - comp(t3, kk);
+                    gp = fmaf(a.coef.ch, eh, gp);
+                    gdk = fmaf(a.coef.cd, edm, gdk);
+                    acc[1] = fmaf(eh, eh, acc[1]);
+                    acc[2] = fmaf(edm, edm, acc[2]);
+                }
+                const float pg = gp * p;
+                acc[0] += pg;
+                if (METHOD == PWR_METHOD_SOFTMAX) {
+                    const float dz = zk - zext;
+                    acc[3] = fmaf(pg, dz, acc[3]);
+                    acc[4] = fmaf(p, dz, acc[4]);
+                }
+                if (METHOD == PWR_METHOD_SUM && zk > 0.f) zpos |= 1u << (4 * i + kk);
+                set_comp(p4, kk, p);
+                set_comp(gv[i], kk, gp);
+                set_comp(gd4, kk, gdk);
+            }
+            pv[i] = p4;
+            if (a.H != nullptr) st_stream(a.H + static_cast<size_t>(it) * kMap + cidx * 4, p4);
+            if (a.gD != nullptr) MapIO<TZ>::st(a.gD, static_cast<size_t>(it) * kMap + cidx * 4, gd4);
+        }
+        // next item's scalars: parked before the barrier below, read after it
+        if (tid < 32 && it + 1 < last) scal[(k + 1) & 1][tid] = next_word;
+        float* sb = scr_b[k & 1];
+        store_scattered5(warp_sum5_scattered(acc), sb);
+        __syncthreads();
+        // every thread is past its shared-memory reads of this item: its slots go back to the FIFO
+        if (tid == 0) fill((k + 1) * lpi + kFusedSlots);
+        if (++j_cur == a.J) { j_cur = 0; ++b_cur; }
+        if (METHOD == PWR_METHOD_SOFTMAX && it + 1 < last) w_next = a.w[j_cur];
+
+        const float s1 = sum_partials(sb);
+        if (a.gz != nullptr) {
+#pragma unroll
+            for (int i = 0; i < kFusedVec; ++i) {
+                float4 g4;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    float g;
+                    if (METHOD == PWR_METHOD_SOFTMAX) g = wj * (comp(pv[i], kk) * (comp(gv[i], kk) - s1));
+                    else g = ((zpos >> (4 * i + kk)) & 1u) ? (comp(gv[i], kk) - s1) * inv_s : 0.f;
+                    set_comp(g4, kk, g);
+                }
+                MapIO<TZ>::st(a.gz, static_cast<size_t>(it) * kMap + (tid + i * kFusedThreads) * 4, g4);
+            }
+        }
+        if (tid == 0) {
+            float* o = a.uvd + static_cast<size_t>(it) * 3;
+            o[0] = u; o[1] = v; o[2] = dcoord;
+            if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr)
+                a.gw_partial[it] = sum_partials(sb + 3 * kFusedWarps) - s1 * sum_partials(sb + 4 * kFusedWarps);
+            if (a.loss_partial != nullptr) {
+                a.loss_partial[it * 3 + 0] = sum_partials(sb + kFusedWarps);
+                a.loss_partial[it * 3 + 1] = sum_partials(sb + 2 * kFusedWarps);
+                a.loss_partial[it * 3 + 2] = lu;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // backward, lean pipelined variant: no dense target / upstream-gradient maps
 // ---------------------------------------------------------------------------
 // With compact (pwr_joint_taps) targets, or with no map terms at all, an item moves only 32 KB in
@@ -1528,6 +1806,61 @@ extern "C" int pwr_decoder_bwd_loss(const void* z, const float* w, const void* D
     coef.scale_dev = loss_scale_dev;
     return launch_bwd(true, z, w, D, L, m, stats, uvd, g_uvd, gH_up, gD_up, heat_gt, dmap_gt, uvd_gt, taps, coef, gz,
                       gD, gw_partial, loss_partial, B, J, method, map_dtype, stream);
+}
+
+extern "C" int pwr_decoder_fwd_bwd_loss(const void* z, const float* w, const void* D, const float* L, const float* m,
+                                        const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
+                                        const pwr_joint_taps* taps, float alpha, float lambda_h, float lambda_d,
+                                        float loss_scale, const float* loss_scale_dev, int n_mean, float* H,
+                                        float* uvd, void* gz, void* gD, float* gw_partial, float* loss_partial,
+                                        int B, int J, int method, int map_dtype, void* stream) {
+    if (method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM) return PWR_E_METHOD;
+    if (bad_dtype(method, map_dtype)) return PWR_E_METHOD;
+    if (int rc = check_bj(B, J)) return rc;
+    if (B == 0) return 0;
+    PWR_REQUIRE_PTR(z); PWR_REQUIRE_PTR(D); PWR_REQUIRE_PTR(L); PWR_REQUIRE_PTR(m);
+    PWR_OPTIONAL_PTR(H); PWR_OPTIONAL_PTR(gz); PWR_OPTIONAL_PTR(gD);
+    if (uvd == nullptr || uvd_gt == nullptr) return PWR_E_NULL;
+    if (method == PWR_METHOD_SOFTMAX && w == nullptr) return PWR_E_NULL;
+    if (taps == nullptr) { PWR_REQUIRE_PTR(heat_gt); PWR_REQUIRE_PTR(dmap_gt); }
+    else PWR_REQUIRE_PTR(taps);
+    const double n = n_mean > 0 ? static_cast<double>(n_mean) : static_cast<double>(B) * J;
+    FusedArgs a;
+    a.coef.cu = static_cast<float>(loss_scale * 2.0 * alpha / n);
+    a.coef.ch = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_h / n);
+    a.coef.cd = static_cast<float>(loss_scale * 2.0 * (1.0 - alpha) * lambda_d / n);
+    a.coef.scale_dev = loss_scale_dev;
+    // the target maps are only visited when their loss terms matter (logged values or non-zero weights)
+    const bool map_terms = loss_partial != nullptr || a.coef.ch != 0.f || a.coef.cd != 0.f;
+    a.z = z; a.w = w; a.D = D; a.L = L; a.m = m;
+    a.heat_gt = (map_terms && taps == nullptr) ? heat_gt : nullptr;
+    a.dmap_gt = (map_terms && taps == nullptr) ? dmap_gt : nullptr;
+    a.uvd_gt = uvd_gt; a.taps = map_terms ? taps : nullptr;
+    a.H = H; a.uvd = uvd; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial; a.loss_partial = loss_partial;
+    a.J = J; a.items = B * J;
+    const bool sparse = a.taps != nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.items < sms * kFusedCtasPerSm ? a.items : sms * kFusedCtasPerSm;
+#define PWR_LAUNCH_FUSED(M, LS, TZ)                                                                          \
+    do {                                                                                                     \
+        cudaFuncSetAttribute(decoder_fused_kernel<M, LS, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                             kFusedSmemBytes);                                                               \
+        decoder_fused_kernel<M, LS, TZ><<<grid, kFusedThreads, kFusedSmemBytes, s>>>(a);                     \
+    } while (0)
+#define PWR_FUSED_TZ(M, LS)                                                                                  \
+    do {                                                                                                     \
+        if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_FUSED(M, LS, float);                                 \
+        else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_FUSED(M, LS, __half);                                \
+        else                                 PWR_LAUNCH_FUSED(M, LS, __nv_bfloat16);                         \
+    } while (0)
+    if (method == PWR_METHOD_SOFTMAX) { if (sparse) PWR_FUSED_TZ(PWR_METHOD_SOFTMAX, LOSS_SPARSE); else PWR_FUSED_TZ(PWR_METHOD_SOFTMAX, LOSS_DENSE); }
+    else                              { if (sparse) PWR_FUSED_TZ(PWR_METHOD_SUM, LOSS_SPARSE); else PWR_FUSED_TZ(PWR_METHOD_SUM, LOSS_DENSE); }
+#undef PWR_FUSED_TZ
+#undef PWR_LAUNCH_FUSED
+    return launch_status();
 }
 
 extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, int C, void* stream) {

@@ -125,6 +125,35 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
     return gz, gD, gw_partial, loss_partial
 
 
+def decoder_fused_raw(z, w, D, label_img, mask, targets, method="softmax", alpha=1.0, lambda_h=1.0, lambda_d=0.01,
+                      loss_scale=1.0, loss_scale_dev=None, n_mean=0, store_heat=True, want_grads=True):
+    """One launch of pwr_decoder_fwd_bwd_loss: last-stage forward + stage loss + backward with z, D and
+    the targets read once.  Returns (H or None, uvd, gz, gD, gw_partial or None, loss_partial [B,J,3])."""
+    require_cuda(z, w, D, label_img, mask)
+    lib = _lib.load()
+    z, D, map_dtype = _conv_maps(z, D, method)
+    label_img, mask = as_f32(label_img), as_f32(mask)
+    _check_maps(z, label_img, mask)
+    B, J = z.shape[0], z.shape[1]
+    wv = as_f32(w).reshape(-1) if w is not None else None
+    heat_gt, dmap_gt, uvd_gt, taps = _unpack_targets(targets, B, J)
+    f32 = dict(device=z.device, dtype=torch.float32)
+    H = torch.empty(z.shape, **f32) if store_heat else None
+    uvd = torch.empty(B, J, 3, **f32)
+    gz = torch.empty_like(z) if want_grads else None
+    gD = torch.empty_like(z) if want_grads else None
+    gw_partial = torch.empty(B, J, **f32) if (want_grads and method == "softmax") else None
+    loss_partial = torch.empty(B, J, 3, **f32)
+    with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd_bwd_loss"):
+        rc = lib.pwr_decoder_fwd_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
+                                          ptr(uvd_gt), ptr(taps), float(alpha), float(lambda_h), float(lambda_d),
+                                          float(loss_scale), ptr(loss_scale_dev), int(n_mean), ptr(H), ptr(uvd),
+                                          ptr(gz), ptr(gD), ptr(gw_partial), ptr(loss_partial), B, J, METHODS[method],
+                                          map_dtype, stream_ptr(z.device))
+    check(rc, "pwr_decoder_fwd_bwd_loss")
+    return H, uvd, gz, gD, gw_partial, loss_partial
+
+
 def reduce_partials(partial):
     """[B, J] or [B, J, C] per-(sample, joint) partials -> [J] / [J, C] batch sums
     (deterministic tree, pwr_reduce_partials)."""
@@ -289,6 +318,11 @@ class DepthFunction(torch.autograd.Function):
         return gD.to(D.dtype), gH.to(heatmaps.dtype), None, None
 
 
+# False sends ops.fused_decoder_loss through the two-kernel route (pwr_decoder_fwd, then pwr_decoder_bwd_loss);
+# bench.py flips it to time both, tests to compare them.
+ONE_PASS_LAST_STAGE = True
+
+
 class DecoderLossFunction(torch.autograd.Function):
     """Last-stage decoder fused with the stage loss, train.py:197-207.
 
@@ -305,11 +339,16 @@ class DecoderLossFunction(torch.autograd.Function):
                 store_heat):
         ctx.set_materialize_grads(False)       # no zero-filled gradient tensors for the detached outputs
         need_grad = any(ctx.needs_input_grad[:3])
-        H, uvd, stats, _ = decoder_forward_raw(z, w, D, label_img, mask, method, store_heat=store_heat)
         targets = _make_targets(heat_gt, dmap_gt, uvd_gt)
-        gz, gD, gw_partial, loss_partial = decoder_backward_raw(
-            z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
-            want_loss=True, want_gz=need_grad, want_gD=need_grad)
+        if need_grad and D is not None and method != "given" and ONE_PASS_LAST_STAGE:
+            # forward + loss + backward in one visit of (z, D, targets)
+            H, uvd, gz, gD, gw_partial, loss_partial = decoder_fused_raw(
+                z, w, D, label_img, mask, targets, method, alpha, lambda_h, lambda_d, store_heat=store_heat)
+        else:
+            H, uvd, stats, _ = decoder_forward_raw(z, w, D, label_img, mask, method, store_heat=store_heat)
+            gz, gD, gw_partial, loss_partial = decoder_backward_raw(
+                z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
+                want_loss=True, want_gz=need_grad, want_gD=need_grad)
         out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
         terms, total = out4[:3], out4[3]
         gw = reduce_partials(gw_partial).view_as(w) if (need_grad and w is not None) else None

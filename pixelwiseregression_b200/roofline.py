@@ -43,6 +43,18 @@ def decoder_bwd_sparse_bytes(J):
     return 4 * J * MAP + 2 * MAP + TAPS * J
 
 
+def decoder_fused_bytes(J, store_heat=True, sparse=False):
+    """pwr_decoder_fwd_bwd_loss: read z, D (+ heat_gt, dmap_gt, or 64 B of taps per joint) + L, m once;
+    write gz, gD (+ H) + uvd."""
+    maps = 2 * J + (0 if sparse else 2 * J) + 2 * J + (J if store_heat else 0)
+    return maps * MAP + 2 * MAP + (TAPS * J if sparse else 0) + 16 * J
+
+
+def step_one_pass_bytes(J, sparse=False):
+    """SFR build + one-pass last stage (the logits and targets are visited once)."""
+    return (sfr_build_sparse_bytes(J) if sparse else sfr_build_bytes(J)) + decoder_fused_bytes(J, sparse=sparse)
+
+
 def step_sparse_bytes(J):
     return sfr_build_sparse_bytes(J) + decoder_fwd_bytes(J) + decoder_bwd_sparse_bytes(J)
 
@@ -56,3 +68,4 @@ assert sfr_build_bytes(14) == 622780 and sfr_build_bytes(21) == 852240
 assert decoder_fwd_bytes(14) == 721120 and decoder_fwd_bytes(21) == 1065296
 assert decoder_bwd_bytes(14) == 1409024 and decoder_bwd_bytes(14, upstream_maps=True) == 1867776
 assert step_bytes(14) == 2752924
+assert decoder_fused_bytes(14) == 1638624 and step_one_pass_bytes(14) == 2261404

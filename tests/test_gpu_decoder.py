@@ -477,3 +477,74 @@ def test_lean_backward_equals_pipelined_backward(method, dtype, B, J, monkeypatc
             if x is not None:
                 tol = 1e-5 if dtype == torch.float32 else 1e-2          # half outputs: one rounding of a ~1e-6-different value
                 assert_close(name, x.float().cpu().numpy(), y.float().cpu().numpy(), tol)
+
+
+@pytest.mark.parametrize("method,dtype", [("softmax", torch.float32), ("sum", torch.float32),
+                                          ("softmax", torch.float16), ("sum", torch.bfloat16)])
+@pytest.mark.parametrize("B,J,alpha", [(1, 1, 0.5), (10, 14, 1.0), (10, 14, 0.3), (151, 5, 0.5)])
+def test_one_pass_last_stage_equals_forward_then_backward(method, dtype, B, J, alpha, monkeypatch):
+    """pwr_decoder_fwd_bwd_loss (forward + loss + backward in one visit of z, D and the targets) against
+    pwr_decoder_fwd followed by pwr_decoder_bwd_loss, with dense and with compact targets, through the raw
+    entry point and through ops.fused_decoder_loss; and against the float64 oracle."""
+    from pixelwiseregression_b200 import sfr
+    shape = synth.NYU
+    rng = np.random.default_rng(3 * B + J)
+    d = synth.make_frames(shape, B, seed=B + 2 * J)
+    batch = sfr.build_sfr(torch.from_numpy(d["frames"]).cuda(), d["com"], d["cube"], d["uvd"][:, :J], fx=shape.fx,
+                          fy=shape.fy, targets="both")
+    g = torch.Generator(device=DEV).manual_seed(B * J + 1)
+    z = (torch.randn(B, J, 64, 64, device=DEV, generator=g) * 3).to(dtype)
+    D = torch.randn(B, J, 64, 64, device=DEV, generator=g).to(dtype)
+    w = None
+    if method == "softmax":
+        wv = rng.uniform(0.5, 1.5, (J, 1)).astype(np.float32)
+        wv[::5] *= -1.0
+        w = cu(wv)
+    L, m = batch.label_img, batch.mask
+    dense = (batch.heatmaps, batch.depthmaps, batch.uvd)
+    sparse = ops.SparseTargets(batch.taps, batch.uvd)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2            # half gradients: one rounding of a ~1e-6-different value
+    for targets in (dense, sparse):
+        for store_heat in (True, False):
+            H1, uvd1, gz1, gD1, gw1, lp1 = ops.decoder_fused_raw(z, w, D, L, m, targets, method, alpha,
+                                                                store_heat=store_heat)
+            H2, uvd2, st2, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
+            gz2, gD2, gw2, lp2 = ops.decoder_backward_raw(z, w, D, L, m, st2, uvd2, method=method, targets=targets,
+                                                          alpha=alpha, want_loss=True)
+            torch.cuda.synchronize()
+            assert (H1 is None) == (not store_heat)
+            if store_heat:
+                assert_close("H", H1.cpu().numpy(), H2.cpu().numpy(), 2e-6)
+            assert_close("uvd", uvd1.cpu().numpy(), uvd2.cpu().numpy(), 2e-6)
+            assert_close("loss partials", lp1.cpu().numpy(), lp2.cpu().numpy(), 1e-5)
+            assert_close("gz", gz1.float().cpu().numpy(), gz2.float().cpu().numpy(), tol)
+            assert_close("gD", gD1.float().cpu().numpy(), gD2.float().cpu().numpy(), tol)
+            if method == "softmax":
+                assert_close("gw", ops.reduce_partials(gw1).cpu().numpy(), ops.reduce_partials(gw2).cpu().numpy(), 2e-5)
+    # public criterion, both routes
+    outs = []
+    for one_pass in (True, False):
+        monkeypatch.setattr(ops, "ONE_PASS_LAST_STAGE", one_pass)
+        zz, DD = z.clone().requires_grad_(True), D.clone().requires_grad_(True)
+        ww = w.clone().requires_grad_(True) if w is not None else None
+        total, terms, uvd_o, H_o = ops.fused_decoder_loss(zz, ww, DD, L, m, batch.heatmaps, batch.depthmaps, batch.uvd,
+                                                          method, alpha)
+        total.backward()
+        outs.append((total.detach(), terms, uvd_o, zz.grad, DD.grad, ww.grad if ww is not None else None))
+    for a, b in zip(*outs):
+        if a is not None:
+            assert_close("criterion", a.float().cpu().numpy(), b.float().cpu().numpy(), tol)
+    # float64 oracle
+    t64 = lambda a: a.detach().cpu().to(torch.float64)
+    w64 = t64(w) if w is not None else None
+    p_ref, _, uvd_ref = do.decoder_forward(t64(z), w64, t64(D), t64(L), t64(m), method)
+    gz_ref, gD_ref, gw_ref = do.decoder_backward(t64(z), w64, t64(D), t64(L), t64(m), torch.zeros(B, J, 3, dtype=torch.float64),
+                                                 None, None, method, targets=tuple(t64(a) for a in dense), alpha=alpha)
+    H1, uvd1, gz1, gD1, gw1, lp1 = ops.decoder_fused_raw(z, w, D, L, m, dense, method, alpha)
+    assert_close("H vs oracle", H1.cpu().numpy(), p_ref.numpy())
+    assert_close("uvd vs oracle", uvd1.cpu().numpy(), uvd_ref.numpy())
+    if dtype == torch.float32:
+        assert_close("gz vs oracle", gz1.cpu().numpy(), gz_ref.numpy(), GRAD_RTOL)
+        assert_close("gD vs oracle", gD1.cpu().numpy(), gD_ref.numpy(), GRAD_RTOL)
+        if method == "softmax":
+            assert_close("gw vs oracle", ops.reduce_partials(gw1).view(-1, 1).cpu().numpy(), gw_ref.numpy(), GRAD_RTOL)

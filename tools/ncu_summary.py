@@ -38,7 +38,8 @@ METRICS = [
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
 ]
 UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
-ENTRY = {"sfr_build_kernel": "pwr_sfr_build", "decoder_fwd_kernel": "pwr_decoder_fwd",
+ENTRY = {"sfr_build_kernel": "pwr_sfr_build", "decoder_fused_kernel": "pwr_decoder_fwd_bwd_loss",
+         "decoder_fwd_kernel": "pwr_decoder_fwd",
          "decoder_bwd_pipe_kernel": "pwr_decoder_bwd_loss", "decoder_bwd_kernel": "pwr_decoder_bwd_loss"}
 
 
@@ -57,6 +58,7 @@ def main():
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     alg = {"pwr_sfr_build": roofline.sfr_build_bytes(args.joints) * args.batch,
+           "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(args.joints) * args.batch,
            "pwr_decoder_fwd": roofline.decoder_fwd_bytes(args.joints) * args.batch,
            "pwr_decoder_bwd_loss": roofline.decoder_bwd_bytes(args.joints) * args.batch}
     out_md = ["# ncu summary %s (`%s`, B=%d, J=%d)\n" % (args.tag, os.path.basename(args.report), args.batch, args.joints),
@@ -79,7 +81,7 @@ def main():
             wr = float(vals["dram__bytes_write.sum"][0]) * UNIT_SCALE[vals["dram__bytes_write.sum"][1]]
         except Exception:
             continue
-        if entry:
+        if entry and entry not in traffic:
             traffic[entry] = {"kernel": short, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                               "algorithmic_bytes_per_launch": alg[entry], "traffic_over_algorithmic": (rd + wr) / alg[entry],
                               "batch": args.batch, "joints": args.joints, "report": os.path.basename(args.report)}

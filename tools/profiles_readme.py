@@ -28,6 +28,8 @@ ev, evtot = bench["kernels"], bench["ms_per_step"]
 def entry(k):
     if "sfr_build_kernel" in k or "sfr_prep" in k:
         return "pwr_sfr_build"
+    if "decoder_fused_kernel" in k:
+        return "pwr_decoder_fwd_bwd_loss"
     if "decoder_fwd_kernel" in k:
         return "pwr_decoder_fwd"
     if "decoder_bwd" in k:
@@ -37,7 +39,7 @@ def entry(k):
 
 L = ["# profiles/ — round 1\n",
      "All captured under `gpurun` on one B200 (sm_100a), `bench.py` at its default workload (NYU shape, B = 4096, "
-     "J = 14, float32 frames, dense targets).\n",
+     "J = 14, float32 frames, dense targets; last stage in one pass = the product default).\n",
      "| file | what |", "|---|---|",
      "| `%s_bench_n1.json`, `%s_bench_n2.json`, `%s_bench_n4.json`, `%s_bench_n8.json` | the JSON line of `bench.py` at N = 1 / 2 / 4 / 8 (torchrun) |" % (tag, tag, tag, tag),
      "| `%s_bench_reference.json` | the JSON line of `bench.py --impl reference` (CPU oracle port) on the same box |" % tag,
@@ -70,15 +72,15 @@ L += ["",
       "| entry point | algorithmic bytes / launch | event-timed ms | achieved GB/s | frac of measured peak | DRAM traffic / algorithmic (ncu) |",
       "|---|---|---|---|---|---|"]
 tr = json.load(open(os.path.join(P, "traffic.json")))
-for e in ("pwr_sfr_build", "pwr_decoder_fwd", "pwr_decoder_bwd_loss"):
+for e in [e_ for e_ in ("pwr_sfr_build", "pwr_decoder_fwd_bwd_loss", "pwr_decoder_fwd", "pwr_decoder_bwd_loss") if e_ in ev]:
     L.append("| `%s` | %d | %.3f | %.0f | %.3f | %.2f |" % (e, ev[e]["algorithmic_bytes"], ev[e]["avg_ms"], ev[e]["achieved_gbs"],
                                                         ev[e]["frac"], tr[e]["traffic_over_algorithmic"]))
 L += ["",
       "Whole step: %d B/sample x 4096 / %.3f ms = %.0f GB/s = %.3f of measured peak (`step_roofline_frac`), %.2f M samples/s."
       % (bench["config"]["algorithmic_bytes_per_sample"], evtot, bench["config"]["algorithmic_bytes_per_sample"] * 4096 / evtot / 1e6,
          bench["step_roofline_frac"], bench["value"] / 1e6),
-      "The measured peak is a torch device-to-device copy; the pipelined backward (1-D bulk TMA into a shared-memory ring, "
-      "one persistent CTA per SM) moves its bytes slightly faster than that copy.",
+      "The measured peak is a torch device-to-device copy; the persistent kernels (1-D bulk TMA into a shared-memory ring, "
+      "one CTA per SM) move their bytes about as fast as that copy.",
       "`pwr_sfr_build` moves %.2fx its algorithmic bytes: the formula counts a 128x128 crop (0.27 GB) where the "
       "non-antialiased bilinear taps of a 176-352 px box touch every source pixel (1.0 GB); writes match the formula. "
       "Against its real DRAM traffic it runs at %.0f GB/s." % (tr["pwr_sfr_build"]["traffic_over_algorithmic"],
@@ -91,13 +93,16 @@ L += ["",
       "* `cpu_baseline` (oracle port, %d host cores): %.0f samples/s." % (bench["cpu_baseline"]["cores"], bench["cpu_baseline"]["value"]),
       "* `gpu_eager_decoder` (the reference's decoder + loss lines as eager PyTorch on the same GPU): %.2f ms vs %.2f ms fused = %.1fx."
       % (bench["gpu_eager_decoder"]["ms"], bench["gpu_eager_decoder"]["fused_ms"], bench["gpu_eager_decoder"]["speedup"]),
+      "* `two_kernel_step` (SURVEY 8d's accounting: forward kernel, then backward+loss kernel, %d B/sample): %.2f M samples/s, "
+      "%.3f ms/step, %.3f of the measured peak; its kernels: %s."
+      % (bench["two_kernel_step"]["algorithmic_bytes_per_sample"], bench["two_kernel_step"]["value"] / 1e6,
+         bench["two_kernel_step"]["ms_per_step"], bench["two_kernel_step"]["step_roofline_frac"],
+         ", ".join("`%s` %.3f ms (%.0f %%)" % (k, v["avg_ms"], 100 * v["frac"]) for k, v in bench["two_kernel_step"]["kernels"].items())),
       "* `sparse_targets` (compact 64-byte targets evaluated inside the loss kernel, reported separately as SURVEY 8d asks): "
       "%.2f M samples/s, %d B/sample." % (bench["sparse_targets"]["value"] / 1e6, bench["sparse_targets"]["algorithmic_bytes_per_sample"])]
 sp = bench["sparse_targets"]["kernels"]
-L.append("  Its kernels: lean SFR build (2 bands, no dense maps) %.3f ms, forward %.3f ms, lean backward "
-         "(`decoder_bwd_lean_kernel`, 2 CTAs/SM) %.3f ms = %.0f %% of the measured peak on its own algorithmic bytes."
-         % (sp["pwr_sfr_build"]["avg_ms"], sp["pwr_decoder_fwd"]["avg_ms"], sp["pwr_decoder_bwd_loss"]["avg_ms"],
-            100 * sp["pwr_decoder_bwd_loss"]["frac"]))
+L.append("  Its kernels: " + ", ".join("`%s` %.3f ms (%.0f %% of the measured peak on its own algorithmic bytes)"
+                                       % (k, v["avg_ms"], 100 * v["frac"]) for k, v in sp.items()) + ".")
 for n in (2, 4, 8):
     f = os.path.join(P, "%s_bench_n%d.json" % (tag, n))
     if os.path.isfile(f):

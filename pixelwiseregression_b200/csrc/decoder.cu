@@ -620,18 +620,20 @@ __device__ __forceinline__ float warp_sum5_scattered(const float (&v)[5]) {
     wv += __shfl_xor_sync(0xffffffffu, wv, 1);
     return wv;
 }
-// scratch layout [5][kFwdWarps]; lanes 0, 4, 8, 16, 20 hold value 0..4
+// scratch layout [5][NW]; lanes 0, 4, 8, 16, 20 hold value 0..4
+template <int NW = kFwdWarps>
 __device__ __forceinline__ void store_scattered5(float wv, float* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int idx = -1;
     if (lane == 0) idx = 0; else if (lane == 4) idx = 1; else if (lane == 8) idx = 2;
     else if (lane == 16) idx = 3; else if (lane == 20) idx = 4;
-    if (idx >= 0) scratch[idx * kFwdWarps + warp] = wv;
+    if (idx >= 0) scratch[idx * NW + warp] = wv;
 }
-__device__ __forceinline__ float sum_partials(const float* row) {      // kFwdWarps floats, fixed order
+template <int NW = kFwdWarps>
+__device__ __forceinline__ float sum_partials(const float* row) {      // NW floats, fixed order
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kFwdWarps / 4; ++i) {
+    for (int i = 0; i < NW / 4; ++i) {
         const float4 t = reinterpret_cast<const float4*>(row)[i];
         s += (t.x + t.y) + (t.z + t.w);
     }
@@ -1139,7 +1141,7 @@ constexpr int kFusedVec = kMap / 4 / kFusedThreads;
 constexpr int kFusedSlots = 6;
 constexpr int kFusedCtasPerSm = 2;
 constexpr int kFusedSmemBytes = kFusedSlots * kSlotBytes + 64;
-static_assert(kFusedThreads == kFwdThreads, "store_scattered5 / sum_partials are laid out for kFwdWarps warps");
+static_assert(kFusedWarps % 4 == 0, "per-warp partials are read as float4");
 static_assert(kFusedVec * 4 <= 32, "one z > 0 bit per pixel of a thread");
 
 struct FusedArgs {
@@ -1288,13 +1290,13 @@ decoder_fused_kernel(FusedArgs a) {
             accf[2] = fmaf(rowsum, ys, accf[2]);
         }
         float* sf = scr_f[k & 1];
-        store_scattered5(warp_sum5_scattered(accf), sf);
+        store_scattered5<kFusedWarps>(warp_sum5_scattered(accf), sf);
         __syncthreads();
-        const float inv_s = 1.f / sum_partials(sf);
-        const float den = fmaf(sum_partials(sf + 3 * kFusedWarps), inv_s, kEps);
-        const float dcoord = (sum_partials(sf + 4 * kFusedWarps) * inv_s) / den;
-        const float u = sum_partials(sf + kFusedWarps) * inv_s / 63.f;
-        const float v = sum_partials(sf + 2 * kFusedWarps) * inv_s / 63.f;
+        const float inv_s = 1.f / sum_partials<kFusedWarps>(sf);
+        const float den = fmaf(sum_partials<kFusedWarps>(sf + 3 * kFusedWarps), inv_s, kEps);
+        const float dcoord = (sum_partials<kFusedWarps>(sf + 4 * kFusedWarps) * inv_s) / den;
+        const float u = sum_partials<kFusedWarps>(sf + kFusedWarps) * inv_s / 63.f;
+        const float v = sum_partials<kFusedWarps>(sf + 2 * kFusedWarps) * inv_s / 63.f;
 
         // ---- loss on the coordinates: the upstream of the backward ----
         const float eu = u - sc[10], ev = v - sc[11], ed = dcoord - sc[12];
@@ -1358,14 +1360,14 @@ decoder_fused_kernel(FusedArgs a) {
         // next item's scalars: parked before the barrier below, read after it
         if (tid < 32 && it + 1 < last) scal[(k + 1) & 1][tid] = next_word;
         float* sb = scr_b[k & 1];
-        store_scattered5(warp_sum5_scattered(acc), sb);
+        store_scattered5<kFusedWarps>(warp_sum5_scattered(acc), sb);
         __syncthreads();
         // every thread is past its shared-memory reads of this item: its slots go back to the FIFO
         if (tid == 0) fill((k + 1) * lpi + kFusedSlots);
         if (++j_cur == a.J) { j_cur = 0; ++b_cur; }
         if (METHOD == PWR_METHOD_SOFTMAX && it + 1 < last) w_next = a.w[j_cur];
 
-        const float s1 = sum_partials(sb);
+        const float s1 = sum_partials<kFusedWarps>(sb);
         if (a.gz != nullptr) {
 #pragma unroll
             for (int i = 0; i < kFusedVec; ++i) {
@@ -1384,10 +1386,10 @@ decoder_fused_kernel(FusedArgs a) {
             float* o = a.uvd + static_cast<size_t>(it) * 3;
             o[0] = u; o[1] = v; o[2] = dcoord;
             if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr)
-                a.gw_partial[it] = sum_partials(sb + 3 * kFusedWarps) - s1 * sum_partials(sb + 4 * kFusedWarps);
+                a.gw_partial[it] = sum_partials<kFusedWarps>(sb + 3 * kFusedWarps) - s1 * sum_partials<kFusedWarps>(sb + 4 * kFusedWarps);
             if (a.loss_partial != nullptr) {
-                a.loss_partial[it * 3 + 0] = sum_partials(sb + kFusedWarps);
-                a.loss_partial[it * 3 + 1] = sum_partials(sb + 2 * kFusedWarps);
+                a.loss_partial[it * 3 + 0] = sum_partials<kFusedWarps>(sb + kFusedWarps);
+                a.loss_partial[it * 3 + 1] = sum_partials<kFusedWarps>(sb + 2 * kFusedWarps);
                 a.loss_partial[it * 3 + 2] = lu;
             }
         }

@@ -3,12 +3,14 @@
 #   gpurun --timeout 1500 -- 'bash tools/capture_profiles.sh r1'
 # then, back in the container:
 #   bash tools/capture_profiles.sh r1 --collect
+# gpurun brings back at most 64 MiB and every report embeds the 12 MB module: reports travel gzipped.
 # Numbers printed by runs under ncu are never benchmark values; the bench lines come from the two
 # un-profiled runs at the top.
 TAG=${1:-r1}
 OUT=gpurun_out
 LEAN="--no-e2e --no-sparse --no-gpu-eager --no-cpu-baseline"
 if [ "$2" == "--collect" ]; then
+    for f in $OUT/prof_${TAG}_*.ncu-rep.gz; do gunzip -kf $f; done
     cp $OUT/${TAG}_bench_n1.json $OUT/${TAG}_bench_reference.json $OUT/${TAG}_launches.csv profiles/
     python tools/ncu_summary.py $OUT/prof_${TAG}_step.ncu-rep --tag $TAG
     python tools/ncu_summary.py $OUT/prof_${TAG}_two.ncu-rep --tag $TAG --append "two-kernel route of the last stage (SURVEY 8d accounting): forward kernel, backward+loss kernel"
@@ -36,6 +38,7 @@ ncu --set full --clock-control none --import-source on -k regex:'sfr_build_kerne
 # inference pass of tools/sweep_inference.py
 ncu --set full --clock-control none --import-source on -k regex:'sfr_build_kernel|decoder_fwd_pipe_kernel' \
     --launch-skip 4 -c 2 -o $OUT/prof_${TAG}_infer -f python tools/sweep_inference.py --batches 4096 --steps 2 --warmup 1 > $OUT/ncu_infer.log 2>&1
+gzip -f -9 $OUT/prof_${TAG}_*.ncu-rep
 python tools/sweep_inference.py > $OUT/${TAG}_sweep_hand17_n1.txt 2> $OUT/sweep.err
 tail -1 $OUT/${TAG}_bench_n1.json | cut -c1-400
 for f in ncu_step ncu_two ncu_lean ncu_infer; do tail -n 2 $OUT/$f.log; done

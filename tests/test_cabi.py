@@ -68,6 +68,17 @@ def test_argument_errors_without_a_gpu(lib):
     assert lib.pwr_reduce_partials(null, fake, 1, 1, 1, null) == -1
     # B == 0 is a successful no-op
     assert lib.pwr_decoder_fwd(fake, fake, fake, fake, fake, null, null, null, null, fake, fake, fake, null, 0, 14, 0, 0, null) == 0
+    # one-pass last stage: (z, w, D, L, m, heat_gt, dmap_gt, uvd_gt, taps, alpha, lambda_h, lambda_d, loss_scale,
+    #                       loss_scale_dev, n_mean, H, uvd, gz, gD, gw_partial, loss_partial, B, J, method, dtype, stream)
+    fused = lambda **kw: lib.pwr_decoder_fwd_bwd_loss(
+        kw.get("z", fake), fake, kw.get("D", fake), fake, fake, kw.get("heat", fake), fake, kw.get("uvd_gt", fake),
+        kw.get("taps", null), 1.0, 1.0, 0.01, 1.0, null, 0, fake, fake, fake, fake, fake, fake, kw.get("B", 1), 14,
+        kw.get("method", 0), 0, null)
+    assert fused(z=null) == -1 and fused(D=null) == -1 and fused(uvd_gt=null) == -1      # depth branch is mandatory
+    assert fused(heat=null) == -1                        # dense targets missing and no taps either
+    assert fused(z=odd) == -3
+    assert fused(method=2) == -4                         # PWR_METHOD_GIVEN has no last-stage loss
+    assert fused(B=-1) == -2 and fused(B=0) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -233,6 +233,54 @@ def golden_raw(datasets, name, shape, frame_format, margin, batch, seed, val_mod
     print(name, "valid", res["ref_valid"].tolist(), "cubes", sorted(set(cubes)))
 
 
+def golden_bb(datasets, name, batch, seed):
+    """HAND17 `process_mode='bb'` (datasets.py:199-206, 974-996): the reference's own load_from_text_bb
+    (plt.imread replaced by its documented conversion, as in golden_raw) and the bb branch of its
+    process_single_data (test-only; CoM and cube from the fallback)."""
+    from oracle import sfr_oracle as so
+    shape = synth.HAND17
+    d = synth.make_frames(shape, batch, seed, mixed_cube=False)
+    raw = np.clip(np.rint(d["frames"]), 0, 65535).astype(np.uint16)
+    rng = np.random.default_rng(seed)
+    # clutter behind the hand inside the box (what the two-pass mean + 100 mm rule removes) and a far wall
+    for b in range(batch):
+        wall = rng.uniform(size=raw[b].shape) < 0.02
+        raw[b][wall & (raw[b] == 0)] = np.uint16(d["com"][b, 2] + 400)
+    boxes = []
+    for b in range(batch):
+        u, v, z = d["com"][b]
+        half = 0.9 * shape.cube / z * shape.fx
+        boxes.append([u - half + rng.uniform(-3, 3), v - half + rng.uniform(-3, 3), 2 * half + 0.5, 2 * half + 1.25])
+    boxes = np.array(boxes)
+    store = {}
+    old_imread = getattr(datasets.plt, "imread", None)
+    datasets.plt.imread = lambda path: so.imread_float(store[path])
+    try:
+        ds = object.__new__(datasets.HAND17Dataset)      # file-reading constructor bypassed: only I/O is replaced
+        ds.fx, ds.fy, ds.halfu, ds.halfv = shape.fx, shape.fy, shape.halfu, shape.halfv
+        ds.path, ds.cube_size, ds.process_mode, ds.test_only = "/synthetic", int(shape.cube), "bb", True
+        ds.image_size, ds.label_size, ds.kernel_size, ds.sigmoid, ds.joint_number = 128, 64, 7, 1.5, shape.joints
+        ds.using_rotation = ds.using_scale = ds.using_shift = ds.using_flip = False
+        frames64, outs = [], []
+        for b in range(batch):
+            rel = "image_D%08d.png" % (b + 1)
+            store[os.path.join(ds.path, "frame", "images", rel)] = raw[b]
+            text = rel + " " + " ".join(repr(float(x)) for x in boxes[b])
+            frames64.append(ds.load_from_text_bb(text))
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                tup = ds.process_single_data(text)
+            outs.append([t.numpy() for t in tup])
+    finally:
+        datasets.plt.imread = old_imread
+    names = FIELDS[:6]
+    res = {"ref_" + n: np.stack([o[i] for o in outs]) for i, n in enumerate(names)}
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), raw=raw, boxes=boxes, ref_frames=np.stack(frames64),
+                        shape_name=np.array(shape.name), versions=versions(), **res)
+    print(name, "box sizes", res["ref_box_size"].tolist(), "com z", res["ref_com"][:, 2].tolist())
+
+
 def golden_augmented(datasets, name, shape, batch, seed, spread=0.6):
     """The reference's augmented branch (datasets.py:216-299, train.py's default flags) with
     `random.random` replaced by a recorded sequence, so the draws can be replayed on the GPU."""
@@ -393,6 +441,7 @@ def main():
     golden_decoder(model_mod, "decoder_softmax_a05_up", "softmax", 2, 3, 11, 0.5, True)
     golden_decoder(model_mod, "decoder_sum_a05_up", "sum", 2, 3, 12, 0.5, True)
     golden_model(model_mod, datasets, "model_nyu_eval", synth.NYU, 6, 40)
+    golden_bb(datasets, "sfr_hand17_bb", 3, 50)
 
 
 if __name__ == "__main__":

@@ -141,6 +141,24 @@ def decode_u16(grey_u16):
     return imread_float(grey_u16) * 65535
 
 
+def load_bb(grey_u16, ustart, vstart, du, dv):
+    """HAND17 `process_mode='bb'` loader, datasets.py:974-996 (test frames that come with a bounding
+    box instead of joint annotations): keep the box, then drop everything deeper than 100 mm behind
+    the mean depth of what is left, in two passes.  `MM = np.zeros(image.shape)` is float64, so the
+    frame the reference carries on is float64 (like MSRA); CoM and cube then come from the fallback of
+    process_single_data (datasets.py:203-214)."""
+    image = decode_u16(grey_u16)
+    mm = np.zeros(image.shape)
+    mm[int(vstart):int(vstart + dv), int(ustart):int(ustart + du)] = 1
+    image = image * mm
+    mean = np.mean(image[image > 0])
+    first = image.copy()
+    first[first > mean + 100] = 0
+    mean = np.mean(first[first > 0])
+    image[image > mean + 100] = 0
+    return image
+
+
 def prefilter(image, com, cube, fx, fy, halfu, halfv, margin):
     """The hand rectangle + depth window of load_from_text (NYU datasets.py:841-857 with
     margin 40, HAND17 :956-972 margin 40, ICVL :666-681 margin 30).  Python slice

@@ -231,3 +231,19 @@ def test_full_batch_properties():
     again = sfr.build_sfr(d["frames"], d["com"], d["cube"], d["uvd"], fx=shape.fx, fy=shape.fy)
     for a, b in zip(out, again):
         assert (a is None and b is None) or torch.equal(a, b)
+
+
+def test_gpu_hand17_bb_frames_match_reference_golden():
+    """Frames of the HAND17 bounding-box loader (float64 upstream, integer-valued, so exact in float32) through
+    the GPU builder with the float64 image path and the centre-of-mass fallback on 480x640 frames, against the
+    reference's `process_mode='bb'` branch.  (The bounding-box filter itself is host-side, see oracle.load_bb.)"""
+    g = load_golden("sfr_hand17_bb")
+    shape = golden_shape(g)
+    frames32 = g["ref_frames"].astype(np.float32)
+    assert np.array_equal(frames32.astype(np.float64), g["ref_frames"])
+    out = sfr.build_sfr(torch.from_numpy(frames32).cuda(), None, float(shape.cube), fx=shape.fx, fy=shape.fy,
+                        frame_f64=True, test_only=True)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS[:6]}
+    assert_sfr_matches(got, ref, SFR_FIELDS[:6], np.ones(len(frames32), np.uint8), prefix="bb:")

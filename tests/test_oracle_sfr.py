@@ -178,3 +178,18 @@ def test_oracle_matches_live_reference(shape_name, batch, seed):
     got = so.process_batch(frames, d["uvd"], None if shape.com_from_frame else d["com"], d["cube"],
                            shape.fx, shape.fy)
     assert_sfr_matches(got, {n: ref["ref_" + n] for n in SFR_FIELDS}, SFR_FIELDS, ref["ref_valid"])
+
+
+def test_hand17_bb_mode_matches_reference_golden():
+    """HAND17 `process_mode='bb'` (datasets.py:199-206, 974-996): the oracle's bounding-box loader equals the
+    reference's load_from_text_bb bit for bit (a float64 frame), and the test-only SFR with the CoM / cube
+    fallback equals the reference's bb branch of process_single_data."""
+    g = load_golden("sfr_hand17_bb")
+    shape = golden_shape(g)
+    frames = np.stack([so.load_bb(g["raw"][b], *g["boxes"][b]) for b in range(len(g["raw"]))])
+    assert frames.dtype == np.float64 and np.array_equal(frames, g["ref_frames"])
+    assert (frames[0] > 0).sum() < (so.decode_u16(g["raw"][0]) > 0).sum()          # the filter removed the clutter
+    cube = np.full(len(frames), float(shape.cube))
+    got = so.process_batch(frames, None, None, cube, shape.fx, shape.fy, test_only=True)
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS[:6]}
+    assert_sfr_matches(got, ref, SFR_FIELDS[:6], np.ones(len(frames), np.uint8), prefix="bb:")

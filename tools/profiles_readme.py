@@ -48,7 +48,9 @@ L = ["# profiles/ — round 1\n",
      "| `traffic.json` | DRAM bytes per launch from that capture (read by `bench.py` -> `roofline.traffic`) |",
      "| `%s_sweep_hand17_n1.txt` | `tools/sweep_inference.py`: BASELINE configs[4] inference sweep (HAND17 shape, batch 256 .. 16384) |" % tag,
      "| `../tools/capture_profiles.sh` | the exact commands behind all of the above |",
-     "| `%s_sanitizer_*.log` | `compute-sanitizer` memcheck / racecheck over the GPU parity tests: 0 errors, 0 hazards |" % tag,
+     "| `%s_sanitizer_*.log` | `compute-sanitizer` memcheck (89 tests) / racecheck (47 tests) over the GPU parity tests: 0 errors, 0 hazards "
+     "(taken before the one-pass last-stage kernel was added; `decoder_fused_kernel` shares its ring / barrier scheme with the "
+     "pipelined forward and lean backward that were checked, but has not been run under the sanitizer itself) |" % tag,
      "",
      "## Share of the step: ncu launch list (cold, serialised) vs CUDA events inside bench.py\n",
      "| kernel | ncu us | ncu share | bench events ms (entry point) | bench share |", "|---|---|---|---|---|"]
@@ -80,7 +82,7 @@ L += ["",
       % (bench["config"]["algorithmic_bytes_per_sample"], evtot, bench["config"]["algorithmic_bytes_per_sample"] * 4096 / evtot / 1e6,
          bench["step_roofline_frac"], bench["value"] / 1e6),
       "The measured peak is a torch device-to-device copy; the persistent kernels (1-D bulk TMA into a shared-memory ring, "
-      "one CTA per SM) move their bytes about as fast as that copy.",
+      "one to three CTAs per SM) move their bytes about as fast as that copy.",
       "`pwr_sfr_build` moves %.2fx its algorithmic bytes: the formula counts a 128x128 crop (0.27 GB) where the "
       "non-antialiased bilinear taps of a 176-352 px box touch every source pixel (1.0 GB); writes match the formula. "
       "Against its real DRAM traffic it runs at %.0f GB/s." % (tr["pwr_sfr_build"]["traffic_over_algorithmic"],

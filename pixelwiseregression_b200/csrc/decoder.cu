@@ -1,4 +1,4 @@
-// Fused differentiable decoder for sm_100a: forward, backward, backward+loss.
+// Fused differentiable decoder for sm_100a: forward, backward, backward+loss, and the one-pass last stage.
 //
 // Replaces the ~16 ATen launches per stage of the reference
 //   model.py:79-97   PlaneRegression.forward (post-conv): softmax / relu-sum
@@ -7,11 +7,25 @@
 //                    weighted depth
 //   model.py:151     cat -> uvd
 //   train.py:197-207 stage loss and everything autograd derives from the above
-// by ONE forward and ONE backward kernel.  Work unit = one (sample, joint)
-// pair = one 64x64 logit map + one 64x64 depth map; one CTA of 256 threads
-// per unit, 16 pixels (four 128-bit accesses) per thread per map, so every
-// map crosses HBM exactly once.  No tensor cores: nothing here is a
-// contraction; the bound is HBM bandwidth.
+// by ONE forward and ONE backward kernel - or, for the last stage, one kernel for
+// both.  Work unit ("item") = one (sample, joint) pair = one 64x64 logit map + one
+// 64x64 depth map, 16 pixels (four 128-bit accesses) per thread per map at 256
+// threads, so every map crosses HBM exactly once.  No tensor cores: nothing here is
+// a contraction; the bound is HBM bandwidth.
+//
+// Kernels (which one an entry point launches is decided in the extern "C" functions
+// at the end of the file; DESIGN.md section 4 has the measurements behind each):
+//   decoder_fwd_kernel       one CTA per item; forward with the heat-map store, with
+//                            or without the loss riding along (inner stages)
+//   decoder_fwd_pipe_kernel  persistent, 3 CTAs/SM, bulk-TMA ring; forward WITHOUT the
+//                            heat-map store (inference, last stage)
+//   decoder_bwd_pipe_kernel  persistent, 1 CTA/SM, 2 x 64 KB stages; backward(+loss)
+//                            with dense targets or dense upstream gradients
+//   decoder_bwd_lean_kernel  persistent, 2 CTAs/SM; backward(+loss) with no dense map
+//                            beyond z, D (compact targets, uvd-only loss)
+//   decoder_bwd_kernel       one CTA per item; the configurations nothing else takes
+//   decoder_fused_kernel     persistent, 2 CTAs/SM, six-slot FIFO ring; last stage
+//                            forward + loss + backward in one pass
 //
 // Pixel mapping: chunk c = tid + 256*i (i = 0..3) covers pixels 4c..4c+3,
 // i.e. column x = 4*(tid & 15) + k and row y = (tid >> 4) + 16*i.  The

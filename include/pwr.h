@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PWR_VERSION 100          /* 0.1.0 */
+#define PWR_VERSION 200          /* 0.2.0: bumped on every ABI change; the binding asserts it */
 
 #define PWR_LABEL_SIZE 64
 #define PWR_IMAGE_SIZE 128
@@ -60,6 +60,19 @@ extern "C" {
 
 int pwr_version(void);
 const char* pwr_error_string(int rc);
+
+/* Dispatch overrides for A/B measurements and for tests that compare two kernels of
+ * the same entry point (process-wide, atomic; 0 = default heuristics).  Nothing on
+ * the launch path reads the environment.  Returns the previous value, or
+ * PWR_E_METHOD for an unknown option. */
+#define PWR_OPT_BWD_DIRECT  0   /* 1: one-CTA-per-item backward instead of the pipelined ones   */
+#define PWR_OPT_FWD_DIRECT  1   /* 1: one-CTA-per-item forward even without the heat-map store  */
+#define PWR_OPT_FWD_PIPE    2   /* 1: pipelined forward even with the heat-map store            */
+#define PWR_OPT_BWD_NO_LEAN 3   /* 1: 1-CTA/SM pipelined backward where the lean one would run  */
+#define PWR_OPT_SFR_GATHER  4   /* 1: SFR build gathers its taps from HBM instead of staging the
+                                      source rows in shared memory                               */
+#define PWR_OPT_COUNT       5
+int pwr_set_option(int option, int value);
 
 /* ------------------------------------------------------------------------ *
  * SFR target builder

@@ -421,9 +421,35 @@ def golden_model(model_mod, datasets, name, shape, B, seed, features=32, level=2
     print(name, "params", n_par, "uvd[0,0]", results[-1][2][0, 0].tolist())
 
 
+STATE_DICT_SPECS = {
+    # name -> (reference class, constructor kwargs): the module trees whose state_dict layout the drop-in
+    # model.py must reproduce key for key (released checkpoints load through utils.py:309-314)
+    "nyu_instance": ("PixelwiseRegression", dict(joints=14, stage=2, features=128, level=4, norm_method="instance")),
+    "msra_batch_sum": ("PixelwiseRegression", dict(joints=21, stage=2, features=64, level=2, norm_method="batch",
+                                                   heatmap_method="sum")),
+    "fullregression_nyu": ("FullRegression", dict(joints=14, stage=2, features=64, level=2, norm_method="instance")),
+}
+
+
+def golden_state_dict_keys(model_mod):
+    """tests/golden/state_dict_keys.json: [key, shape] lists of the reference's own modules."""
+    import json
+    spec = {}
+    for name, (cls, kwargs) in STATE_DICT_SPECS.items():
+        net = getattr(model_mod, cls)(**kwargs)
+        spec[name] = {"class": cls, "kwargs": kwargs,
+                      "keys": [[k, list(v.shape)] for k, v in net.state_dict().items()]}
+        print("state_dict", name, len(spec[name]["keys"]), "entries")
+    with open(os.path.join(GOLDEN, "state_dict_keys.json"), "w") as f:
+        json.dump(spec, f)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     model_mod, _, datasets = ref_shim.load()
+    golden_state_dict_keys(model_mod)
+    if sys.argv[1:] == ["--state-dict-only"]:
+        return
     golden_sfr(datasets, "sfr_nyu", synth.NYU, 4, 0)
     golden_sfr(datasets, "sfr_nyu_test_only", synth.NYU, 2, 5, test_only=True)
     golden_sfr(datasets, "sfr_hand17", synth.HAND17, 2, 1)

@@ -29,6 +29,7 @@ _SZ = ctypes.c_size_t
 SIGNATURES = {
     "pwr_version": [],
     "pwr_error_string": [_I],
+    "pwr_set_option": [_I, _I],
     "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
     "pwr_sfr_workspace_bytes": [_I, _I],
     "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
@@ -45,6 +46,12 @@ SIGNATURES = {
     "pwr_joint_error": [_P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _I, _I, _P],
 }
 
+ABI_VERSION = 200      # PWR_VERSION of include/pwr.h this binding is written against
+OPTIONS = {"bwd_direct": 0, "fwd_direct": 1, "fwd_pipe": 2, "bwd_no_lean": 3, "sfr_gather": 4}
+_ENV_OPTIONS = {"PWR_BWD_DIRECT": ("bwd_direct", "1"), "PWR_FWD_DIRECT": ("fwd_direct", "1"),
+                "PWR_FWD_PIPE": ("fwd_pipe", "1"), "PWR_BWD_LEAN": ("bwd_no_lean", "0"),
+                "PWR_SFR_GATHER": ("sfr_gather", "1")}
+
 _lib = None
 
 
@@ -57,13 +64,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH) and "PWR_LIB_PATH" not in os.environ:
-        try:                                   # a fresh checkout: compile once (needs nvcc), never fall back
-            from . import build as _build
-            _build.build()
-        except Exception as exc:
-            raise PwrError("libpwr_b200.so not found at %s and building it failed (%s): run `python -m "
-                           "pixelwiseregression_b200.build` (there is no CPU fallback)" % (LIB_PATH, exc))
+    if "PWR_LIB_PATH" not in os.environ:
+        from . import build as _build
+        if _build.needs_build():               # missing, or built from other sources (stale ABI): compile, never fall back
+            try:
+                _build.build()
+            except Exception as exc:
+                raise PwrError("libpwr_b200.so at %s is missing or stale and building it failed (%s): run `python "
+                               "-m pixelwiseregression_b200.build` (there is no CPU fallback)" % (LIB_PATH, exc))
     if not os.path.isfile(LIB_PATH):
         raise PwrError(
             "libpwr_b200.so not found at %s: build it with `python -m pixelwiseregression_b200.build` "
@@ -73,8 +81,39 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = {"pwr_error_string": ctypes.c_char_p, "pwr_sfr_workspace_bytes": _SZ}.get(name, _I)
+    if lib.pwr_version() != ABI_VERSION:
+        raise PwrError("libpwr_b200.so at %s has ABI version %d, this binding is written for %d: rebuild it with "
+                       "`python -m pixelwiseregression_b200.build --force`" % (LIB_PATH, lib.pwr_version(), ABI_VERSION))
+    # dispatch overrides: the environment is read here, once, never on the launch path
+    for env, (opt, on) in _ENV_OPTIONS.items():
+        val = os.environ.get(env)
+        if val is not None:
+            lib.pwr_set_option(OPTIONS[opt], 1 if val[:1] == on else 0)
     _lib = lib
     return lib
+
+
+def set_option(name, value):
+    """Dispatch override of include/pwr.h (A/B measurements, tests): returns the previous value."""
+    prev = load().pwr_set_option(OPTIONS[name], int(value))
+    if prev < 0:
+        raise PwrError("unknown option %r" % (name,))
+    return prev
+
+
+class option:
+    """`with _lib.option("bwd_no_lean", 1): ...` — scoped dispatch override."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.prev = set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.prev)
+        return False
 
 
 LAUNCHES = {}          # entry point -> number of kernels launched through it

@@ -5,6 +5,7 @@
 The library is a plain C-ABI shared object (include/pwr.h) loaded with ctypes,
 so it travels to the GPU box with the repo snapshot.
 """
+import hashlib
 import os
 import shutil
 import subprocess
@@ -27,12 +28,25 @@ def find_nvcc():
     raise RuntimeError("nvcc not found; libpwr_b200.so cannot be built")
 
 
+STAMP = LIB + ".stamp"
+
+
+def source_digest():
+    """sha256 over the sources, headers and flags the library is built from.  The stamp written next to
+    the .so travels with it (gpurun snapshot), so a stale library is detected by content, not by mtimes
+    (which a snapshot copy does not preserve)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.isfile(LIB):
+    if not os.path.isfile(LIB) or not os.path.isfile(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
@@ -48,6 +62,8 @@ def build(force=False, verbose=False):
         print(res.stderr)
     with open(os.path.join(PKG, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_digest() + "\n")
     return LIB
 
 

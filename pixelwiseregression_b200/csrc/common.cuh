@@ -1,5 +1,6 @@
 // Shared device helpers for libpwr_b200 (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/pwr.h"
@@ -20,6 +21,31 @@ static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_
 #define PWR_OPTIONAL_PTR(p) do { if ((p) != nullptr && pwr::misaligned(p)) return PWR_E_ALIGN; } while (0)
 
 static inline int launch_status() { return static_cast<int>(cudaGetLastError()); }
+
+// ---- per-device facts, looked up once ----------------------------------------
+// The launch path must not pay a driver query per call (at batch 128-256 the kernels last tens of
+// microseconds): the SM count is cached per device, and the dynamic-shared-memory opt-in of a kernel is
+// made once per (kernel instantiation, device).  Benign race: two threads may both query / set once.
+static inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+static inline int sm_count(int dev) {
+    static std::atomic<int> cache[64];
+    const bool cached = dev >= 0 && dev < 64;
+    if (cached) { const int v = cache[dev].load(std::memory_order_relaxed); if (v > 0) return v; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if (cached) cache[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
+#define PWR_ENSURE_DYN_SMEM(bytes, dev, ...)                                                               \
+    do {                                                                                                   \
+        static std::atomic<unsigned long long> done_{0ull};                                                \
+        const unsigned long long bit_ = 1ull << ((dev) & 63);                                              \
+        if (!(done_.load(std::memory_order_acquire) & bit_)) {                                             \
+            cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes));       \
+            done_.fetch_or(bit_, std::memory_order_release);                                               \
+        }                                                                                                  \
+    } while (0)
 
 // ---- memory access with cache hints ----------------------------------------
 // Streams that are touched exactly once (logits in, gradients out) use the

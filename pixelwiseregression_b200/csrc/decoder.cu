@@ -32,7 +32,7 @@
 // coordinate filter of utils.py:24-35 (U = (x-32)/63, V = (y-32)/63) is
 // synthesised from the indices: sums are taken over the integer offsets
 // (x-32), (y-32) and scaled by 1/63 once.
-#include <cstdlib>
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -1615,27 +1615,14 @@ decoder_bwd_lean_kernel(PipeArgs a) {
     }
 }
 
-// PWR_BWD_DIRECT=1 forces the direct-load backward (A/B measurements, tests of both paths).
-static bool force_direct_bwd() {
-    const char* e = getenv("PWR_BWD_DIRECT");
-    return e != nullptr && e[0] == '1';
-}
-// PWR_FWD_DIRECT=1 forces the one-CTA-per-item forward, PWR_FWD_PIPE=1 the pipelined one also when
-// the heat maps are stored (A/B measurements, tests of both paths).
-static bool force_direct_fwd() {
-    const char* e = getenv("PWR_FWD_DIRECT");
-    return e != nullptr && e[0] == '1';
-}
-static bool force_pipe_fwd() {
-    const char* e = getenv("PWR_FWD_PIPE");
-    return e != nullptr && e[0] == '1';
-}
-// PWR_BWD_LEAN=0 sends the configurations without dense target / upstream maps through the
-// one-CTA-per-SM pipelined backward instead of the lean one.
-static bool no_lean_bwd() {
-    const char* e = getenv("PWR_BWD_LEAN");
-    return e != nullptr && e[0] == '0';
-}
+// Dispatch overrides (A/B measurements, tests of both variants of a kernel): process-wide atomics set
+// through pwr_set_option.  Nothing on the launch path reads the environment; the Python binding
+// translates PWR_BWD_DIRECT / PWR_FWD_DIRECT / PWR_FWD_PIPE / PWR_BWD_LEAN once, when it loads the library.
+static std::atomic<int> g_options[PWR_OPT_COUNT] = {};
+static bool force_direct_bwd() { return g_options[PWR_OPT_BWD_DIRECT].load(std::memory_order_relaxed) != 0; }
+static bool force_direct_fwd() { return g_options[PWR_OPT_FWD_DIRECT].load(std::memory_order_relaxed) != 0; }
+static bool force_pipe_fwd() { return g_options[PWR_OPT_FWD_PIPE].load(std::memory_order_relaxed) != 0; }
+static bool no_lean_bwd() { return g_options[PWR_OPT_BWD_NO_LEAN].load(std::memory_order_relaxed) != 0; }
 static bool bad_method(int method) {
     return method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM && method != PWR_METHOD_GIVEN;
 }
@@ -1696,14 +1683,12 @@ extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, con
     if (loss_mode == LOSS_NONE && D != nullptr && (H == nullptr || force_pipe_fwd()) && !force_direct_fwd()) {
         FwdPipeArgs a;
         a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.H = H; a.uvd = uvd; a.stats = stats; a.J = J; a.items = B * J;
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int dev = current_device(), sms = sm_count(dev);
         const int grid = a.items < sms * kFwdCtasPerSm ? a.items : sms * kFwdCtasPerSm;
 #define PWR_LAUNCH_FWD_PIPE(M, TZ)                                                                            \
     do {                                                                                                      \
-        cudaFuncSetAttribute(decoder_fwd_pipe_kernel<M, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                             kFwdSmemBytes);                                                                  \
+        PWR_ENSURE_DYN_SMEM(kFwdSmemBytes, dev, decoder_fwd_pipe_kernel<M, TZ>);    \
+                                                                  \
         decoder_fwd_pipe_kernel<M, TZ><<<grid, kFwdThreads, kFwdSmemBytes, s>>>(a);                            \
     } while (0)
         if (method == PWR_METHOD_GIVEN) PWR_LAUNCH_FWD_PIPE(PWR_METHOD_GIVEN, float);
@@ -1762,15 +1747,13 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
         a.uvd_gt = uvd_gt; a.taps = taps; a.coef = coef; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial;
         a.loss_partial = loss_partial; a.J = J; a.items = B * J;
         a.slots_are_targets = need_targets ? 1 : 0;
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int dev = current_device(), sms = sm_count(dev);
         if (lean) {
             const int lean_grid = a.items < sms * kLeanCtasPerSm ? a.items : sms * kLeanCtasPerSm;
 #define PWR_LAUNCH_LEAN(M, LS, TZ)                                                                             \
     do {                                                                                                       \
-        cudaFuncSetAttribute(decoder_bwd_lean_kernel<M, LS, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             kLeanSmemBytes);                                                                  \
+        PWR_ENSURE_DYN_SMEM(kLeanSmemBytes, dev, decoder_bwd_lean_kernel<M, LS, TZ>);    \
+                                                                  \
         decoder_bwd_lean_kernel<M, LS, TZ><<<lean_grid, kLeanThreads, kLeanSmemBytes, s>>>(a);                 \
     } while (0)
             PWR_DISPATCH(PWR_LAUNCH_LEAN);
@@ -1780,8 +1763,8 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
         const int grid = a.items < sms ? a.items : sms;
 #define PWR_LAUNCH_PIPE(M, LS, TZ)                                                                             \
     do {                                                                                                       \
-        cudaFuncSetAttribute(decoder_bwd_pipe_kernel<M, LS, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             kPipeSmemBytes);                                                                  \
+        PWR_ENSURE_DYN_SMEM(kPipeSmemBytes, dev, decoder_bwd_pipe_kernel<M, LS, TZ>);    \
+                                                                  \
         decoder_bwd_pipe_kernel<M, LS, TZ><<<grid, kPipeThreads, kPipeSmemBytes, s>>>(a);                      \
     } while (0)
         PWR_DISPATCH(PWR_LAUNCH_PIPE);
@@ -1856,14 +1839,12 @@ extern "C" int pwr_decoder_fwd_bwd_loss(const void* z, const float* w, const voi
     a.J = J; a.items = B * J;
     const bool sparse = a.taps != nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int dev = current_device(), sms = sm_count(dev);
     const int grid = a.items < sms * kFusedCtasPerSm ? a.items : sms * kFusedCtasPerSm;
 #define PWR_LAUNCH_FUSED(M, LS, TZ)                                                                          \
     do {                                                                                                     \
-        cudaFuncSetAttribute(decoder_fused_kernel<M, LS, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                             kFusedSmemBytes);                                                               \
+        PWR_ENSURE_DYN_SMEM(kFusedSmemBytes, dev, decoder_fused_kernel<M, LS, TZ>);    \
+                                                               \
         decoder_fused_kernel<M, LS, TZ><<<grid, kFusedThreads, kFusedSmemBytes, s>>>(a);                     \
     } while (0)
 #define PWR_FUSED_TZ(M, LS)                                                                                  \
@@ -1904,7 +1885,8 @@ extern "C" int pwr_scale_inplace(void* x, const float* scale_dev, long long n, i
     if (scale_dev == nullptr) return PWR_E_NULL;
     const long long n4 = n / 4;
     long long blocks = (n4 + kThreads - 1) / kThreads;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    const long long cap = static_cast<long long>(sm_count(current_device())) * 16;
+    if (blocks > cap) blocks = cap;
     const unsigned g = static_cast<unsigned>(blocks);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (map_dtype == PWR_DTYPE_F32)       scale_inplace_kernel<float><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
@@ -1942,6 +1924,12 @@ extern "C" int pwr_joint_error(const float* uvd_pred, const float* uvd_true, con
 }
 
 extern "C" int pwr_version(void) { return PWR_VERSION; }
+
+extern "C" int pwr_set_option(int option, int value) {
+    if (option < 0 || option >= PWR_OPT_COUNT) return PWR_E_METHOD;
+    return g_options[option].exchange(value, std::memory_order_relaxed);
+}
+namespace pwr { int get_option(int option) { return g_options[option].load(std::memory_order_relaxed); } }
 
 extern "C" const char* pwr_error_string(int rc) {
     switch (rc) {

@@ -55,6 +55,22 @@ def _regression_head(features, joints, kernel_size, norm, inplace):
     return torch.nn.Sequential(*layers)
 
 
+_NORMS = {'batch': torch.nn.BatchNorm2d, 'instance': torch.nn.InstanceNorm2d}
+
+
+def _stem(features, kernel_size, norm):
+    """1 -> 32 -> 64 -> ... -> features channels at 128x128, then a stride-2 conv to 64x64
+    (model.py:164-186 and :268-288 share this layout)."""
+    layers = _conv_norm_relu(norm, True, 1, 32, kernel_size)
+    width = 32
+    while width < features:
+        nxt = min(2 * width, features)
+        layers += _conv_norm_relu(norm, True, width, nxt, kernel_size)
+        width = nxt
+    layers += _conv_norm_relu(norm, True, features, features, kernel_size, stride=2)
+    return torch.nn.Sequential(*layers)
+
+
 class ResBlock(torch.nn.Module):
     """Pre-activation bottleneck, model.py:6-23."""
 
@@ -159,15 +175,8 @@ class PixelwiseRegression(torch.nn.Module):
     def __init__(self, joints, stage=2, label_size=64, features=256, level=4, kernel_size=3, norm_method='batch',
                  heatmap_method='softmax'):
         super().__init__()
-        norm = {'batch': torch.nn.BatchNorm2d, 'instance': torch.nn.InstanceNorm2d}[norm_method]
-        stem = _conv_norm_relu(norm, True, 1, 32, kernel_size)
-        width = 32
-        while width < features:
-            nxt = min(2 * width, features)
-            stem += _conv_norm_relu(norm, True, width, nxt, kernel_size)
-            width = nxt
-        stem += _conv_norm_relu(norm, True, features, features, kernel_size, stride=2)
-        self.conv = torch.nn.Sequential(*stem)
+        norm = _NORMS[norm_method]
+        self.conv = _stem(features, kernel_size, norm)
         concat_dim = 2 * joints + 1
         self.stages = torch.nn.ModuleList([
             PredictionBlock(features if i == 0 else concat_dim, joints, label_size, features, level,
@@ -184,14 +193,16 @@ class PixelwiseRegression(torch.nn.Module):
             f = torch.cat([heatmaps, depthmaps, label_img], dim=1)
         return results
 
-    def forward_loss(self, img, label_img, mask, uvd, heatmaps, depthmaps, alpha=1.0, lambda_h=1.0, lambda_d=0.01):
+    def forward_loss(self, img, label_img, mask, uvd, heatmaps, depthmaps, alpha=1.0, lambda_h=1.0, lambda_d=0.01,
+                     n_mean=0):
         """Fused criterion: the training forward plus the loss of train.py:194-205 with
         the loss arithmetic inside the decoder kernels.  Returns (loss, every_loss, uvds):
         `every_loss[i]` is a [3] tensor (heatmap_loss, depthmap_loss, uvd_loss) of stage i
         (what train.py logs, :296-310) and `uvds[i]` the decoded coordinates.  The last
         stage runs forward and backward+loss back to back (ops.fused_decoder_loss).
         `heatmaps` may be the sparse `taps` tensor of sfr.build_sfr(targets="sparse")
-        (`depthmaps` is then ignored): the loss kernels evaluate the targets on the fly."""
+        (`depthmaps` is then ignored): the loss kernels evaluate the targets on the fly.
+        `n_mean`: the B*J of the loss means (0 = this batch; see ops.fused_decoder_loss)."""
         f = self.conv(img)
         loss = 0
         every_loss, uvds = [], []
@@ -202,17 +213,65 @@ class PixelwiseRegression(torch.nn.Module):
             if i < last:
                 H, D, uvd_i, stage_loss, terms = ops.fused_decoder_with_loss(
                     z, plane.temperature, d_raw, label_img, mask, heatmaps, depthmaps, uvd, plane.method, alpha,
-                    lambda_h, lambda_d)
+                    lambda_h, lambda_d, n_mean)
                 f = torch.cat([H, D, label_img], dim=1)
             else:
                 stage_loss, terms, uvd_i = ops.fused_decoder_loss(
                     z, plane.temperature, d_raw, label_img, mask, heatmaps, depthmaps, uvd, plane.method, alpha,
-                    lambda_h, lambda_d, store_heat=False)[:3]
+                    lambda_h, lambda_d, store_heat=False, n_mean=n_mean)[:3]
             loss = loss + stage_loss
             every_loss.append(terms)
             uvds.append(uvd_i.detach())
         return loss, every_loss, uvds
 
 
+class FullRegressionBlock(torch.nn.Module):
+    """Ablation baseline, model.py:215-257: hourglass features -> three stride-2 convs -> MLP -> [B,J,3].
+    No decoder (nothing of the hot path runs here); kept so that `train_fullregression.py` /
+    `test_fullregression.py` find the names they import and released ablation checkpoints load
+    (same Sequential layouts, same state_dict keys)."""
+
+    def __init__(self, in_dim, joints, label_size=64, features=256, level=4, norm=torch.nn.BatchNorm2d):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(in_dim, features, 1, stride=1, padding=0)
+        self.hourglass = Hourglass(features, level, norm=norm)
+        self.flatten_dim = label_size ** 2 * features // 64
+        self.joints = joints
+        down = []
+        for _ in range(3):
+            down += _conv_norm_relu(norm, True, features, features, 3, stride=2)
+        self.downsampling = torch.nn.Sequential(*down)
+        self.regression = torch.nn.Sequential(torch.nn.Linear(self.flatten_dim, 1024), torch.nn.ReLU(True),
+                                              torch.nn.Linear(1024, 1024), torch.nn.ReLU(True),
+                                              torch.nn.Linear(1024, joints * 3))
+
+    def forward(self, x, label_img, mask):
+        f = self.hourglass(self.conv(x))
+        coordinates = self.regression(self.downsampling(f).view(-1, self.flatten_dim))
+        return f, coordinates.view(-1, self.joints, 3)
+
+
+class FullRegression(torch.nn.Module):
+    """Ablation baseline, model.py:259-309.  forward(img, label_img, mask) -> list over stages of uvd [B,J,3]."""
+
+    def __init__(self, joints, stage=2, label_size=64, features=256, level=4, norm_method='batch'):
+        super().__init__()
+        norm = _NORMS[norm_method]
+        self.conv = _stem(features, 3, norm)
+        self.stages = torch.nn.ModuleList([
+            FullRegressionBlock(features if i == 0 else features + 1, joints, label_size, features, norm=norm)
+            for i in range(stage)])
+        self.apply(xavier_weights_init)
+
+    def forward(self, img, label_img, mask):
+        f = self.conv(img)
+        results = []
+        for stage in self.stages:
+            f, uvd = stage(f, label_img, mask)
+            results.append(uvd)
+            f = torch.cat([f, label_img], dim=1)
+        return results
+
+
 __all__ = ["ResBlock", "Hourglass", "PlaneRegression", "DepthRegression", "PredictionBlock", "PixelwiseRegression",
-           "com_filter", "xavier_weights_init"]
+           "FullRegressionBlock", "FullRegression", "com_filter", "xavier_weights_init"]

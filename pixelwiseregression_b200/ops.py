@@ -104,21 +104,25 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
     g_uvd = as_f32(g_uvd)
     gH_up = as_f32(gH_up)
     gD_up = gD_up.to(z.dtype).contiguous() if gD_up is not None else None
+    # every converted tensor is bound to a local that outlives the launch: a temporary inside the
+    # argument list would be freed (and its block possibly re-used by the next temporary) before the kernel runs
+    label_img, mask, stats, uvd = as_f32(label_img), as_f32(mask), as_f32(stats), as_f32(uvd)
+    scale_dev = as_f32(loss_scale_dev)
     s = stream_ptr(z.device)
     with torch.cuda.device(z.device), _lib.timed("pwr_decoder_bwd" if targets is None else "pwr_decoder_bwd_loss"):
         if targets is None:
-            rc = lib.pwr_decoder_bwd(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
+            rc = lib.pwr_decoder_bwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask),
                                      ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(gz), ptr(gD),
                                      ptr(gw_partial), B, J, METHODS[method], map_dtype, s)
             check(rc, "pwr_decoder_bwd")
             return gz, gD, gw_partial, None
         heat_gt, dmap_gt, uvd_gt, taps = _unpack_targets(targets, B, J)
         loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32) if want_loss else None
-        rc = lib.pwr_decoder_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(as_f32(label_img)), ptr(as_f32(mask)),
+        rc = lib.pwr_decoder_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask),
                                       ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(heat_gt),
                                       ptr(dmap_gt), ptr(uvd_gt), ptr(taps), float(alpha), float(lambda_h),
                                       float(lambda_d),
-                                      float(loss_scale), ptr(as_f32(loss_scale_dev)), int(n_mean), ptr(gz),
+                                      float(loss_scale), ptr(scale_dev), int(n_mean), ptr(gz),
                                       ptr(gD), ptr(gw_partial),
                                       ptr(loss_partial), B, J, METHODS[method], map_dtype, s)
     check(rc, "pwr_decoder_bwd_loss")
@@ -144,6 +148,7 @@ def decoder_fused_raw(z, w, D, label_img, mask, targets, method="softmax", alpha
     gD = torch.empty_like(z) if want_grads else None
     gw_partial = torch.empty(B, J, **f32) if (want_grads and method == "softmax") else None
     loss_partial = torch.empty(B, J, 3, **f32)
+    loss_scale_dev = as_f32(loss_scale_dev)
     with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd_bwd_loss"):
         rc = lib.pwr_decoder_fwd_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
                                           ptr(uvd_gt), ptr(taps), float(alpha), float(lambda_h), float(lambda_d),
@@ -158,11 +163,12 @@ def reduce_partials(partial):
     """[B, J] or [B, J, C] per-(sample, joint) partials -> [J] / [J, C] batch sums
     (deterministic tree, pwr_reduce_partials)."""
     require_cuda(partial)
+    partial = as_f32(partial)
     B, J = partial.shape[0], partial.shape[1]
     C = partial.shape[2] if partial.dim() == 3 else 1
     out = torch.empty((J, C) if partial.dim() == 3 else (J,), device=partial.device, dtype=torch.float32)
     with torch.cuda.device(partial.device):
-        rc = _lib.load().pwr_reduce_partials(ptr(partial.contiguous()), ptr(out), B, J, C,
+        rc = _lib.load().pwr_reduce_partials(ptr(partial), ptr(out), B, J, C,
                                              stream_ptr(partial.device))
     check(rc, "pwr_reduce_partials")
     return out
@@ -171,8 +177,9 @@ def reduce_partials(partial):
 def scale_inplace_(x, scale):
     """x *= scale, with `scale` a 0-dim CUDA tensor (no host sync; a no-op launch when scale == 1)."""
     require_cuda(x, scale)
+    scale = as_f32(scale)
     with torch.cuda.device(x.device):
-        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(as_f32(scale)), x.numel(), _lib.MAP_DTYPES[x.dtype],
+        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(scale), x.numel(), _lib.MAP_DTYPES[x.dtype],
                                            stream_ptr(x.device))
     check(rc, "pwr_scale_inplace")
     return x
@@ -182,6 +189,7 @@ def stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean=0):
     """train.py:197-205 from per-(b,j) sums of squares in one launch (pwr_stage_loss):
     returns a [4] tensor (heatmap_loss, depthmap_loss, uvd_loss, combined loss)."""
     require_cuda(loss_partial)
+    loss_partial = as_f32(loss_partial)
     B, J = loss_partial.shape[0], loss_partial.shape[1]
     out = torch.empty(4, device=loss_partial.device, dtype=torch.float32)
     with torch.cuda.device(loss_partial.device):
@@ -219,19 +227,19 @@ class DecoderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, w, D, label_img, mask, method, heat_gt=None, dmap_gt=None, uvd_gt=None, alpha=1.0,
-                lambda_h=1.0, lambda_d=0.01):
+                lambda_h=1.0, lambda_d=0.01, n_mean=0):
         ctx.set_materialize_grads(False)
         targets = _make_targets(heat_gt, dmap_gt, uvd_gt)
         H, uvd, stats, loss_partial = decoder_forward_raw(z, w, D, label_img, mask, method, targets=targets)
         ctx.method = method
         ctx.in_dtypes = (z.dtype, D.dtype)
-        ctx.loss_cfg = (alpha, lambda_h, lambda_d) if targets is not None else None
+        ctx.loss_cfg = (alpha, lambda_h, lambda_d, n_mean) if targets is not None else None
         ctx.save_for_backward(z, w, D, label_img, mask, stats, uvd, heat_gt, dmap_gt, uvd_gt)
         # heat maps and coordinates are float32 even for half-precision logits, as under autocast
         outs = (H, D.view_as(D), uvd)
         if targets is None:
             return outs
-        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
+        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean)
         terms, total = out4[:3], out4[3]
         ctx.mark_non_differentiable(terms)
         return outs + (total, terms)
@@ -240,18 +248,18 @@ class DecoderFunction(torch.autograd.Function):
     def backward(ctx, gH, gD_up, g_uvd, g_total=None, g_terms=None):
         z, w, D, label_img, mask, stats, uvd, heat_gt, dmap_gt, uvd_gt = ctx.saved_tensors
         if ctx.loss_cfg is not None and g_total is not None:
-            alpha, lambda_h, lambda_d = ctx.loss_cfg
+            alpha, lambda_h, lambda_d, n_mean = ctx.loss_cfg
             gz, gD, gw_partial, _ = decoder_backward_raw(
                 z, w, D, label_img, mask, stats, uvd, g_uvd, gH, gD_up, ctx.method,
                 targets=_make_targets(heat_gt, dmap_gt, uvd_gt), alpha=alpha, lambda_h=lambda_h, lambda_d=lambda_d,
-                loss_scale_dev=g_total)
+                loss_scale_dev=g_total, n_mean=n_mean)
         else:
             gz, gD, gw_partial, _ = decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd, gH, gD_up,
                                                          ctx.method)
         gw = None
         if w is not None and ctx.needs_input_grad[1]:
             gw = reduce_partials(gw_partial).view_as(w).to(w.dtype)
-        return (gz.to(ctx.in_dtypes[0]), gw, gD.to(ctx.in_dtypes[1])) + (None,) * 9
+        return (gz.to(ctx.in_dtypes[0]), gw, gD.to(ctx.in_dtypes[1])) + (None,) * 10
 
 
 def fused_decoder(z, w, D, label_img, mask, method="softmax"):
@@ -263,11 +271,11 @@ def fused_decoder(z, w, D, label_img, mask, method="softmax"):
 
 
 def fused_decoder_with_loss(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method="softmax", alpha=1.0,
-                            lambda_h=1.0, lambda_d=0.01):
+                            lambda_h=1.0, lambda_d=0.01, n_mean=0):
     """Inner-stage variant: returns (heatmaps, depthmaps, uvd, stage_loss, terms[3])
-    with heatmaps/depthmaps/uvd/stage_loss all differentiable."""
+    with heatmaps/depthmaps/uvd/stage_loss all differentiable.  `n_mean`: see fused_decoder_loss."""
     return DecoderFunction.apply(z, w, D, label_img, mask, method, heat_gt, dmap_gt, uvd_gt, float(alpha),
-                                 float(lambda_h), float(lambda_d))
+                                 float(lambda_h), float(lambda_d), int(n_mean))
 
 
 class PlaneFunction(torch.autograd.Function):
@@ -318,6 +326,9 @@ class DepthFunction(torch.autograd.Function):
         return gD.to(D.dtype), gH.to(heatmaps.dtype), None, None
 
 
+# Loss scale built into the eagerly computed float16 gradients of the last stage (see DecoderLossFunction.forward)
+EAGER_FP16_SCALE = 65536.0
+
 # False sends ops.fused_decoder_loss through the two-kernel route (pwr_decoder_fwd, then pwr_decoder_bwd_loss);
 # bench.py flips it to time both, tests to compare them.
 ONE_PASS_LAST_STAGE = True
@@ -336,24 +347,32 @@ class DecoderLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method, alpha, lambda_h, lambda_d,
-                store_heat):
+                store_heat, n_mean):
         ctx.set_materialize_grads(False)       # no zero-filled gradient tensors for the detached outputs
         need_grad = any(ctx.needs_input_grad[:3])
         targets = _make_targets(heat_gt, dmap_gt, uvd_gt)
+        # float16 conv outputs (autocast + GradScaler, train.py:170-189): the eager gradients are stored in
+        # float16, and at unit loss scale their typical size 2/(B*J) * p * err (1e-6 .. 1e-10) is subnormal or
+        # flushes to zero.  The reference scales the loss BEFORE backward, so its float16 gradients are 2^16
+        # larger; do the same here: the kernel produces them pre-scaled by EAGER_FP16_SCALE and backward()
+        # multiplies by g_total / EAGER_FP16_SCALE (exactly 1 for GradScaler's initial scale of 2^16).
+        pre = EAGER_FP16_SCALE if (need_grad and z.dtype == torch.float16 and method != "given") else 1.0
         if need_grad and D is not None and method != "given" and ONE_PASS_LAST_STAGE:
             # forward + loss + backward in one visit of (z, D, targets)
             H, uvd, gz, gD, gw_partial, loss_partial = decoder_fused_raw(
-                z, w, D, label_img, mask, targets, method, alpha, lambda_h, lambda_d, store_heat=store_heat)
+                z, w, D, label_img, mask, targets, method, alpha, lambda_h, lambda_d, loss_scale=pre,
+                n_mean=n_mean, store_heat=store_heat)
         else:
             H, uvd, stats, _ = decoder_forward_raw(z, w, D, label_img, mask, method, store_heat=store_heat)
             gz, gD, gw_partial, loss_partial = decoder_backward_raw(
                 z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
-                want_loss=True, want_gz=need_grad, want_gD=need_grad)
-        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha)
+                loss_scale=pre, n_mean=n_mean, want_loss=True, want_gz=need_grad, want_gD=need_grad)
+        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean)
         terms, total = out4[:3], out4[3]
         gw = reduce_partials(gw_partial).view_as(w) if (need_grad and w is not None) else None
         # the eager gradients live on the node until its (single) backward consumes them
         ctx.grads = (gz, gD, gw)
+        ctx.pre = pre
         outs = (total, terms, uvd) + ((H,) if store_heat else ())
         ctx.mark_non_differentiable(*outs[1:])
         return outs
@@ -368,21 +387,26 @@ class DecoderLossFunction(torch.autograd.Function):
         if gz is None:
             raise _lib.PwrError("fused_decoder_loss: forward ran without gradient tracking")
         if g_total is None:
-            return (None,) * 13
+            return (None,) * 14
+        if ctx.pre != 1.0:
+            g_total = g_total.float() * (1.0 / ctx.pre)
         scale_inplace_(gz, g_total)
         scale_inplace_(gD, g_total)
         if gw is not None:
             gw = gw * g_total
-        return (gz, gw, gD) + (None,) * 10
+        return (gz, gw, gD) + (None,) * 11
 
 
 def fused_decoder_loss(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method="softmax", alpha=1.0,
-                       lambda_h=1.0, lambda_d=0.01, store_heat=True):
+                       lambda_h=1.0, lambda_d=0.01, store_heat=True, n_mean=0):
     """Returns (total_loss, loss_terms[3] = (heatmap, depthmap, uvd), uvd[, heatmaps]).
     `heat_gt` may be the uint8 taps tensor of sfr.build_sfr(targets="sparse") (then `dmap_gt` is
-    ignored / None): the targets are evaluated inside the loss kernel."""
+    ignored / None): the targets are evaluated inside the loss kernel.
+    `n_mean` = the B*J the means of train.py:197-199 run over; 0 = this call's own B*J (what DDP's
+    gradient AVERAGING needs); the global B*J when per-rank losses / gradients are SUMMED across ranks
+    or micro-batches."""
     return DecoderLossFunction.apply(z, w, D, label_img, mask, heat_gt, dmap_gt, uvd_gt, method, float(alpha),
-                                     float(lambda_h), float(lambda_d), bool(store_heat))
+                                     float(lambda_h), float(lambda_d), bool(store_heat), int(n_mean))
 
 
 def recover_uvd(uvd_norm, box_size, com, cube_size, intrinsics=None):
@@ -391,13 +415,13 @@ def recover_uvd(uvd_norm, box_size, com, cube_size, intrinsics=None):
     (datasets.py:100-111)."""
     require_cuda(uvd_norm, box_size, com, cube_size)
     B, J = uvd_norm.shape[0], uvd_norm.shape[1]
-    uvd_norm = as_f32(uvd_norm)
+    uvd_norm, box_size, cube_size, com = as_f32(uvd_norm), as_f32(box_size), as_f32(cube_size), as_f32(com)
     uvd_px = torch.empty_like(uvd_norm)
     xyz = torch.empty_like(uvd_norm) if intrinsics is not None else None
     fx, fy, hu, hv = intrinsics if intrinsics is not None else (1.0, 1.0, 0.0, 0.0)
     with torch.cuda.device(uvd_norm.device):
-        rc = _lib.load().pwr_recover_uvd(ptr(uvd_norm), ptr(as_f32(box_size)), ptr(as_f32(cube_size)),
-                                         ptr(as_f32(com)), fx, fy, hu, hv, ptr(uvd_px), ptr(xyz), B, J,
+        rc = _lib.load().pwr_recover_uvd(ptr(uvd_norm), ptr(box_size), ptr(cube_size),
+                                         ptr(com), fx, fy, hu, hv, ptr(uvd_px), ptr(xyz), B, J,
                                          stream_ptr(uvd_norm.device))
     check(rc, "pwr_recover_uvd")
     return (uvd_px, xyz) if intrinsics is not None else uvd_px
@@ -411,9 +435,11 @@ def joint_error(uvd_pred, uvd_true, box_size, com, cube_size, intrinsics):
     B, J = uvd_pred.shape[0], uvd_pred.shape[1]
     err = torch.empty(B, device=uvd_pred.device, dtype=torch.float32)
     fx, fy, hu, hv = intrinsics
+    uvd_pred, uvd_true = as_f32(uvd_pred), as_f32(uvd_true)
+    box_size, cube_size, com = as_f32(box_size), as_f32(cube_size), as_f32(com)
     with torch.cuda.device(uvd_pred.device):
-        rc = _lib.load().pwr_joint_error(ptr(as_f32(uvd_pred)), ptr(as_f32(uvd_true)), ptr(as_f32(box_size)),
-                                         ptr(as_f32(cube_size)), ptr(as_f32(com)), fx, fy, hu, hv, ptr(err), B, J,
+        rc = _lib.load().pwr_joint_error(ptr(uvd_pred), ptr(uvd_true), ptr(box_size),
+                                         ptr(cube_size), ptr(com), fx, fy, hu, hv, ptr(err), B, J,
                                          stream_ptr(uvd_pred.device))
     check(rc, "pwr_joint_error")
     return err

@@ -42,10 +42,32 @@ def test_signature_arity_matches_header():
 
 
 def test_version_and_error_strings(lib):
-    assert lib.pwr_version() == 100
+    assert lib.pwr_version() == _lib.ABI_VERSION == 200
     assert lib.pwr_error_string(0) == b"ok"
     assert b"NULL" in lib.pwr_error_string(-1)
     assert b"aligned" in lib.pwr_error_string(-3)
+
+
+def test_dispatch_options_are_explicit_not_environment(lib):
+    assert lib.pwr_set_option(99, 1) == -4
+    assert _lib.set_option("bwd_direct", 1) == 0
+    assert _lib.set_option("bwd_direct", 0) == 1
+    with _lib.option("fwd_pipe", 1):
+        assert lib.pwr_set_option(_lib.OPTIONS["fwd_pipe"], 1) == 1
+    assert lib.pwr_set_option(_lib.OPTIONS["fwd_pipe"], 0) == 0
+    text = "".join(open(os.path.join(ROOT, "pixelwiseregression_b200", "csrc", f)).read() for f in ("decoder.cu", "sfr.cu"))
+    assert "getenv" not in text                       # nothing on the launch path reads the environment
+
+
+def test_stale_library_is_detected_by_content(lib, tmp_path, monkeypatch):
+    assert not build.needs_build()
+    stamp = open(build.STAMP).read()
+    try:
+        open(build.STAMP, "w").write("0" * 64 + "\n")
+        assert build.needs_build()
+    finally:
+        open(build.STAMP, "w").write(stamp)
+    assert not build.needs_build()
 
 
 def test_argument_errors_without_a_gpu(lib):

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import decoder_oracle as do
-from pixelwiseregression_b200 import ops, synth
+from pixelwiseregression_b200 import _lib, ops, synth
 from helpers import GRAD_RTOL, assert_close, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -409,12 +409,10 @@ def test_pipelined_forward_equals_direct_forward(method, dtype, B, J, monkeypatc
         wv[::3] *= -1.0                                     # extremum = min for these joints
         w = cu(wv)
     for store_heat in (True, False):
-        monkeypatch.setenv("PWR_FWD_DIRECT", "1")
-        Hd, uvd_d, st_d, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
-        monkeypatch.setenv("PWR_FWD_DIRECT", "0")
-        monkeypatch.setenv("PWR_FWD_PIPE", "1")             # default: pipelined only without the heat-map store
-        Hp, uvd_p, st_p, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
-        monkeypatch.delenv("PWR_FWD_PIPE")
+        with _lib.option("fwd_direct", 1):
+            Hd, uvd_d, st_d, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
+        with _lib.option("fwd_pipe", 1):                    # default: pipelined only without the heat-map store
+            Hp, uvd_p, st_p, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=store_heat)
         torch.cuda.synchronize()
         assert torch.equal(st_d[..., 0], st_p[..., 0])      # extremum: exact
         assert_close("1/sum", st_p[..., 1].cpu().numpy(), st_d[..., 1].cpu().numpy(), 1e-6)
@@ -427,9 +425,8 @@ def test_pipelined_forward_equals_direct_forward(method, dtype, B, J, monkeypatc
     # against the float64 oracle as well (the pipelined kernel is the default path)
     t64 = lambda a: a.detach().cpu().to(torch.float64)
     p_ref, _, uvd_ref = do.decoder_forward(t64(z), t64(w) if w is not None else None, t64(D), t64(L), t64(m), method)
-    monkeypatch.setenv("PWR_FWD_PIPE", "1")
-    Hp, uvd_p, _, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
-    monkeypatch.delenv("PWR_FWD_PIPE")
+    with _lib.option("fwd_pipe", 1):
+        Hp, uvd_p, _, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
     _, uvd_n, _, _ = ops.decoder_forward_raw(z, w, D, L, m, method, store_heat=False, want_stats=False)   # default route
     assert_close("heat vs oracle", Hp.cpu().numpy(), p_ref.numpy())
     assert_close("uvd vs oracle", uvd_p.cpu().numpy(), uvd_ref.numpy())
@@ -467,9 +464,8 @@ def test_lean_backward_equals_pipelined_backward(method, dtype, B, J, monkeypatc
              dict(g_uvd=g_uvd),                                                # plain backward
              dict(g_uvd=g_uvd, want_gD=False)]
     for kw in cases:
-        monkeypatch.setenv("PWR_BWD_LEAN", "0")
-        a = ops.decoder_backward_raw(z, w, D, L, m, st, uvd, method=method, **kw)
-        monkeypatch.setenv("PWR_BWD_LEAN", "1")
+        with _lib.option("bwd_no_lean", 1):
+            a = ops.decoder_backward_raw(z, w, D, L, m, st, uvd, method=method, **kw)
         b = ops.decoder_backward_raw(z, w, D, L, m, st, uvd, method=method, **kw)
         torch.cuda.synchronize()
         for name, x, y in zip(("gz", "gD", "gw_partial", "loss_partial"), b, a):

@@ -15,10 +15,11 @@ from helpers import GOLDEN
 def test_state_dict_layout_equals_reference():
     spec = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
     for name, s in spec.items():
-        m = model.PixelwiseRegression(**s["kwargs"])
+        m = getattr(model, s.get("class", "PixelwiseRegression"))(**s["kwargs"])
         got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
         assert got == s["keys"], name
     assert len(spec["nyu_instance"]["keys"]) == 344
+    assert spec["fullregression_nyu"]["class"] == "FullRegression"     # the ablation modules are re-exported too
 
 
 def test_constructor_signatures_match_reference():

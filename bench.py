@@ -1,28 +1,35 @@
 #!/usr/bin/env python
-"""bench.py — SFR + decoder micro-benchmark (BASELINE.json configs[1]).
+"""bench.py — SFR + decoder micro-benchmark (BASELINE.json configs[1]) plus the records of configs[2-4].
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One step = one pass of the hot path over one batch of synthetic NYU-shaped input
-(B = 4096 samples per GPU, J = 14): SFR target build from raw 480x640 depth
-frames -> fused decoder forward on N(0,1) logits -> fused backward + stage loss
-(+ the batch reduction of dL/dw and the loss sums).  With N > 1 (torchrun) every
-rank owns its own B samples (weak scaling); the only exchange is the all-reduce
-of the [J + 3] vector (dL/dw and the three loss terms) the DDP bucket would carry.
+(B = 4096 samples per GPU, J = 14): SFR target build from 480x640 depth frames ->
+last-stage decoder forward + stage loss + backward on N(0,1) logits (one pass) ->
+batch reduction of dL/dw and the loss sums.  With N > 1 (torchrun) every rank owns
+its own B samples (weak scaling); the only exchange is the all-reduce of dL/dw [J]
+and the three logged loss terms, issued on a side stream so it overlaps the next
+step's SFR build (what DDP's bucket does for the backbone).
 
-Prints ONE JSON line (rank 0): whole-job samples/s with inputs resident in HBM
-(`value`), the same through host buffers with H2D/D2H inside the timed region
-(`e2e`), the dominant kernel's achieved HBM bandwidth against the measured peak
-(`roofline`), and the oracle port timed on the host cores (`cpu_baseline`).
+Prints ONE JSON line (rank 0):
+  value        whole-job samples/s with inputs resident in HBM, CUDA events, max over ranks
+  e2e          the same path fed from pinned HOST memory through the public feed API
+               (feed.HostFeed: annotations H2D + pwr_sfr_fetch pulling only the crop windows
+               of the raw uint16 frames over PCIe, double-buffered against the compute
+               stream), loss + decoded joints read back to the host every step
+  roofline     dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline the oracle port on the host cores (bounded sample)
+  extras       inner_stage / two_stage_decoder (kernels of a 2-stage training step),
+               raw_frames_step, two_kernel_step, sparse_targets, train_step (configs[2]),
+               train_msra (configs[3]), sweep (configs[4])
 
-`--impl reference` times the CPU oracle port (the reference is Python; its path
-cannot travel to the GPU box) on the same workload definition.
+`--impl reference` times the CPU oracle port (the reference is Python; it cannot
+travel to the GPU box) on the same workload definition.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -48,23 +55,34 @@ def parse_args():
     ap.add_argument("--shape", default="NYU")
     ap.add_argument("--alpha", type=float, default=1.0)
     ap.add_argument("--frame-format", default="f32", choices=["f32", "nyu_gb16", "u16"],
-                    help="f32 = decoded frames (what process_single_data receives, default); nyu_gb16 / u16 = raw "
-                         "sensor samples decoded inside the SFR kernel (SURVEY 8f-1), with the load_from_text "
-                         "hand rectangle applied in the crop taps")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+                    help="format of the HBM-resident frames of the main timed region: f32 = decoded frames (what "
+                         "process_single_data receives; SURVEY 8d's synthetic input); nyu_gb16 / u16 = raw sensor "
+                         "samples decoded inside the SFR kernel with the load_from_text hand rectangle (8f-1)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--cpu-samples", type=int, default=512, help="samples in the bounded CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--augment", action="store_true",
                     help="build the SFR targets through the augmented branch (datasets.py:216-299, train.py defaults)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-sparse", action="store_true", help="skip the compact-target variant of the step")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the variants of the step (two-kernel, compact, raw)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager decoder baseline on the GPU")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip inner_stage / two_stage_decoder / train_step / train_msra / sweep")
+    ap.add_argument("--train-steps", type=int, default=8, help="timed steps of each training configuration")
+    ap.add_argument("--sweep-batches", default="256,1024,4096,16384")
     return ap.parse_args()
 
 
 def workload_name(shape, batch):
     return ("configs[1]: decoder+SFR microbenchmark alone, %s shape (J=%d, %dx%d frames), batch %d per GPU, "
             "SFR build + decoder fwd + fused bwd/loss" % (shape.name, shape.joints, shape.height, shape.width, batch))
+
+
+def workload_config(shape, batch, frame_format, augment, alpha, lambda_h, lambda_d):
+    """The keys both arms print, so that the driver's `same_config` check compares like with like."""
+    return {"workload": workload_name(shape, batch), "batch_per_gpu": batch, "joints": shape.joints,
+            "frame_format": frame_format, "augment": bool(augment), "alpha": alpha, "lambda_h": lambda_h,
+            "lambda_d": lambda_d}
 
 
 def measured_peak():
@@ -89,10 +107,23 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
         self.error = None
         self.marked = 0
+        self.sections = {}
 
     def mark(self):
         """Start of the timed region: samples taken from here on are `samples_timed`."""
         self.marked = len(self.sm)
+
+    def section(self, name):
+        """Start of a named extra: the record of that extra carries its own clock summary."""
+        self.sections[name] = [len(self.sm), None]
+        return name
+
+    def end_section(self, name):
+        self.sections[name][1] = len(self.sm)
+        lo, hi = self.sections[name]
+        sm = self.sm[lo:hi]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.sm_max, "samples": len(sm), "reasons": sorted(self.reasons)}
 
     def run(self):
         try:
@@ -116,16 +147,19 @@ class ClockSampler(threading.Thread):
         except Exception as exc:  # NVML missing: report it, do not fake numbers
             self.error = repr(exc)
 
-    def summary(self):
+    def summary(self, upto=None):
+        sm = self.sm[:upto] if upto else self.sm
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable: %s" % self.error]}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "samples_timed": len(sm) - self.marked,
+                "sm_mhz_timed": statistics.median(sm[self.marked:]) if len(sm) > self.marked else None,
+                "power_w_max": max(self.power) if self.power else None}
+
+    def stop(self):
         self.stop_flag.set()
         self.join(timeout=5)
-        if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable: %s" % self.error]}
-        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "samples_timed": len(self.sm) - self.marked,
-                "sm_mhz_timed": statistics.median(self.sm[self.marked:]) if len(self.sm) > self.marked else None,
-                "power_w_max": max(self.power) if self.power else None}
 
 
 # --------------------------------------------------------------------------- #
@@ -152,12 +186,15 @@ def run_reference(args):
     cpu_baseline.shutdown()
     res = {"sample": cpu_baseline.describe(shape, n, cores)}
     value = n * args.steps / dt
+    cfg = workload_config(shape, args.batch, "f32", False, args.alpha, 1.0, 0.01)
+    cfg["note"] = ("each step is a bounded sample of %d samples of that workload on the host CPU; the port (fork pool over "
+                   "all cores, OpenCV resize / blur) is FASTER than the stock reference path, whose process_single_data "
+                   "takes 38-63 ms per sample per DataLoader worker (SURVEY section 6; measured in the build container)" % n)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(shape, args.batch),
-                   "note": "each step is a bounded sample of %d samples of that workload on the host CPU" % n},
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": res["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -213,7 +250,7 @@ def eager_decoder_baseline(z, D, w, batch, alpha, lambda_h, lambda_d, iters=5):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from pixelwiseregression_b200 import _lib, ops, roofline, sfr, synth
+    from pixelwiseregression_b200 import _lib, feed, ops, roofline, sfr, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,6 +266,7 @@ def run_b200(args):
     shape = synth.SHAPES[args.shape]
     B, J = args.batch, shape.joints
     alpha, lambda_h, lambda_d = args.alpha, 1.0, 0.01
+    peak, peak_src = measured_peak()
 
     # ---- synthetic inputs, resident in HBM (seed = rank: every rank owns different samples) ----
     d = synth.make_frames_device(shape, B, seed=rank, device=dev)
@@ -237,34 +275,62 @@ def run_b200(args):
     D = torch.randn(B, J, 64, 64, device=dev, generator=g).requires_grad_(True)
     w = (torch.rand(J, 1, device=dev, generator=g) + 0.5).requires_grad_(True)
     frames, com, cube, uvd = d["frames"], d["com"], d["cube"], d["uvd"]
+    raw_fmt = "nyu_gb16" if shape.name == "NYU" else "u16"
+    raw_frames = None
+    if not shape.frame_f64:
+        raw_frames = frames.round().clamp_(0, 65535).to(torch.int32).to(torch.uint16)      # sensor counts (mm)
+    raw_kw = dict(fx=shape.fx, fy=shape.fy, frame_format=raw_fmt, prefilter=(40.0, shape.halfu, shape.halfv))
     sfr_kw = dict(fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
     if args.frame_format != "f32":
-        frames = frames.round().clamp_(0, 65535).to(torch.int32).to(torch.uint16)      # sensor counts (mm)
-        sfr_kw.update(frame_format=args.frame_format, prefilter=(40.0, shape.halfu, shape.halfv), frame_f64=False)
-        d["frames"] = frames
+        frames = raw_frames
+        sfr_kw = dict(raw_kw, frame_format=args.frame_format)
     if args.augment:
         import numpy as np
         sfr_kw["augment"] = sfr.draw_augmentation(B, np.random.default_rng(rank))
 
-    def step(frames_, com_, cube_, uvd_, z_, D_, kw=None):
+    # the [J + 3] all-reduce rides on a side stream: it overlaps the NEXT step's SFR build, and the decoder
+    # of the next step (which would read the updated temperature w) waits for it - DDP's overlap, in small
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    pending = {"work": False}
+    arenas = {}
+
+    def step(frames_, com_, cube_, uvd_, z_, D_, kw=None, key="main"):
         """The public-API call sequence a training loop makes for this path."""
-        batch = sfr.build_sfr(frames_, com_, cube_, uvd_, **(kw or sfr_kw))
+        kw = kw or sfr_kw
+        arena = arenas.setdefault(key, sfr.SfrArena())
+        batch = frames_ if isinstance(frames_, sfr.SFRBatch) else sfr.build_sfr(frames_, com_, cube_, uvd_, arena=arena, **kw)
         heat_t = batch.heatmaps if batch.heatmaps is not None else batch.taps     # dense maps, or compact taps
-        total, terms, uvd_out, _ = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, heat_t,
-                                                          batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
-                                                          lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)
+        if world > 1 and pending["work"]:
+            torch.cuda.current_stream().wait_stream(comm_stream)                  # w of the previous step is reduced
+            pending["work"] = False
+        total, terms, uvd_out = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, heat_t,
+                                                       batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
+                                                       lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)[:3]
         z_.grad = D_.grad = w.grad = None
         total.backward()
         if world > 1:
             # what the DDP bucket carries for this path: dL/dw [J] and the logged loss terms [3]
-            vec = torch.cat([w.grad.reshape(-1), terms])
-            dist.all_reduce(vec, op=dist.ReduceOp.AVG)
+            comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                dist.all_reduce(w.grad, op=dist.ReduceOp.AVG)
+                dist.all_reduce(terms, op=dist.ReduceOp.AVG)
+            w.grad.record_stream(comm_stream)
+            terms.record_stream(comm_stream)
+            pending["work"] = True
         return total, terms, uvd_out
 
     def barrier():
         if world > 1:
+            torch.cuda.current_stream().wait_stream(comm_stream)
+            pending["work"] = False
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # clocks are sampled from the warm-up on (same load as the timed region, which may last
     # only tens of milliseconds); samples inside the timed region are counted separately
@@ -278,31 +344,29 @@ def run_b200(args):
     sampler.mark()
     launches0 = _lib.launch_count()
     _lib.PROFILE = []
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    start.record()
+    marks[0].record()
     t_issue = time.perf_counter()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         step(frames, com, cube, uvd, z, D)
+        marks[k + 1].record()
     issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps
-    end.record()
     barrier()
-    elapsed_ms = start.elapsed_time(end)
+    elapsed_ms = marks[0].elapsed_time(marks[-1])
+    step_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
     launches = (_lib.launch_count() - launches0) * world      # every rank launches the same sequence
     prof, _lib.PROFILE = _lib.PROFILE, None
     clocks = sampler.summary()
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     value = B * world * args.steps / (elapsed_ms * 1e-3)
+    median_ms = max_over_ranks(statistics.median(step_ms))
 
     kernel_ms = {}
     for name, s, e in prof:
         kernel_ms.setdefault(name, []).append(s.elapsed_time(e))
-    # device time between the three big kernels (small kernels, launch gaps), averaged per step
+    # device time between the big kernels (small kernels, launch gaps), averaged per step
     gap_ms = sum(prof[i][2].elapsed_time(prof[i + 1][1]) for i in range(len(prof) - 1)) / args.steps
-    peak, peak_src = measured_peak()
     per_launch_bytes = {"pwr_sfr_build": roofline.sfr_build_bytes(J) * B,
                         "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J) * B,
                         "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J) * B,
@@ -312,73 +376,217 @@ def run_b200(args):
     for name, ms in kernel_ms.items():
         avg = sum(ms) / len(ms)
         gbs = per_launch_bytes[name] / (avg * 1e-3) / 1e9
-        kernels[name] = {"avg_ms": avg, "launches": len(ms), "algorithmic_bytes": per_launch_bytes[name],
-                         "achieved_gbs": gbs, "frac": gbs / peak}
+        kernels[name] = {"avg_ms": avg, "median_ms": statistics.median(ms), "launches": len(ms),
+                         "algorithmic_bytes": per_launch_bytes[name], "achieved_gbs": gbs, "frac": gbs / peak}
     dominant = max(kernels, key=lambda k: kernels[k]["avg_ms"])
     step_kernel_ms = sum(k["avg_ms"] for k in kernels.values())
+
+    def kernel_table(prof_v, bytes_table):
+        kms = {}
+        for name, s_, e_ in prof_v:
+            kms.setdefault(name, []).append(s_.elapsed_time(e_))
+        return {k: {"avg_ms": sum(v) / len(v), "algorithmic_bytes": bytes_table[k] * B,
+                    "frac": bytes_table[k] * B / (sum(v) / len(v) * 1e-3) / 1e9 / peak}
+                for k, v in kms.items() if k in bytes_table}
 
     # ---- variants of the same step, each against ITS OWN algorithmic bytes ("report the
     # elided variant separately, never against the larger figure"); identical loss terms and gradients
     # (tests/test_gpu_decoder.py) ----
-    def timed_variant(kw, one_pass, bytes_table, sample_bytes, note):
+    def timed_variant(frames_v, kw, one_pass, bytes_table, sample_bytes, note, key):
         ops.ONE_PASS_LAST_STAGE = one_pass
         try:
             for _ in range(3):
-                step(frames, com, cube, uvd, z, D, kw)
+                step(frames_v, com, cube, uvd, z, D, kw, key)
             barrier()
             _lib.PROFILE = []
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             for _ in range(args.steps):
-                step(frames, com, cube, uvd, z, D, kw)
+                step(frames_v, com, cube, uvd, z, D, kw, key)
             s1.record()
             barrier()
             prof_v, _lib.PROFILE = _lib.PROFILE, None
         finally:
             ops.ONE_PASS_LAST_STAGE = True
-        tv = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        ms_v = float(tv.item()) / args.steps
-        kms = {}
-        for name, s_, e_ in prof_v:
-            kms.setdefault(name, []).append(s_.elapsed_time(e_))
+        ms_v = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+        arenas.pop(key, None)
         return {"value": B * world / (ms_v * 1e-3), "unit": UNIT, "ms_per_step": ms_v,
                 "algorithmic_bytes_per_sample": sample_bytes,
                 "step_roofline_frac": sample_bytes * B / (ms_v * 1e-3) / 1e9 / peak,
-                "kernels": {k: {"avg_ms": sum(v) / len(v), "algorithmic_bytes": bytes_table[k] * B,
-                                "frac": bytes_table[k] * B / (sum(v) / len(v) * 1e-3) / 1e9 / peak}
-                            for k, v in kms.items()},
-                "note": note}
+                "kernels": kernel_table(prof_v, bytes_table), "note": note}
 
-    two_kernel = sparse = None
+    two_kernel = sparse = raw_step = None
     if not args.no_sparse:
         # (1) SURVEY 8d's own accounting: forward kernel, then backward+loss kernel (the logits are read twice)
         two_kernel = timed_variant(
-            None, False,
+            frames, None, False,
             {"pwr_sfr_build": roofline.sfr_build_bytes(J), "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J),
              "pwr_decoder_bwd_loss": roofline.decoder_bwd_bytes(J)}, roofline.step_bytes(J),
             "SURVEY 8d accounting: pwr_decoder_fwd then pwr_decoder_bwd_loss (ops.ONE_PASS_LAST_STAGE = False), "
-            "622 780 + 721 120 + 1 409 024 B/sample")
+            "622 780 + 721 120 + 1 409 024 B/sample", "two")
         # (2) compact targets: the SFR builder emits 64 B of taps per joint instead of two dense maps and the
         # loss kernel evaluates the heat-map / depth-map targets on the fly
         sparse = timed_variant(
-            dict(sfr_kw, targets="sparse"), True,
+            frames, dict(sfr_kw, targets="sparse"), True,
             {"pwr_sfr_build": roofline.sfr_build_sparse_bytes(J),
              "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, sparse=True)},
             roofline.step_one_pass_bytes(J, sparse=True),
             "same step, same results; targets handed to the loss kernel as 64-byte taps per joint instead of two "
-            "dense 16 KiB maps (sfr.build_sfr(targets='sparse'))")
+            "dense 16 KiB maps (sfr.build_sfr(targets='sparse'))", "sparse")
+        # (3) the step fed with the raw 16-bit sensor frames (half the source bytes; PNG decode + hand rectangle of
+        # load_from_text inside the SFR kernel), dense targets, against SURVEY 8d's bytes
+        if raw_frames is not None and args.frame_format == "f32" and not args.augment:
+            raw_step = timed_variant(
+                raw_frames, raw_kw, True,
+                {"pwr_sfr_build": roofline.sfr_build_bytes(J), "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J)},
+                roofline.step_one_pass_bytes(J),
+                "same step on raw uint16 %s frames resident in HBM, decoded inside the SFR kernel with the "
+                "load_from_text hand rectangle (SURVEY 8f-1)" % raw_fmt, "raw")
+
+    # ---- the kernels of an INNER stage (north_star's training is 2 stages, model.py:200-210): forward with the
+    # loss riding along, and the backward with dense upstream gradients on the heat maps and depth maps ----
+    def time_launch(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(iters):
+            fn()
+        s1.record()
+        torch.cuda.synchronize()
+        return max_over_ranks(s0.elapsed_time(s1) / iters)
+
+    def entry(ms, bytes_per_sample, what):
+        gbs = bytes_per_sample * B / (ms * 1e-3) / 1e9
+        return {"avg_ms": ms, "algorithmic_bytes_per_sample": bytes_per_sample, "achieved_gbs": gbs, "frac": gbs / peak,
+                "what": what}
+
+    inner = two_stage = None
+    if not args.no_extras:
+        sampler.section("inner_stage")
+        batch = sfr.build_sfr(frames, com, cube, uvd, **sfr_kw)
+        zd, Dd, wd = z.detach(), D.detach(), w.detach()
+        dense_t = (batch.heatmaps, batch.depthmaps, batch.uvd)
+        gH_up = torch.randn(B, J, 64, 64, device=dev, generator=g) * 1e-4
+        gD_up = torch.randn(B, J, 64, 64, device=dev, generator=g) * 1e-4
+        g_uvd = torch.randn(B, J, 3, device=dev, generator=g) * 1e-3
+        one = torch.ones((), device=dev)
+        it = max(10, args.steps // 2)
+        _, uvd_f, stats_f, _ = ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t)
+        ms_fwd = time_launch(lambda: ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t), it)
+        ms_bwd_a1 = time_launch(lambda: ops.decoder_backward_raw(
+            zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, g_uvd, gH_up, gD_up, targets=dense_t, alpha=1.0,
+            loss_scale_dev=one), it)
+        ms_bwd_a05 = time_launch(lambda: ops.decoder_backward_raw(
+            zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, g_uvd, gH_up, gD_up, targets=dense_t, alpha=0.5,
+            loss_scale_dev=one), it)
+        inner = {
+            "pwr_decoder_fwd+loss": entry(ms_fwd, roofline.decoder_fwd_bytes(J, with_targets=True),
+                                          "inner-stage forward, H stored, loss value from dense targets (decoder_fwd_kernel)"),
+            "pwr_decoder_bwd_loss alpha=1": entry(ms_bwd_a1, roofline.decoder_bwd_bytes(J, with_targets=False, upstream_maps=True),
+                                                  "inner-stage backward, dense gH_up / gD_up, map targets carry no weight "
+                                                  "and are not read (train.py default alpha = 1): 6J + 2 maps"),
+            "pwr_decoder_bwd_loss alpha=0.5": entry(ms_bwd_a05, roofline.decoder_bwd_bytes(J, with_targets=True, upstream_maps=True),
+                                                    "inner-stage backward, dense targets AND dense gH_up / gD_up: SURVEY 8d's "
+                                                    "131 072 J + 32 768 B (six-slot pipelined kernel)"),
+            "clocks": sampler.end_section("inner_stage"),
+        }
+        # the decoder work of one 2-stage training step, in forward_loss's order (model.py:200-210, train.py:192-207):
+        # stage-0 forward+loss, last stage in one pass, stage-0 backward with the dense gradients the next stage's
+        # conv would hand back (synthetic here: the conv backbone is out of scope)
+        sampler.section("two_stage_decoder")
+
+        def two_stage_pass():
+            ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t)
+            ops.decoder_fused_raw(zd, wd, Dd, batch.label_img, batch.mask, dense_t, "softmax", alpha, store_heat=False)
+            ops.decoder_backward_raw(zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, None, gH_up, gD_up,
+                                     targets=dense_t, alpha=alpha, loss_scale_dev=one)
+
+        ms_two = time_launch(two_stage_pass, it)
+        bytes_two = (roofline.decoder_fwd_bytes(J, with_targets=True) + roofline.decoder_fused_bytes(J, store_heat=False) +
+                     roofline.decoder_bwd_bytes(J, with_targets=(alpha != 1.0), upstream_maps=True))
+        two_stage = entry(ms_two, bytes_two, "decoder kernels of a 2-stage training step at alpha = %g: stage-0 forward+loss, "
+                          "last stage in one pass (no H store), stage-0 backward with dense upstream maps" % alpha)
+        two_stage["samples_per_s"] = B * world / (ms_two * 1e-3)
+        two_stage["clocks"] = sampler.end_section("two_stage_decoder")
+        del batch, gH_up, gD_up, stats_f, uvd_f
+        torch.cuda.empty_cache()
 
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region ----
-    def run_e2e(frames_dev, kw, what):
-        src = dict(frames=frames_dev, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach())
+    def run_e2e():
+        """Public feed API: raw uint16 frames + annotations live in pinned host memory; every step the annotations are
+        copied and pwr_sfr_fetch pulls the crop windows over PCIe on the copy stream while the previous batch is being
+        built and decoded; the loss vector and the decoded joints are read back and waited for every step.  The
+        logits stand in for the conv backbone's outputs, which only ever exist on the device."""
+        import numpy as np
+        fmt = raw_fmt if raw_frames is not None else "f32"
+        src = raw_frames if raw_frames is not None else frames
+        host_frames = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        host_frames.copy_(src)
+        host = {"com": com.cpu().numpy(), "cube": cube.cpu().numpy(), "uvd": uvd.cpu().numpy()}
+        pf = (40.0, shape.halfu, shape.halfv) if raw_frames is not None else None
+        hf = feed.HostFeed(shape, B, frame_format=fmt, prefilter=pf, device=dev)
+        out_host = torch.empty(4 + B * J * 3, pin_memory=True)
+        done = torch.cuda.Event()
+        zz, DD = z.detach().requires_grad_(True), D.detach().requires_grad_(True)
+
+        def submit():
+            return hf.submit(host_frames, host["com"], host["cube"], host["uvd"])
+
+        def consume(t):
+            batch = hf.build(t)
+            total, terms, uvd_out = step(batch, None, None, None, zz, DD)
+            if world > 1:                                    # the logged terms are being averaged on the side stream
+                torch.cuda.current_stream().wait_stream(comm_stream)
+                pending["work"] = False
+            out_host[:1].copy_(total.detach().reshape(1), non_blocking=True)
+            out_host[1:4].copy_(terms, non_blocking=True)
+            out_host[4:].copy_(uvd_out.reshape(-1), non_blocking=True)
+            done.record()
+
+        n_e2e = args.e2e_steps or min(args.steps, 20)
+        t = submit()
+        for _ in range(3):                                   # warm-up with the pipeline running
+            nxt = submit()
+            consume(t)
+            done.synchronize()
+            t = nxt
+        fetched = hf.fetched_bytes(t)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            nxt = submit()                                   # batch k+1 starts crossing PCIe
+            consume(t)                                       # batch k: build + decode + loss + backward + D2H
+            done.synchronize()                               # the host holds loss and joints of batch k
+            t = nxt
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt)
+        loss_host = float(out_host[0])
+        h2d = fetched + hf.h2d_bytes_small
+        res = {"value": B * world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": out_host.numel() * 4, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+               "pcie_gbs_per_gpu": h2d / (dt / n_e2e) / 1e9, "window_hw": list(hf.win_hw), "loss_read_back": loss_host,
+               "frames_in_host_memory_bytes": host_frames.numel() * host_frames.element_size(),
+               "note": "per rank and step: com + cube + uvd (%d B) copied from pinned host memory and the crop windows of "
+                       "the raw %s frames (%d B of the %d B the frames occupy) pulled over PCIe by pwr_sfr_fetch on a "
+                       "copy stream, one batch ahead of the compute stream (feed.HostFeed); loss[4] + uvd[B,J,3] read back "
+                       "and waited for every step; the logits z, D stay on the device (they are the conv backbone's outputs); "
+                       "wall clock, max over ranks" % (hf.h2d_bytes_small, fmt, fetched,
+                                                       host_frames.numel() * host_frames.element_size())}
+        del host_frames, hf
+        return res
+
+    def run_e2e_whole_frames(n_steps=3):
+        """Round 1's definition, kept for continuity: whole float32 frames AND the logits cross PCIe, serially."""
+        src = dict(frames=frames, com=com, cube=cube, uvd=uvd, z=z.detach(), D=D.detach())
         host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in src.items()}
         for k, v in src.items():
             host[k].copy_(v)
         out_host = {"loss": torch.empty(4, pin_memory=True), "uvd": torch.empty(B, J, 3, pin_memory=True)}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
         dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
 
         def e2e_step():
@@ -386,42 +594,33 @@ def run_b200(args):
                 dev_in[k].copy_(host[k], non_blocking=True)
             z_ = dev_in["z"].requires_grad_(True)
             D_ = dev_in["D"].requires_grad_(True)
-            total, terms, uvd_out = step(dev_in["frames"], dev_in["com"], dev_in["cube"], dev_in["uvd"], z_, D_, kw)
-            out_host["loss"].copy_(torch.cat([total.detach().reshape(1), terms]), non_blocking=True)
+            total, terms, uvd_out = step(dev_in["frames"], dev_in["com"], dev_in["cube"], dev_in["uvd"], z_, D_, None, "e2e_r1")
+            out_host["loss"][:1].copy_(total.detach().reshape(1), non_blocking=True)
+            out_host["loss"][1:].copy_(terms, non_blocking=True)
             out_host["uvd"].copy_(uvd_out, non_blocking=True)
             torch.cuda.synchronize()
             dev_in["z"].requires_grad_(False)
             dev_in["D"].requires_grad_(False)
 
-        n_e2e = args.e2e_steps or min(args.steps, 10)
-        for _ in range(2):
-            e2e_step()
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
+        for _ in range(n_steps):
             e2e_step()
         barrier()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        del host, dev_in
-        return {"value": B * world * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": n_e2e,
-                "note": "per rank and step: %s + com + cube + uvd + z + D copied from pinned host memory, "
-                        "loss[4] + uvd[B,J,3] read back; wall clock with device sync, max over ranks" % what}
+        dt = max_over_ranks(time.perf_counter() - t0)
+        arenas.pop("e2e_r1", None)
+        return {"value": B * world * n_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "steps": n_steps,
+                "note": "round 1's e2e definition: whole %s frames + com + cube + uvd + the logits z, D copied serially "
+                        "from pinned host memory every step (no overlap, no windows)" % args.frame_format}
 
-    e2e = e2e_raw = None
+    e2e = e2e_r1 = None
     if not args.no_e2e:
-        e2e = run_e2e(frames, sfr_kw, "%s frames" % args.frame_format)
-        if args.frame_format == "f32" and not shape.frame_f64:
-            # the same step fed with the raw 16-bit sensor frame (what the host actually holds before
-            # load_from_text decodes it): PNG decode + hand rectangle run inside the SFR kernel
-            raw_fmt = "nyu_gb16" if shape.name == "NYU" else "u16"
-            raw = frames.round().clamp_(0, 65535).to(torch.int32).to(torch.uint16)
-            raw_kw = dict(fx=shape.fx, fy=shape.fy, frame_format=raw_fmt, prefilter=(40.0, shape.halfu, shape.halfv))
-            e2e_raw = run_e2e(raw, raw_kw, "raw uint16 (%s) frames" % raw_fmt)
-            del raw
+        sampler.section("e2e")
+        e2e = run_e2e()
+        e2e["clocks"] = sampler.end_section("e2e")
+        if not args.no_extras:
+            e2e_r1 = run_e2e_whole_frames()
 
     # ---- GPU baseline of configs[1] ("vs reference PyTorch path"): the reference's decoder + loss
     # lines as plain eager PyTorch ops on the same GPU and inputs (the SFR builder has no GPU
@@ -435,6 +634,44 @@ def run_b200(args):
         del batch
         torch.cuda.empty_cache()
 
+    # ---- the records of BASELINE configs[2], [3], [4] ----
+    train_step = train_msra = sweep = None
+    if not args.no_extras:
+        del frames, raw_frames, z, D, d
+        arenas.clear()
+        torch.cuda.empty_cache()
+        from examples import train_synthetic as ts
+        from tools import sweep_inference
+        # configs[2]: NYU-shape end-to-end training step (train.py:158-208), batch 128 per GPU, DDP over NCCL when
+        # N > 1; the same step with the decoder + loss as the reference writes them (eager), with the drop-in
+        # model (fused decoder kernels, reference loss lines), and with the fused criterion
+        sampler.section("train_step")
+        train_step = {"config": "configs[2]: NYU shape (J=14), batch 128 per GPU, 2 stages, features 128, level 4, "
+                                "InstanceNorm, AdamW; on-GPU SFR build + cuDNN backbone + decoder + loss; DDP over NCCL "
+                                "when n_gpus > 1", "n_gpus": world, "batch_per_gpu": 128}
+        for mode in ("eager", "dropin", "fused"):
+            train_step[mode] = ts.run_training(synth.NYU, 128, args.train_steps, 3, mode, world=world, rank=rank,
+                                               local=local_rank)
+        train_step["speedup_fused_over_eager"] = train_step["eager"]["ms_per_step"] / train_step["fused"]["ms_per_step"]
+        train_step["clocks"] = sampler.end_section("train_step")
+        # configs[3]: MSRA shape (J = 21, 240x320 float64-semantics frames, centre-of-mass fallback, cube 125)
+        sampler.section("train_msra")
+        train_msra = {"config": "configs[3]: MSRA shape (J=21, float64 frame semantics, CoM from the frame), batch 128 per "
+                                "GPU, fused criterion, DDP over NCCL when n_gpus > 1", "n_gpus": world, "batch_per_gpu": 128}
+        train_msra["fused"] = ts.run_training(synth.MSRA, 128, args.train_steps, 3, "fused", world=world, rank=rank,
+                                              local=local_rank)
+        train_msra["clocks"] = sampler.end_section("train_msra")
+        # configs[4]: HAND17-shape inference sweep (test.py:93-124 around the backbone), every rank its own replica
+        sampler.section("sweep")
+        rows = sweep_inference.sweep(synth.HAND17, [int(b) for b in args.sweep_batches.split(",")], 10, 3, world, rank,
+                                     local_rank, peak)
+        sweep = {"config": "configs[4]: HAND17 shape (J=21), test-only SFR + decoder forward without the heat-map store + "
+                           "recover_uvd, per-replica batch swept, %d independent replica(s)" % world,
+                 "rows": [{k: r[k] for k in ("batch_per_gpu", "ms_calls", "ms_graph", "samples_per_s_calls",
+                                             "samples_per_s_graph", "roofline_frac_calls", "roofline_frac_graph",
+                                             "graph_equals_calls")} for r in rows],
+                 "clocks": sampler.end_section("sweep")}
+
     # ---- CPU baseline: oracle port on the host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -442,26 +679,34 @@ def run_b200(args):
         res = cpu_baseline.time_path(shape, args.cpu_samples, seed=0, repeats=2)
         cpu = {"value": res["samples_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
                "sample": res["sample"] + "; best of 2 passes"}
+    sampler.stop()
 
     if rank == 0:
         dk = kernels[dominant]
+        cfg = workload_config(shape, B, args.frame_format, args.augment, alpha, lambda_h, lambda_d)
+        cfg.update({"l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
+                          % (B * shape.height * shape.width * (4 if args.frame_format == "f32" else 2) / 1e9,
+                             B * J * 4096 * 4 / 1e9),
+                    "algorithmic_bytes_per_sample": step_bytes,
+                    "last_stage": "one pass (pwr_decoder_fwd_bwd_loss): forward + loss + backward visit z, D and "
+                                  "the targets once; the two-kernel route of SURVEY 8d is timed in `two_kernel_step`"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, B), "batch_per_gpu": B, "joints": J,
-                       "frame_format": args.frame_format, "augment": bool(args.augment),
-                       "alpha": alpha, "lambda_h": lambda_h, "lambda_d": lambda_d,
-                       "l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
-                             % (frames.numel() * frames.element_size() / 1e9, z.numel() * 4 / 1e9),
-                       "algorithmic_bytes_per_sample": step_bytes,
-                       "last_stage": "one pass (pwr_decoder_fwd_bwd_loss): forward + loss + backward visit z, D and "
-                                     "the targets once; the two-kernel route of SURVEY 8d is timed in `two_kernel_step`"},
+            "config": cfg,
             "clocks": clocks,
             "e2e": e2e,
-            "e2e_raw_frames": e2e_raw,
+            "ms_per_step_median": median_ms, "value_median": B * world / (median_ms * 1e-3),
+            "e2e_whole_frames_r1_definition": e2e_r1,
             "two_kernel_step": two_kernel,
             "sparse_targets": sparse,
+            "raw_frames_step": raw_step,
+            "inner_stage": inner,
+            "two_stage_decoder": two_stage,
+            "train_step": train_step,
+            "train_msra": train_msra,
+            "sweep": sweep,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
                          "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,

@@ -70,6 +70,62 @@ class _LossModule(torch.nn.Module):
         return self.net.forward_loss(*a)[0]
 
 
+def run_training(shape, batch, steps, warmup, decoder="fused", features=128, level=4, stages=2, alpha=1.0,
+                 world=1, rank=0, local=0, on_timed_start=None):
+    """One training configuration, timed on the device (CUDA events, max over ranks).  The process group must
+    already exist when world > 1.  Returns dict(ms_per_step, samples_per_s, loss, peak_mem_gb)."""
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    net = M.PixelwiseRegression(shape.joints, stage=stages, features=features, level=level,
+                                norm_method="instance").to(dev)
+    # the fused criterion is exposed to DDP as a module whose forward returns the loss
+    wrapped = _LossModule(net) if decoder == "fused" else net
+    model = pd.wrap_ddp(wrapped, local) if world > 1 else wrapped
+    optim = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    d = synth.make_frames_device(shape, batch, seed=rank, device=dev)
+    lambda_h, lambda_d = 1.0, 0.01
+    arena = sfr.SfrArena()
+
+    def step():
+        b = sfr.build_sfr(d["frames"], None if shape.com_from_frame else d["com"], d["cube"], d["uvd"],
+                          fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64, arena=arena)
+        optim.zero_grad(set_to_none=True)
+        if decoder == "fused":
+            loss = model(b.img, b.label_img, b.mask, b.uvd, b.heatmaps, b.depthmaps, alpha, lambda_h, lambda_d)
+        else:
+            if decoder == "eager":
+                results = eager_forward(net, b.img, b.label_img, b.mask)
+            else:
+                results = model(b.img, b.label_img, b.mask)
+            loss = train_py_loss(results, b.uvd, b.heatmaps, b.depthmaps, alpha, lambda_h, lambda_d)
+        loss.backward()
+        optim.step()
+        return loss
+
+    torch.cuda.reset_peak_memory_stats(dev)
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if on_timed_start is not None:
+        on_timed_start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out = {"ms_per_step": ms.item(), "samples_per_s": batch * world / ms.item() * 1e3, "loss": loss.item(),
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    del model, wrapped, net, optim, d, arena
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--decoder", default="fused", choices=["eager", "dropin", "fused"])
@@ -88,68 +144,28 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     shape = synth.SHAPES[args.shape]
-    torch.manual_seed(0)
-    net = M.PixelwiseRegression(shape.joints, stage=args.stages, features=args.features, level=args.level,
-                                norm_method="instance").to(dev)
-    # the fused criterion is exposed to DDP as a module whose forward returns the loss
-    wrapped = _LossModule(net) if args.decoder == "fused" else net
-    model = pd.wrap_ddp(wrapped, local) if world > 1 else wrapped
-    optim = torch.optim.AdamW(net.parameters(), lr=1e-3)
-    d = synth.make_frames_device(shape, args.batch, seed=rank, device=dev)
-    lambda_h, lambda_d = 1.0, 0.01
-
-    def step():
-        batch = sfr.build_sfr(d["frames"], None if shape.com_from_frame else d["com"], d["cube"], d["uvd"],
-                              fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
-        optim.zero_grad(set_to_none=True)
-        if args.decoder == "fused":
-            loss = model(batch.img, batch.label_img, batch.mask, batch.uvd, batch.heatmaps, batch.depthmaps,
-                         args.alpha, lambda_h, lambda_d)
-        else:
-            if args.decoder == "eager":
-                results = eager_forward(net, batch.img, batch.label_img, batch.mask)
-            else:
-                results = model(batch.img, batch.label_img, batch.mask)
-            loss = train_py_loss(results, batch.uvd, batch.heatmaps, batch.depthmaps, args.alpha, lambda_h, lambda_d)
-        loss.backward()
-        optim.step()
-        return loss
-
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(args.steps):
-        loss = step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([s.elapsed_time(e) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    r = run_training(shape, args.batch, args.steps, args.warmup, args.decoder, args.features, args.level, args.stages,
+                     args.alpha, world, rank, local)
     if rank == 0:
         print("decoder=%s shape=%s gpus=%d batch/gpu=%d: %.2f ms/step, %.0f samples/s, loss %.5f, peak mem %.1f GB" % (
-            args.decoder, shape.name, world, args.batch, ms.item(), args.batch * world / ms.item() * 1e3, loss.item(),
-            torch.cuda.max_memory_allocated() / 1e9))
+            args.decoder, shape.name, world, args.batch, r["ms_per_step"], r["samples_per_s"], r["loss"],
+            r["peak_mem_gb"]))
         if args.json:
             import json
             with open(args.json, "w") as f:
                 f.write(json.dumps({
-                    "metric": "end-to-end training samples/s", "value": args.batch * world / ms.item() * 1e3,
+                    "metric": "end-to-end training samples/s", "value": r["samples_per_s"],
                     "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                    "ms_per_step": ms.item(), "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                    "ms_per_step": r["ms_per_step"], "scaling": "weak", "dtype": "f32", "data": "synthetic",
                     "config": {"workload": "configs[2]: %s-shape end-to-end training step (on-GPU SFR build, cuDNN "
                                            "hourglass backbone, fused decoder + loss, AdamW), batch %d/GPU, DDP over NCCL"
                                            % (shape.name, args.batch),
                                "decoder": args.decoder, "features": args.features, "stages": args.stages,
                                "level": args.level, "joints": shape.joints},
-                    "loss": loss.item(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}) + "\n")
+                    "loss": r["loss"], "peak_mem_gb": r["peak_mem_gb"]}) + "\n")
     if world > 1:
         dist.destroy_process_group()
 

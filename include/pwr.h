@@ -139,6 +139,7 @@ int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf,
                  float* img, float* label_img, float* mask,
                  float* box_size, float* cube_size, float* com_out,
                  uint8_t* valid, void* workspace, size_t workspace_size,
+                 const int* win_extent, int win_h, int win_w,
                  int B, void* stream);
 
 /* Train-mode SFR (the 9-tuple of datasets.py:403): everything pwr_sfr_crop
@@ -173,7 +174,33 @@ int pwr_sfr_build(const void* frames, int frame_format, int Hf, int Wf,
                   float* uvd_norm, float* heatmaps, float* dmap,
                   pwr_joint_taps* joint_taps,
                   uint8_t* valid, void* workspace, size_t workspace_size,
+                  const int* win_extent, int win_h, int win_w,
                   int B, int J, void* stream);
+
+/* Host -> device feed of the depth frames (replaces the `.to(device)` of the whole frame,
+ * train.py:161-166 / test.py:96-100).  `frames` [B,Hf,Wf] in `frame_format` may live in PINNED host
+ * memory (cudaHostAlloc / torch pin_memory: device-addressable under UVA) - the one exception to
+ * "every pointer is a device pointer" - or in device memory.  For every sample the kernel copies
+ * only the region the builder can read, rows x cols of the crop box (datasets.py:306-311,
+ * utils.py:167-173) intersected with the frame and, with the prefilter, with the hand rectangle of
+ * load_from_text, columns rounded outwards to 16 bytes, into windows[b] ([win_h, win_w] elements of
+ * the same format) and records it in win_extent[b] = (row0, col0, rows, cols).  With `aug`
+ * (the [B,8] block of pwr_sfr_build) the union with the shifted-centre box is fetched.
+ * pwr_sfr_crop / pwr_sfr_build then take (windows, win_extent, win_h, win_w) in place of the frames
+ * ("window mode": frames = windows, Hf / Wf still the true frame size) and produce bit-identical
+ * results; win_extent == NULL there means whole frames.
+ *   fetched_bytes: optional device counter, incremented by the bytes read from `frames`.
+ *   status: optional device int, OR-ed with 1 if some region did not fit [win_h, win_w] (the caller
+ *   sized the windows too small; that sample is then built from a truncated window).
+ * Requires Wf * elem % 16 == 0 and win_w * elem % 16 == 0 (PWR_E_SHAPE otherwise). */
+int pwr_sfr_fetch(const void* frames, int frame_format, int Hf, int Wf,
+                  const double* com, const double* cube, const double* aug,
+                  double fx, double fy,
+                  double prefilter_margin, double prefilter_umax,
+                  double prefilter_vmax,
+                  void* windows, int win_h, int win_w, int* win_extent,
+                  unsigned long long* fetched_bytes, int* status,
+                  int B, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Differentiable decoder

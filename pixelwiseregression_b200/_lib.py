@@ -32,9 +32,11 @@ SIGNATURES = {
     "pwr_set_option": [_I, _I],
     "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
     "pwr_sfr_workspace_bytes": [_I, _I],
-    "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I, _P],
+    "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _I, _I,
+                     _I, _P],
     "pwr_sfr_build": [_P, _I, _I, _I, _P, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                      _P, _P, _SZ, _I, _I, _P],
+                      _P, _P, _SZ, _P, _I, _I, _I, _I, _P],
+    "pwr_sfr_fetch": [_P, _I, _I, _I, _P, _P, _P, _D, _D, _D, _D, _D, _P, _I, _I, _P, _P, _P, _I, _P],
     "pwr_decoder_fwd": [_P] * 13 + [_I, _I, _I, _I, _P],
     "pwr_decoder_bwd": [_P] * 13 + [_I, _I, _I, _I, _P],
     "pwr_decoder_bwd_loss": [_P] * 14 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _I, _P],
@@ -117,7 +119,7 @@ class option:
 
 
 LAUNCHES = {}          # entry point -> number of kernels launched through it
-KERNELS_PER_CALL = {"pwr_sfr_build": 2, "pwr_sfr_crop": 2}    # prep + main; every other entry point is one kernel
+KERNELS_PER_CALL = {"pwr_sfr_build": 2, "pwr_sfr_crop": 2, "pwr_sfr_fetch": 1}    # prep + main; every other entry point is one kernel
 PROFILE = None         # when a list: (entry point, start event, end event) per launch
 
 

@@ -23,7 +23,7 @@
 //                            with dense targets or dense upstream gradients
 //   decoder_bwd_lean_kernel  persistent, 2 CTAs/SM; backward(+loss) with no dense map
 //                            beyond z, D (compact targets, uvd-only loss)
-//   decoder_bwd_kernel       one CTA per item; the configurations nothing else takes
+//   decoder_bwd_kernel       one CTA per item; only the plane-only call (no depth branch) lands here
 //   decoder_fused_kernel     persistent, 2 CTAs/SM, six-slot FIFO ring; last stage
 //                            forward + loss + backward in one pass
 //
@@ -515,8 +515,9 @@ decoder_bwd_kernel(const void* __restrict__ z, const float* __restrict__ w, cons
 //
 // A stage has four 16 KB slots: z, D and two optional maps whose meaning the
 // host picks: (heat_gt, dmap_gt) for the fused loss, or (gH_up, gD_up) for
-// dense upstream gradients.  Configurations that need both pairs at once go
-// through the direct-load kernel.
+// dense upstream gradients.  Configurations that need both pairs at once (an inner
+// stage trained with alpha < 1 on dense targets) run the six-slot instantiation (BOTH):
+// 2 x 96 KB of stages, with L, m read through L2 instead of a shared-memory pair.
 #ifndef PWR_PIPE_THREADS
 #define PWR_PIPE_THREADS 512
 #endif
@@ -526,6 +527,9 @@ constexpr int kPipeVec = kMap / 4 / kPipeThreads;     // float4 chunks per threa
 constexpr int kPipeStages = 2;
 constexpr int kSlotBytes = kMap * 4;                  // 16 KB
 constexpr int kPipeSmemBytes = kPipeStages * 4 * kSlotBytes + 2 * 2 * kSlotBytes + 64;
+// six-slot variant (dense targets AND dense upstream gradients at once: an inner stage with alpha < 1):
+// z, D, heat_gt, dmap_gt, gH_up, gD_up per stage; L, m are then read through L2 instead of a shared-memory pair
+constexpr int kPipeSmemBytesBoth = kPipeStages * 6 * kSlotBytes + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -800,6 +804,7 @@ struct PipeArgs {
     const void* z; const float* w; const void* D; const float* L; const float* m;
     const float* stats; const float* uvd; const float* g_uvd;
     const float* slot2; const void* slot3;     // (heat_gt, dmap_gt) or (gH_up, gD_up); either may be NULL
+    const float* slot4; const void* slot5;     // BOTH variant only: (gH_up, gD_up) next to the targets in slot2/3
     const float* uvd_gt;
     const pwr_joint_taps* taps;                // sparse targets (then slot2/slot3 carry no targets)
     LossCoef coef;
@@ -808,13 +813,15 @@ struct PipeArgs {
     int slots_are_targets;                     // 1: slot2/3 = heat_gt/dmap_gt, 0: = gH_up/gD_up
 };
 
-template <int METHOD, int LOSS, typename TZ>
+template <int METHOD, int LOSS, typename TZ, bool BOTH = false>
 __global__ void __launch_bounds__(kPipeThreads, 1)
 decoder_bwd_pipe_kernel(PipeArgs a) {
+    static_assert(!BOTH || LOSS == LOSS_DENSE, "six slots = dense targets + dense upstream gradients");
+    constexpr int kSlots = BOTH ? 6 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stage_base = reinterpret_cast<float*>(smem_raw);                               // [stages][4][4096]
-    float* lm_base = stage_base + kPipeStages * 4 * kMap;                                 // [2][2][4096]
-    uint64_t* full = reinterpret_cast<uint64_t*>(lm_base + 2 * 2 * kMap);                 // [stages]
+    float* stage_base = reinterpret_cast<float*>(smem_raw);                               // [stages][kSlots][4096]
+    float* lm_base = stage_base + kPipeStages * kSlots * kMap;                            // [2][2][4096] (not BOTH)
+    uint64_t* full = reinterpret_cast<uint64_t*>(lm_base + (BOTH ? 0 : 2 * 2 * kMap));    // [stages]
     __shared__ float scratch[2][kPipeWarps * 5];      // double-buffered: one barrier per reduction
     // Per-item scalars (stats, upstream / predicted / target uvd, the 64-byte taps record) are
     // prefetched one item ahead by the first 32 threads: the global loads are issued at the top of
@@ -839,16 +846,18 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
     __syncthreads();
 
     const bool has2 = a.slot2 != nullptr, has3 = a.slot3 != nullptr;
-    const bool tg = a.slots_are_targets != 0;
+    const bool has4 = BOTH && a.slot4 != nullptr, has5 = BOTH && a.slot5 != nullptr;
+    const bool tg = BOTH || a.slots_are_targets != 0;
     constexpr uint32_t kZBytes = kMap * sizeof(TZ);                  // z, D (and gD_up) in the conv dtype
     const uint32_t slot3_bytes = tg ? kSlotBytes : kZBytes;          // dmap_gt is float32, gD_up is TZ
-    const uint32_t stage_tx = 2 * kZBytes + (has2 ? kSlotBytes : 0) + (has3 ? slot3_bytes : 0);
+    const uint32_t stage_tx = 2 * kZBytes + (has2 ? kSlotBytes : 0) + (has3 ? slot3_bytes : 0) +
+                              (has4 ? kSlotBytes : 0) + (has5 ? kZBytes : 0);
 
     // producer (thread 0): stream item `it` into stage `s`; fetch L, m when the sample changes
     auto issue = [&](long long it, int b, int s, int prev_b, int lm_buf) {
         const size_t off = static_cast<size_t>(it) * kMap;
-        float* st = stage_base + s * 4 * kMap;
-        const bool new_lm = (b != prev_b);
+        float* st = stage_base + s * kSlots * kMap;
+        const bool new_lm = !BOTH && (b != prev_b);
         mbar_expect_tx(&full[s], stage_tx + (new_lm ? 2 * kSlotBytes : 0));
         bulk_g2s(st, static_cast<const TZ*>(a.z) + off, kZBytes, &full[s]);
         bulk_g2s(st + kMap, static_cast<const TZ*>(a.D) + off, kZBytes, &full[s]);
@@ -857,6 +866,8 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
             if (tg) bulk_g2s(st + 3 * kMap, static_cast<const float*>(a.slot3) + off, kSlotBytes, &full[s]);
             else    bulk_g2s(st + 3 * kMap, static_cast<const TZ*>(a.slot3) + off, kZBytes, &full[s]);
         }
+        if (has4) bulk_g2s(st + 4 * kMap, a.slot4 + off, kSlotBytes, &full[s]);
+        if (has5) bulk_g2s(st + 5 * kMap, static_cast<const TZ*>(a.slot5) + off, kZBytes, &full[s]);
         if (new_lm) {
             float* lm = lm_base + lm_buf * 2 * kMap;
             bulk_g2s(lm, a.L + static_cast<size_t>(b) * kMap, kSlotBytes, &full[s]);
@@ -924,7 +935,7 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
             __syncthreads();
         }
 
-        const float* sz = stage_base + s * 4 * kMap;          // slot bases (each slot is 16 KiB apart)
+        const float* sz = stage_base + s * kSlots * kMap;     // slot bases (each slot is 16 KiB apart)
         const float* sD = sz + kMap;
         const float4* s2 = reinterpret_cast<const float4*>(sz + 2 * kMap);
         const float* s3 = sz + 3 * kMap;
@@ -942,13 +953,20 @@ decoder_bwd_pipe_kernel(PipeArgs a) {
 #pragma unroll
         for (int i = 0; i < kPipeVec; ++i) {
             const int cidx = tid + i * kPipeThreads;
-            const float4 z4 = MapIO<TZ>::smem(sz, cidx), d4 = MapIO<TZ>::smem(sD, cidx), l4 = sL[cidx], m4 = sM[cidx];
+            const float4 z4 = MapIO<TZ>::smem(sz, cidx), d4 = MapIO<TZ>::smem(sD, cidx);
+            // BOTH: no shared-memory pair for L, m (the six slots fill it); the J items of a sample share them in L2
+            const float4 l4 = BOTH ? ld_keep(a.L + static_cast<size_t>(b_cur) * kMap + cidx * 4) : sL[cidx];
+            const float4 m4 = BOTH ? ld_keep(a.m + static_cast<size_t>(b_cur) * kMap + cidx * 4) : sM[cidx];
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             // slot 2 / 3 hold either dense targets (tg) or dense upstream gradients
             const float4 q2 = has2 ? s2[cidx] : zero4;
             const float4 q3 = has3 ? (tg ? MapIO<float>::smem(s3, cidx) : MapIO<TZ>::smem(s3, cidx)) : zero4;
             float4 t2 = tg ? q2 : zero4, t3 = tg ? q3 : zero4;          // targets
-            const float4 u2 = tg ? zero4 : q2, u3 = tg ? zero4 : q3;    // upstream gradients
+            float4 u2 = tg ? zero4 : q2, u3 = tg ? zero4 : q3;          // upstream gradients
+            if (BOTH) {
+                if (has4) u2 = reinterpret_cast<const float4*>(sz + 4 * kMap)[cidx];
+                if (has5) u3 = MapIO<TZ>::smem(sz + 5 * kMap, cidx);
+            }
             if (sparse) sparse_lookup(tp, fp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
             const bool have_h = sparse || (tg && has2), have_d = sparse || (tg && has3);
             const float gyrow = gv63 * (ys0 + static_cast<float>(kPipeThreads / 16) * i);
@@ -1738,12 +1756,15 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
     if (!map_terms) taps = nullptr;
     const int loss_mode = !loss ? LOSS_NONE : (taps != nullptr ? LOSS_SPARSE : LOSS_DENSE);
     const bool need_up = gH_up != nullptr || gD_up != nullptr;
-    if (D != nullptr && !(need_targets && need_up) && !force_direct_bwd()) {
+    if (D != nullptr && !force_direct_bwd()) {
         PipeArgs a;
         const bool lean = !need_targets && !need_up && !no_lean_bwd();      // no dense map beyond z, D
+        const bool both = need_targets && need_up;                          // six-slot stage
         a.z = z; a.w = w; a.D = D; a.L = L; a.m = m; a.stats = stats; a.uvd = uvd; a.g_uvd = g_uvd;
         a.slot2 = need_targets ? heat_gt : gH_up;
         a.slot3 = need_targets ? static_cast<const void*>(dmap_gt) : gD_up;
+        a.slot4 = both ? gH_up : nullptr;
+        a.slot5 = both ? gD_up : nullptr;
         a.uvd_gt = uvd_gt; a.taps = taps; a.coef = coef; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial;
         a.loss_partial = loss_partial; a.J = J; a.items = B * J;
         a.slots_are_targets = need_targets ? 1 : 0;
@@ -1761,6 +1782,26 @@ static int launch_bwd(bool loss, const void* z, const float* w, const void* D, c
             return launch_status();
         }
         const int grid = a.items < sms ? a.items : sms;
+        if (both) {
+            // dense targets + dense upstream gradients (inner stage, alpha < 1): loss_mode is LOSS_DENSE here
+#define PWR_LAUNCH_PIPE6(M, TZ)                                                                                \
+    do {                                                                                                       \
+        PWR_ENSURE_DYN_SMEM(kPipeSmemBytesBoth, dev, decoder_bwd_pipe_kernel<M, LOSS_DENSE, TZ, true>);        \
+        decoder_bwd_pipe_kernel<M, LOSS_DENSE, TZ, true><<<grid, kPipeThreads, kPipeSmemBytesBoth, s>>>(a);    \
+    } while (0)
+            if (method == PWR_METHOD_GIVEN) PWR_LAUNCH_PIPE6(PWR_METHOD_GIVEN, float);
+            else if (method == PWR_METHOD_SOFTMAX) {
+                if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_PIPE6(PWR_METHOD_SOFTMAX, float);
+                else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_PIPE6(PWR_METHOD_SOFTMAX, __half);
+                else                                 PWR_LAUNCH_PIPE6(PWR_METHOD_SOFTMAX, __nv_bfloat16);
+            } else {
+                if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_PIPE6(PWR_METHOD_SUM, float);
+                else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_PIPE6(PWR_METHOD_SUM, __half);
+                else                                 PWR_LAUNCH_PIPE6(PWR_METHOD_SUM, __nv_bfloat16);
+            }
+#undef PWR_LAUNCH_PIPE6
+            return launch_status();
+        }
 #define PWR_LAUNCH_PIPE(M, LS, TZ)                                                                             \
     do {                                                                                                       \
         PWR_ENSURE_DYN_SMEM(kPipeSmemBytes, dev, decoder_bwd_pipe_kernel<M, LS, TZ>);    \

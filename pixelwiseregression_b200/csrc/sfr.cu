@@ -74,8 +74,14 @@ struct SampleGeom {
     int nrows, ncols;          // crop extent (== 2*shift unless truncated)
     int r0, c0;                // int(com_v), int(com_u)
     int pr0, pr1, pc0, pc1;    // frame rows [pr0,pr1) x cols [pc0,pc1) that may be non-zero: the whole frame,
-                               // or the hand rectangle of load_from_text when the prefilter is on
+                               // or the hand rectangle of load_from_text when the prefilter is on; in window
+                               // mode additionally clipped to the part of the frame that was fetched
+    int org_r, org_c;          // frame row / column of element (0,0) of this sample's pixel buffer: (0,0) for
+                               // whole frames, the window origin written by pwr_sfr_fetch in window mode
 };
+
+// Part of frame b that pwr_sfr_fetch copied into windows[b]: rows [row0, row0+rows) x cols [col0, col0+cols).
+struct WinExtent { int row0, col0, rows, cols; };
 
 struct JointParam {
     double tap[4];             // a, b, c, d of utils.py:48-58
@@ -115,6 +121,7 @@ __device__ void sample_geometry(SampleGeom& g, const double* com, double cube, d
                                 double pf_margin, double pf_umax, double pf_vmax) {
     const double cu = com[0], cv = com[1], z = com[2];
     g.z = z; g.cube = cube; g.ok = 0;
+    g.org_r = 0; g.org_c = 0;
     g.pr0 = 0; g.pr1 = Hf; g.pc0 = 0; g.pc1 = Wf;
     g.fr0 = g.fc0 = 0; g.nrows = g.ncols = 0; g.r0 = g.c0 = 0;
     g.scale_x = g.scale_y = 1.0;
@@ -160,6 +167,15 @@ __device__ void sample_geometry(SampleGeom& g, const double* com, double cube, d
     g.scale_y = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(kImage), static_cast<double>(g.nrows)));
     g.scale_x = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(kImage), static_cast<double>(g.ncols)));
     g.ok = 1;
+}
+
+// Window mode: the pixel buffer of the sample holds only `w` of the frame.  Every tap of the crop lies inside
+// the box, and pwr_sfr_fetch copied (box AND non-zero rectangle) rounded outwards to 16 bytes, so clipping the
+// non-zero rectangle to the fetched extent changes no tap's value and guarantees no read outside the buffer.
+__device__ __forceinline__ void clip_to_window(SampleGeom& g, const WinExtent& w) {
+    g.org_r = w.row0; g.org_c = w.col0;
+    g.pr0 = max(g.pr0, w.row0); g.pr1 = min(g.pr1, w.row0 + w.rows);
+    g.pc0 = max(g.pc0, w.col0); g.pc1 = min(g.pc1, w.col0 + w.cols);
 }
 
 // cv::resize INTER_LINEAR tap for destination index d, source extent n
@@ -292,6 +308,9 @@ struct SfrArgs {
     pwr_joint_taps* taps_out;   // [B,J] compact ("sparse") targets, or NULL
     const double* aug;          // [B,8] (scale, shift_u, shift_v, cos a, sin a, cos a', sin a', -) or NULL
     WarpParam* prep_warp;       // workspace: [B] (augmentation only)
+    const WinExtent* win;       // [B] window mode (frames = [B, win_h, win_w] windows written by pwr_sfr_fetch) or NULL
+    int pitch;                  // elements per row of a sample's pixel buffer: Wf, or win_w
+    long long frame_stride;     // elements per sample: Hf*Wf, or win_h*win_w
 };
 
 // Raw sensor formats.  The float32 value the reference would hold is reproduced bit
@@ -319,13 +338,14 @@ __device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx
 // lies inside the frame, so no bounds predicates are needed.
 template <typename T, int FMT, bool INTERIOR>
 __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __restrict__ frame, const SampleGeom& g,
-                                               const TapX* ytap2, const TapX* xtap2, int Wf) {
+                                               const TapX* ytap2, const TapX* xtap2, int pitch) {
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
         const TapX ty = ytap2[dy];
         const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
         const bool ra = INTERIOR || (fr_a >= g.pr0 && fr_a < g.pr1), rb = INTERIOR || (fr_b >= g.pr0 && fr_b < g.pr1);
-        const int row_a = fr_a * Wf, row_b = fr_b * Wf;          // Hf*Wf < 2^31 (checked on the host)
+        // element offsets inside the sample's pixel buffer (Hf*Wf < 2^31, checked on the host)
+        const int row_a = (fr_a - g.org_r) * pitch - g.org_c, row_b = (fr_b - g.org_r) * pitch - g.org_c;
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
             const TapX tx = xtap2[dx];
@@ -440,6 +460,7 @@ sfr_prep_kernel(SfrArgs a) {
             SampleGeom g;
             const double com2[3] = {__dadd_rn(a.com[3 * b + 0], au[1]), __dadd_rn(a.com[3 * b + 1], au[2]), a.com[3 * b + 2]};
             sample_geometry(g, com2, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+            if (a.win != nullptr) clip_to_window(g, a.win[b]);
             *gp = g;
         }
         __syncwarp();
@@ -475,6 +496,7 @@ sfr_prep_kernel(SfrArgs a) {
     if (lane == 0) {
         SampleGeom g;
         sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+        if (a.win != nullptr) clip_to_window(g, a.win[b]);
         *gp = g;
         write_scalar_outputs(a, b, g);
     }
@@ -557,7 +579,7 @@ sfr_build_kernel(SfrArgs a) {
     float* lab_b = a.label_img + static_cast<size_t>(b) * kMap;
     float* msk_b = a.mask + static_cast<size_t>(b) * kMap;
     const void* frame = static_cast<const unsigned char*>(a.frames) +
-                        static_cast<size_t>(b) * a.Hf * a.Wf * (FMT == FMT_F32 ? 4 : 2);
+                        static_cast<size_t>(b) * a.frame_stride * (FMT == FMT_F32 ? 4 : 2);
     const T cube_t = static_cast<T>(g.cube);
     const T cube_r = Arith<T>::rcp(cube_t);
     const bool interior = g.ok && g.fc0 >= g.pc0 && g.fc0 + g.ncols <= g.pc1 && g.fr0 + ytap[0].s0 >= g.pr0 &&
@@ -572,8 +594,8 @@ sfr_build_kernel(SfrArgs a) {
         float2 o0 = make_float2(0.f, 0.f), o1 = o0;
         if (g.ok) {
             T px[2][2];
-            if (interior) resample_block<T, FMT, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Wf);
-            else          resample_block<T, FMT, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.Wf);
+            if (interior) resample_block<T, FMT, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch);
+            else          resample_block<T, FMT, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch);
             // 2x2 mean (cv::resize reroutes an exact 2x INTER_LINEAR shrink to the area path)
             lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
                                 T(0.25));
@@ -714,7 +736,7 @@ sfr_aug_kernel(SfrArgs a) {
 
     // ---- phase 1a: the resized crop (datasets.py:271), one pixel per thread and iteration
     const void* frame = static_cast<const unsigned char*>(a.frames) +
-                        static_cast<size_t>(b) * a.Hf * a.Wf * (FMT == FMT_F32 ? 4 : 2);
+                        static_cast<size_t>(b) * a.frame_stride * (FMT == FMT_F32 ? 4 : 2);
     if (g.ok) {
         for (int p = tid; p < kImage * kImage; p += kAugThreads) {
             const int y = p >> 7, x = p & (kImage - 1);
@@ -722,10 +744,11 @@ sfr_aug_kernel(SfrArgs a) {
             const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1, fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
             const bool ra = fr_a >= g.pr0 && fr_a < g.pr1, rb = fr_b >= g.pr0 && fr_b < g.pr1;
             const bool ca = fc_a >= g.pc0 && fc_a < g.pc1, cb = fc_b >= g.pc0 && fc_b < g.pc1;
-            const float v00 = (ra && ca) ? load_px<FMT>(frame, fr_a * a.Wf + fc_a) : 0.f;
-            const float v01 = (ra && cb) ? load_px<FMT>(frame, fr_a * a.Wf + fc_b) : 0.f;
-            const float v10 = (rb && ca) ? load_px<FMT>(frame, fr_b * a.Wf + fc_a) : 0.f;
-            const float v11 = (rb && cb) ? load_px<FMT>(frame, fr_b * a.Wf + fc_b) : 0.f;
+            const int row_a = (fr_a - g.org_r) * a.pitch - g.org_c, row_b = (fr_b - g.org_r) * a.pitch - g.org_c;
+            const float v00 = (ra && ca) ? load_px<FMT>(frame, row_a + fc_a) : 0.f;
+            const float v01 = (ra && cb) ? load_px<FMT>(frame, row_a + fc_b) : 0.f;
+            const float v10 = (rb && ca) ? load_px<FMT>(frame, row_b + fc_a) : 0.f;
+            const float v11 = (rb && cb) ? load_px<FMT>(frame, row_b + fc_b) : 0.f;
             const T w00 = Arith<T>::window(static_cast<T>(v00), g), w01 = Arith<T>::window(static_cast<T>(v01), g);
             const T w10 = Arith<T>::window(static_cast<T>(v10), g), w11 = Arith<T>::window(static_cast<T>(v11), g);
             const T xa0 = static_cast<T>(tx.a0), xa1 = static_cast<T>(tx.a1);
@@ -785,6 +808,101 @@ sfr_aug_kernel(SfrArgs a) {
 
     // ---- phase 2, pass B
     if (dense && g.ok) patch_footprints<T>(a, g, sm.joints, sm.list, sm.list_n, sm.label, b, 0, kLabel, tid, kAugThreads);
+}
+
+// ---------------------------------------------------------------------------
+// host -> device feed: fetch only what the builder will read (pwr_sfr_fetch)
+// ---------------------------------------------------------------------------
+// train.py:161-166 ships every tensor of the batch with .to(device); for the depth frame that is the whole
+// 480x640 image although the builder reads only the crop box (176-352 px at NYU depths) inside the hand
+// rectangle.  Here the frames stay in pinned (device-mapped) host memory and this kernel pulls, per sample,
+// exactly that region over PCIe with coalesced 16-byte reads - no host-side repacking, no per-sample memcpy
+// call - into a compact [B, win_h, win_w] buffer the builder then reads in "window mode".  One CTA per
+// (sample, row group); thread 0 re-derives the crop geometry with the builder's own code, so the two agree
+// bit for bit.  The same kernel works on device-resident frames (then it is a plain gather in HBM).
+constexpr int kFetchThreads = 256;
+constexpr int kFetchGroups = 4;              // CTAs per sample
+constexpr int kFetchUnroll = 4;              // 16-byte loads in flight per thread
+
+struct FetchArgs {
+    const void* frames; int elem; int Hf, Wf;
+    const double* com; const double* cube; const double* aug;
+    double fx, fy, pf_margin, pf_umax, pf_vmax;
+    void* windows; int win_h, win_w;
+    WinExtent* extent; unsigned long long* fetched_bytes; int* status;
+    int B;
+};
+
+// rows / cols of the frame the builder can touch for this geometry: box AND non-zero rectangle
+__device__ __forceinline__ void needed_region(const SampleGeom& g, int& r0, int& r1, int& c0, int& c1) {
+    if (!g.ok) { r0 = r1 = c0 = c1 = 0; return; }
+    r0 = max(g.fr0, g.pr0); r1 = min(g.fr0 + g.nrows, g.pr1);
+    c0 = max(g.fc0, g.pc0); c1 = min(g.fc0 + g.ncols, g.pc1);
+    if (r1 <= r0 || c1 <= c0) r0 = r1 = c0 = c1 = 0;
+}
+
+__global__ void __launch_bounds__(kFetchThreads)
+sfr_fetch_kernel(FetchArgs a) {
+    __shared__ WinExtent ext;
+    const int b = blockIdx.x / kFetchGroups, grp = blockIdx.x % kFetchGroups;
+    const int per16 = 16 / a.elem;                       // elements per 16-byte chunk
+    if (threadIdx.x == 0) {
+        SampleGeom g;
+        int r0, r1, c0, c1;
+        sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+        needed_region(g, r0, r1, c0, c1);
+        if (a.aug != nullptr) {
+            // the augmented branch crops around the shifted centre (datasets.py:236-246) and falls back to
+            // the plain branch when it raises: fetch the union of both regions
+            const double* au = a.aug + 8 * static_cast<size_t>(b);
+            const double com2[3] = {__dadd_rn(a.com[3 * b + 0], au[1]), __dadd_rn(a.com[3 * b + 1], au[2]), a.com[3 * b + 2]};
+            int q0, q1, p0, p1;
+            sample_geometry(g, com2, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+            needed_region(g, q0, q1, p0, p1);
+            if (q1 > q0) {
+                if (r1 > r0) { r0 = min(r0, q0); r1 = max(r1, q1); c0 = min(c0, p0); c1 = max(c1, p1); }
+                else { r0 = q0; r1 = q1; c0 = p0; c1 = p1; }
+            }
+        }
+        c0 = c0 / per16 * per16;                          // outwards to 16 bytes (Wf * elem % 16 == 0)
+        c1 = min((c1 + per16 - 1) / per16 * per16, a.Wf);
+        int rows = r1 - r0, cols = c1 - c0;
+        if (rows > a.win_h || cols > a.win_w) {           // the caller sized the windows too small
+            if (a.status != nullptr) atomicOr(a.status, 1);
+            rows = min(rows, a.win_h); cols = min(cols, a.win_w / per16 * per16);
+        }
+        ext.row0 = r0; ext.col0 = c0; ext.rows = rows; ext.cols = cols;
+        if (grp == 0) {
+            a.extent[b] = ext;
+            if (a.fetched_bytes != nullptr)
+                atomicAdd(a.fetched_bytes, static_cast<unsigned long long>(rows) * cols * a.elem);
+        }
+    }
+    __syncthreads();
+    const WinExtent e = ext;
+    const int cpr = e.cols / per16;                       // 16-byte chunks per row
+    const int total = e.rows * cpr;
+    const int per = (total + kFetchGroups - 1) / kFetchGroups;
+    const int lo = grp * per, hi = min(total, lo + per);
+    const unsigned char* src = static_cast<const unsigned char*>(a.frames) +
+                               (static_cast<size_t>(b) * a.Hf * a.Wf + static_cast<size_t>(e.row0) * a.Wf + e.col0) * a.elem;
+    unsigned char* dst = static_cast<unsigned char*>(a.windows) + static_cast<size_t>(b) * a.win_h * a.win_w * a.elem;
+    const size_t src_pitch = static_cast<size_t>(a.Wf) * a.elem, dst_pitch = static_cast<size_t>(a.win_w) * a.elem;
+    for (int i = lo + threadIdx.x; i < hi; i += kFetchThreads * kFetchUnroll) {
+        uint4 v[kFetchUnroll];
+        int rr[kFetchUnroll], cc[kFetchUnroll];
+#pragma unroll
+        for (int u = 0; u < kFetchUnroll; ++u) {
+            const int k = i + u * kFetchThreads;
+            rr[u] = k / cpr; cc[u] = k - rr[u] * cpr;
+            if (k < hi) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + rr[u] * src_pitch + cc[u] * 16));
+        }
+#pragma unroll
+        for (int u = 0; u < kFetchUnroll; ++u) {
+            const int k = i + u * kFetchThreads;
+            if (k < hi) *reinterpret_cast<uint4*>(dst + rr[u] * dst_pitch + cc[u] * 16) = v[u];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -857,13 +975,13 @@ static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t str
     if (frame_f64 && fmt != FMT_F32) return PWR_E_METHOD;       // float64 semantics exist for decoded frames only
     const unsigned prep_grid = (a.B + kPrepThreads / 32 - 1) / (kPrepThreads / 32);
     if (TRAIN && a.aug != nullptr) {
+        const int dev = current_device();
         // augmented batch: one CTA per sample, the whole resized image staged in shared memory
         sfr_prep_kernel<true, true><<<prep_grid, kPrepThreads, 0, stream>>>(a);
         if (int rc = launch_status()) return rc;
 #define PWR_LAUNCH_AUG(T, F)                                                                                  \
     do {                                                                                                      \
-        cudaFuncSetAttribute(sfr_aug_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
-                             static_cast<int>(sizeof(AugSmem<T>)));                                           \
+        PWR_ENSURE_DYN_SMEM(static_cast<int>(sizeof(AugSmem<T>)), dev, sfr_aug_kernel<T, F>);                 \
         sfr_aug_kernel<T, F><<<a.B, kAugThreads, sizeof(AugSmem<T>), stream>>>(a);                            \
     } while (0)
         if (frame_f64)            PWR_LAUNCH_AUG(double, FMT_F32);
@@ -900,6 +1018,19 @@ static int check_frames(int Hf, int Wf, int B) {
     return 0;
 }
 
+// whole frames, or the windows of pwr_sfr_fetch
+static int set_pixel_source(SfrArgs& a, const int* win_extent, int win_h, int win_w) {
+    if (win_extent == nullptr) {
+        a.win = nullptr; a.pitch = a.Wf; a.frame_stride = static_cast<long long>(a.Hf) * a.Wf;
+        return 0;
+    }
+    if (win_h < 1 || win_w < 1 || win_h > 16384 || win_w > 16384) return PWR_E_SHAPE;
+    if (misaligned(win_extent)) return PWR_E_ALIGN;
+    a.win = reinterpret_cast<const WinExtent*>(win_extent);
+    a.pitch = win_w; a.frame_stride = static_cast<long long>(win_h) * win_w;
+    return 0;
+}
+
 }  // namespace pwr
 
 using namespace pwr;
@@ -921,7 +1052,7 @@ extern "C" int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf
                             const double* cube, double fx, double fy, int frame_f64, double prefilter_margin,
                             double prefilter_umax, double prefilter_vmax, float* img, float* label_img, float* mask, float* box_size,
                             float* cube_size, float* com_out, uint8_t* valid, void* workspace, size_t workspace_size,
-                            int B, void* stream) {
+                            const int* win_extent, int win_h, int win_w, int B, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
     if (B == 0) return 0;
     if (frames == nullptr || com == nullptr || cube == nullptr || box_size == nullptr || cube_size == nullptr ||
@@ -931,7 +1062,8 @@ extern "C" int pwr_sfr_crop(const void* frames, int frame_format, int Hf, int Wf
     if (workspace_size < workspace_bytes(B, 0)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, nullptr, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  nullptr, nullptr, nullptr, valid, B, 0, nullptr, nullptr, nullptr, nullptr,
-                 prefilter_margin, prefilter_umax, prefilter_vmax, nullptr, nullptr, nullptr};
+                 prefilter_margin, prefilter_umax, prefilter_vmax, nullptr, nullptr, nullptr, nullptr, 0, 0};
+    if (int rc = set_pixel_source(a, win_extent, win_h, win_w)) return rc;
     carve_workspace(a, workspace);
     return launch_sfr<false>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
 }
@@ -944,6 +1076,7 @@ extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int W
                              float* mask, float* box_size, float* cube_size, float* com_out, float* uvd_norm,
                              float* heatmaps, float* dmap, pwr_joint_taps* joint_taps, uint8_t* valid,
                              void* workspace, size_t workspace_size,
+                             const int* win_extent, int win_h, int win_w,
                              int B, int J, void* stream) {
     if (int rc = check_frames(Hf, Wf, B)) return rc;
     if (J < 1 || J > PWR_MAX_JOINTS) return PWR_E_SHAPE;
@@ -958,7 +1091,27 @@ extern "C" int pwr_sfr_build(const void* frames, int frame_format, int Hf, int W
     if (workspace_size < workspace_bytes(B, J)) return PWR_E_SHAPE;
     SfrArgs a = {frames, Hf, Wf, com, cube, uvd, fx, fy, img, label_img, mask, box_size, cube_size, com_out,
                  uvd_norm, heatmaps, dmap, valid, B, J, nullptr, nullptr, nullptr, nullptr,
-                 prefilter_margin, prefilter_umax, prefilter_vmax, joint_taps, aug, nullptr};
+                 prefilter_margin, prefilter_umax, prefilter_vmax, joint_taps, aug, nullptr, nullptr, 0, 0};
+    if (int rc = set_pixel_source(a, win_extent, win_h, win_w)) return rc;
     carve_workspace(a, workspace);
     return launch_sfr<true>(a, frame_f64, frame_format, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pwr_sfr_fetch(const void* frames, int frame_format, int Hf, int Wf, const double* com,
+                             const double* cube, const double* aug, double fx, double fy, double prefilter_margin,
+                             double prefilter_umax, double prefilter_vmax, void* windows, int win_h, int win_w,
+                             int* win_extent, unsigned long long* fetched_bytes, int* status, int B, void* stream) {
+    if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (frame_format != FMT_F32 && frame_format != FMT_GB16 && frame_format != FMT_U16) return PWR_E_METHOD;
+    const int elem = frame_format == FMT_F32 ? 4 : 2;
+    if ((Wf * elem) % 16 != 0 || win_h < 1 || win_w < 1 || (win_w * elem) % 16 != 0 || win_h > 16384 || win_w > 16384)
+        return PWR_E_SHAPE;                                   // rows of both buffers must keep 16-byte alignment
+    if (B == 0) return 0;
+    if (com == nullptr || cube == nullptr) return PWR_E_NULL;
+    PWR_REQUIRE_PTR(frames); PWR_REQUIRE_PTR(windows); PWR_REQUIRE_PTR(win_extent);
+    if (static_cast<long long>(B) * kFetchGroups > 0x7fffffffLL) return PWR_E_SHAPE;
+    FetchArgs a = {frames, elem, Hf, Wf, com, cube, aug, fx, fy, prefilter_margin, prefilter_umax, prefilter_vmax,
+                   windows, win_h, win_w, reinterpret_cast<WinExtent*>(win_extent), fetched_bytes, status, B};
+    sfr_fetch_kernel<<<static_cast<unsigned>(B) * kFetchGroups, kFetchThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
 }

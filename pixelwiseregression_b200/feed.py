@@ -1,0 +1,142 @@
+"""Double-buffered host -> device feed of the SFR builder.
+
+Replaces the per-batch `.to(device, non_blocking=True)` of train.py:161-166 / test.py:96-100 for the path's
+inputs.  The reference ships whole collated tensors; the only large one is the depth frame, of which the
+builder reads just the crop box inside the hand rectangle.  Here the raw frames stay in pinned host memory and
+`pwr_sfr_fetch` pulls exactly that region over PCIe (a kernel reading device-mapped host memory with coalesced
+16-byte loads: no host-side repacking, no per-sample memcpy calls; `tools/pcie_probe.cu` has the measurements
+behind this choice), on a side stream, `depth` batches ahead of the compute stream:
+
+    feed = HostFeed(synth.NYU, batch=4096, frame_format="nyu_gb16", prefilter=(40, 320, 240))
+    t = feed.submit(frames_pinned, com, cube, uvd)            # copy stream: annotations H2D + window fetch
+    for ...:
+        nxt = feed.submit(...)                                # batch k+1 crosses PCIe ...
+        batch = feed.build(t)                                 # ... while batch k is built and decoded
+        ...
+        t = nxt
+
+CUDA only; PyTorch is plumbing (streams, events, pinned memory).
+"""
+import numpy as np
+import torch
+
+from . import _lib, sfr
+
+
+class _Slot:
+    def __init__(self):
+        self.fw = None            # FrameWindows
+        self.dev = {}             # device copies of the annotations
+        self.pin = {}             # pinned staging of the annotations
+        self.arena = sfr.SfrArena()
+        self.ready = torch.cuda.Event()       # copy stream: windows + annotations are on the device
+        self.consumed = torch.cuda.Event()    # compute stream: the builder has read the windows
+        self.used = False
+        self.meta = None
+
+
+class HostFeed:
+    """`shape`: a synth.DatasetShape (intrinsics + frame size); `batch`: samples per submit; `prefilter`:
+    (margin, halfu, halfv) of load_from_text or None; `win_hw`: window size, default = large enough for the
+    first submitted batch with 12.5 % headroom on the box (a later batch that needs more raises, never
+    truncates silently); `depth`: batches in flight (2 = double buffering)."""
+
+    def __init__(self, shape, batch, *, frame_format="f32", prefilter=None, test_only=False, targets="dense",
+                 win_hw=None, depth=2, device=None, augment=False):
+        if not torch.cuda.is_available():
+            raise _lib.PwrError("HostFeed needs a CUDA device (there is no CPU fallback)")
+        self.shape, self.batch = shape, int(batch)
+        self.frame_format, self.prefilter = frame_format, prefilter
+        self.test_only, self.targets, self.augment = test_only, targets, augment
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.win_hw = win_hw
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = [_Slot() for _ in range(max(int(depth), 1))]
+        self.n = 0
+        self.h2d_bytes_small = 0       # annotation bytes of the last submit (the window bytes are counted on the device)
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _stage(self, slot, name, value, shape):
+        """Host value -> the slot's pinned staging buffer -> its device buffer (async on the copy stream)."""
+        if isinstance(value, torch.Tensor) and value.is_cuda:
+            slot.dev[name] = value.to(torch.float64)
+            return 0
+        arr = value.numpy() if isinstance(value, torch.Tensor) else np.asarray(value, dtype=np.float64)
+        if arr.ndim == 0:
+            arr = np.full(shape, float(arr))
+        if tuple(arr.shape) != tuple(shape):
+            raise _lib.PwrError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(arr.shape)))
+        if name not in slot.pin:
+            slot.pin[name] = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+            slot.dev[name] = torch.empty(shape, dtype=torch.float64, device=self.device)
+        slot.pin[name].numpy()[...] = arr
+        slot.dev[name].copy_(slot.pin[name], non_blocking=True)
+        return slot.pin[name].numel() * 8
+
+    def submit(self, frames, com, cube, uvd=None, augment=None):
+        """Enqueue one batch on the copy stream; returns a ticket for `build`.  `frames` [B,Hf,Wf]: pinned host
+        tensor in `frame_format` (or a device tensor); com [B,3], cube [B] or scalar, uvd [B,J,3]: host arrays
+        / tensors (float64 semantics).  Does not block unless the slot's previous batch is still unread."""
+        B = self.batch
+        if tuple(frames.shape) != (B, self.shape.height, self.shape.width):
+            raise _lib.PwrError("frames must be [%d, %d, %d]" % (B, self.shape.height, self.shape.width))
+        slot = self.slots[self.n % len(self.slots)]
+        ticket = self.n
+        self.n += 1
+        if slot.used:
+            slot.ready.synchronize()               # its staging buffers may be rewritten now
+        if self.win_hw is None:
+            h, w = sfr.window_size(com, cube, self.shape.fx, self.shape.fy, self.shape.height, self.shape.width,
+                                   self.frame_format, self.augment)
+            per16 = 4 if self.frame_format == "f32" else 8
+            h = min(h + h // 8, self.shape.height)
+            w = min(-(-(w + w // 8) // per16) * per16, -(-self.shape.width // per16) * per16)
+            self.win_hw = (h, w)
+        with torch.cuda.stream(self.copy_stream):
+            if slot.used:
+                self.copy_stream.wait_event(slot.consumed)     # the builder is done with this slot's windows
+            small = self._stage(slot, "com", com, (B, 3)) + self._stage(slot, "cube", cube, (B,))
+            if not self.test_only:
+                if uvd is None:
+                    raise _lib.PwrError("train-mode feed needs joint annotations (uvd)")
+                J = int(np.shape(uvd)[1])
+                small += self._stage(slot, "uvd", uvd, (B, J, 3))
+            aug_dev = None
+            if augment is not None:
+                aug_dev = sfr._aug_device_params(augment, B, self.device)
+                small += B * 8 * 8
+            if slot.fw is not None:
+                slot.fw.fetched_bytes.zero_()
+            slot.fw = sfr.fetch_windows(frames, slot.dev["com"], slot.dev["cube"], fx=self.shape.fx, fy=self.shape.fy,
+                                        frame_format=self.frame_format, prefilter=self.prefilter, augment=aug_dev,
+                                        win_hw=self.win_hw, out=slot.fw)
+            slot.ready.record(self.copy_stream)
+        slot.used = True
+        slot.meta = (ticket, aug_dev)
+        self.h2d_bytes_small = small
+        return ticket
+
+    def build(self, ticket):
+        """Build the SFR batch of `ticket` on the CURRENT stream (waits for its fetch).  The returned batch
+        aliases the slot's arena: it stays valid until `depth` further builds."""
+        slot = self.slots[ticket % len(self.slots)]
+        if slot.meta is None or slot.meta[0] != ticket:
+            raise _lib.PwrError("ticket %d is not in flight (depth %d)" % (ticket, len(self.slots)))
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(slot.ready)
+        batch = sfr.build_sfr(slot.fw, slot.dev["com"], slot.dev["cube"], None if self.test_only else slot.dev["uvd"],
+                              fx=self.shape.fx, fy=self.shape.fy, frame_format=self.frame_format,
+                              prefilter=self.prefilter, test_only=self.test_only, targets=self.targets,
+                              augment=slot.meta[1], arena=slot.arena)
+        slot.consumed.record(cur)
+        return batch
+
+    def fetched_bytes(self, ticket):
+        """Bytes `pwr_sfr_fetch` pulled from the frames for `ticket` (device -> host read: synchronises), and
+        whether every region fitted its window."""
+        slot = self.slots[ticket % len(self.slots)]
+        vals = torch.cat([slot.fw.fetched_bytes, slot.fw.status.to(torch.int64)]).cpu()
+        if int(vals[1]) != 0:
+            raise _lib.PwrError("a crop region did not fit the %s window: construct HostFeed with a larger win_hw"
+                                % (self.win_hw,))
+        return int(vals[0])

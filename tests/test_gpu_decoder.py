@@ -72,8 +72,11 @@ def oracle_case(B, J, method, alpha, upstream, seed):
 @pytest.mark.parametrize("method", ["softmax", "sum"])
 @pytest.mark.parametrize("J", [14, 21])
 @pytest.mark.parametrize("alpha,upstream", [(1.0, False), (0.5, True), (1.0, True)])
-def test_forward_backward_match_fp64_oracle(method, J, alpha, upstream):
-    B = 6
+@pytest.mark.parametrize("direct", [False, True])
+def test_forward_backward_match_fp64_oracle(method, J, alpha, upstream, direct):
+    """direct=False: the pipelined backward kernels (targets + dense upstream gradients at once = the six-slot
+    stage); direct=True: the one-CTA-per-item kernel forced through the dispatch option."""
+    B = 37 if not direct else 6            # 37*J items: several per CTA of the persistent kernels, ragged ranges
     d, tg, ups = oracle_case(B, J, method, alpha, upstream, seed=J + int(alpha * 10))
     dd = torch.float64
     t64 = lambda a: torch.from_numpy(a).to(dd)
@@ -90,9 +93,10 @@ def test_forward_backward_match_fp64_oracle(method, J, alpha, upstream):
     H, uvd, stats, _ = ops.decoder_forward_raw(z, w, D, L, m, method)
     assert_close("heat", H.cpu().numpy(), p_ref.numpy())
     assert_close("uvd", uvd.cpu().numpy(), uvd_ref.numpy())
-    gz, gD, gwp, lp = ops.decoder_backward_raw(
-        z, w, D, L, m, stats, uvd, cu(ups[0]) if ups else None, cu(ups[1]) if ups else None,
-        cu(ups[2]) if ups else None, method, tuple(cu(a) for a in tg), alpha, 1.0, 0.01, want_loss=True)
+    with _lib.option("bwd_direct", int(direct)):
+        gz, gD, gwp, lp = ops.decoder_backward_raw(
+            z, w, D, L, m, stats, uvd, cu(ups[0]) if ups else None, cu(ups[1]) if ups else None,
+            cu(ups[2]) if ups else None, method, tuple(cu(a) for a in tg), alpha, 1.0, 0.01, want_loss=True)
     assert_close("gz", gz.cpu().numpy(), gz_ref.numpy(), GRAD_RTOL)
     assert_close("gD", gD.cpu().numpy(), gD_ref.numpy(), GRAD_RTOL)
     if method == "softmax":

@@ -62,3 +62,35 @@ def test_synthetic_generators_are_deterministic():
     assert d["frames"].shape == (3, 480, 640) and d["uvd"].dtype == torch.float64
     frac = float((d["frames"] > 0).float().mean())
     assert 0.01 < frac < 0.5
+
+
+def test_window_size_covers_the_oracle_crop_geometry():
+    """sfr.window_size (host side of the PCIe feed) must be at least the in-frame extent of every crop box the
+    oracle derives (datasets.py:306-311, utils.py:167-173), plus 16-byte alignment slack per row."""
+    from oracle import sfr_oracle as so
+    for shape, fmt in ((synth.NYU, "nyu_gb16"), (synth.HAND17, "u16"), (synth.ICVL, "f32"), (synth.MSRA, "f32")):
+        d = synth.make_frames(shape, 64, seed=9)
+        d["com"][0, :2] = (1.5, 2.5)
+        d["com"][1, 2] = 120.0                       # a box larger than the frame
+        win_h, win_w = sfr.window_size(d["com"], d["cube"], shape.fx, shape.fy, shape.height, shape.width, fmt)
+        per16 = 4 if fmt == "f32" else 8
+        assert win_w % per16 == 0 and win_h <= shape.height
+        for b in range(64):
+            box = so.crop_box(d["com"][b, 2], d["cube"][b], shape.fx, shape.fy)
+            r0, c0, shift, nrows, ncols, rs, cs = so.crop_geometry(d["com"][b], box, shape.height, shape.width)
+            fr0, fc0 = rs - shift, cs - shift
+            rows = max(0, min(fr0 + nrows, shape.height) - max(fr0, 0))
+            ca, cb = max(fc0, 0), min(fc0 + ncols, shape.width)
+            cols = max(0, -(-cb // per16) * per16 - ca // per16 * per16)
+            assert rows <= win_h and cols <= win_w, (shape.name, b, rows, cols, win_h, win_w)
+
+
+def test_host_feed_and_fetch_refuse_to_run_without_cuda():
+    from pixelwiseregression_b200 import feed
+    if not torch.cuda.is_available():
+        with pytest.raises(PwrError, match="no CPU fallback"):
+            feed.HostFeed(synth.NYU, 4)
+    with pytest.raises(PwrError):
+        sfr.fetch_windows(torch.zeros(1, 480, 640), torch.zeros(1, 3), torch.zeros(1), fx=1.0, fy=1.0)
+    with pytest.raises(PwrError, match="kernel_size=7"):
+        sfr.build_sfr(torch.zeros(1, 480, 640), np.zeros((1, 3)), 150.0, np.zeros((1, 14, 3)), fx=1.0, fy=1.0, kernel_size=9)

@@ -85,6 +85,16 @@ int pwr_set_option(int option, int value);
 int pwr_sfr_com(const float* frames, int Hf, int Wf, double* com /*[B,3]*/,
                 int B, void* stream);
 
+/* HAND17 bounding-box loader, datasets.py:974-996 (`process_mode='bb'`: test frames that come with
+ * a box instead of joints): raw [B,Hf,Wf] uint16 sensor counts, boxes [B,4] f64 = (ustart, vstart,
+ * du, dv) -> frames_out [B,Hf,Wf] float32: zero outside MM[int(vstart):int(vstart+dv),
+ * int(ustart):int(ustart+du)], and zero where depth > mean + 100 with the reference's two-pass mean
+ * (exact integer sums, float64 divisions: bit-identical to NumPy; the values are integers, so the
+ * reference's float64 frame is represented exactly).  Follow with pwr_sfr_com and pwr_sfr_crop
+ * (frame_f64 = 1), as process_single_data does (datasets.py:203-214). */
+int pwr_sfr_bb_filter(const uint16_t* raw, int Hf, int Wf, const double* boxes,
+                      float* frames_out, int B, void* stream);
+
 /* Frame formats (raw sensor frames can be fed directly).  The
  * float32 value the reference would hold after plt.imread + its decode line is
  * reproduced bit for bit. */
@@ -292,14 +302,20 @@ int pwr_reduce_partials(const float* in, float* out, int B, int J, int C,
 /* Stage loss values of train.py:197-205 from loss_partial [B,J,3]:
  *   out4 = (lambda_h*mean_h, lambda_d*mean_d, mean_u, alpha*mean_u +
  *   (1-alpha)*(lambda_h*mean_h + lambda_d*mean_d)), means over n_mean (0 =
- *   B*J) of the per-(b,j) sums of squares.  One launch, fixed summation order. */
+ *   B*J) of the per-(b,j) sums of squares.  One launch, fixed summation order.
+ *   gw_partial [B,J] / gw_out [J] (both or neither): the same launch also sums
+ *   dL/dw over the batch (what pwr_reduce_partials with C = 1 would do). */
 int pwr_stage_loss(const float* loss_partial, int B, int J,
                    float lambda_h, float lambda_d, float alpha, int n_mean,
-                   float* out4, void* stream);
+                   float* out4, const float* gw_partial, float* gw_out,
+                   void* stream);
 
-/* In-place multiply n elements (n % 4 == 0, element type map_dtype) by *scale_dev (device scalar); used to apply a
- * non-unit upstream gradient to gradients that were produced eagerly. */
-int pwr_scale_inplace(void* x, const float* scale_dev, long long n,
+/* In-place multiply by *scale_dev (device scalar; an early exit when it is 1): n elements
+ * (n % 4 == 0, element type map_dtype) of x and, if not NULL, of x2, plus n_small <= 256 float32 of
+ * `small`.  Applies a non-unit upstream gradient (GradScaler) to gz, gD and dL/dw that were produced
+ * eagerly by the one-pass last stage - one launch for all three. */
+int pwr_scale_inplace(void* x, void* x2, float* small, int n_small,
+                      const float* scale_dev, long long n,
                       int map_dtype, void* stream);
 
 /* utils.py:332-337 recover_uvd fused with uvd2xyz datasets.py:100-111:

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pwr_error_string": [_I],
     "pwr_set_option": [_I, _I],
     "pwr_sfr_com": [_P, _I, _I, _P, _I, _P],
+    "pwr_sfr_bb_filter": [_P, _I, _I, _P, _P, _I, _P],
     "pwr_sfr_workspace_bytes": [_I, _I],
     "pwr_sfr_crop": [_P, _I, _I, _I, _P, _P, _D, _D, _I, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _I, _I,
                      _I, _P],
@@ -42,8 +43,8 @@ SIGNATURES = {
     "pwr_decoder_bwd_loss": [_P] * 14 + [_F, _F, _F, _F, _P, _I] + [_P] * 4 + [_I, _I, _I, _I, _P],
     "pwr_decoder_fwd_bwd_loss": [_P] * 9 + [_F, _F, _F, _F, _P, _I] + [_P] * 6 + [_I, _I, _I, _I, _P],
     "pwr_reduce_partials": [_P, _P, _I, _I, _I, _P],
-    "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P],
-    "pwr_scale_inplace": [_P, _P, _LL, _I, _P],
+    "pwr_stage_loss": [_P, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P],
+    "pwr_scale_inplace": [_P, _P, _P, _I, _P, _LL, _I, _P],
     "pwr_recover_uvd": [_P, _P, _P, _P, _D, _D, _D, _D, _P, _P, _I, _I, _P],
     "pwr_joint_error": [_P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _I, _I, _P],
 }
@@ -134,36 +135,47 @@ def launch_count():
     return sum(LAUNCHES.values())
 
 
-class timed:
-    """Brackets one launch with CUDA events on the current stream when profiling
-    is switched on (bench.py); free otherwise."""
+class launch:
+    """`with launch(device, "pwr_xyz"):` — everything a launch needs around the ctypes call, at the lowest host
+    cost: make `device` current only if it is not already (torch.cuda.device() costs ~5 us per use), and, when
+    profiling is switched on (bench.py), bracket the launch with CUDA events on the current stream."""
+    __slots__ = ("idx", "what", "prev", "start", "end")
 
-    def __init__(self, what):
+    def __init__(self, device, what=None):
+        self.idx = device.index
         self.what = what
 
     def __enter__(self):
-        if PROFILE is not None:
+        self.prev = None
+        if self.idx is not None:
+            cur = torch._C._cuda_getDevice()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        if PROFILE is not None and self.what is not None:
             self.start = torch.cuda.Event(enable_timing=True)
             self.end = torch.cuda.Event(enable_timing=True)
             self.start.record()
         return self
 
     def __exit__(self, *exc):
-        if PROFILE is not None and exc[0] is None:
+        if PROFILE is not None and self.what is not None and exc[0] is None:
             self.end.record()
             PROFILE.append((self.what, self.start, self.end))
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
         return False
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
-    if t is None:
-        return None
-    return ctypes.c_void_p(t.data_ptr())
+    """Device pointer of a tensor as an int (None -> NULL); ctypes converts it for the c_void_p parameters."""
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr(device=None):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """cudaStream_t of torch's current stream on `device` (raw handle, no Stream object built)."""
+    idx = device.index if (device is not None and device.index is not None) else torch._C._cuda_getDevice()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 def require_cuda(*tensors):

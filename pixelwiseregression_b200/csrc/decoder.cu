@@ -1060,8 +1060,24 @@ reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out, in
 constexpr int kLossThreads = 1024;
 __global__ void __launch_bounds__(kLossThreads)
 stage_loss_kernel(const float* __restrict__ loss_partial, int n_items, float scale_h, float scale_d, float scale_u,
-                  float alpha, float* __restrict__ out) {
+                  float alpha, float* __restrict__ out, const float* __restrict__ gw_partial, float* __restrict__ gw_out,
+                  int B, int J) {
     __shared__ float scratch[(kLossThreads / 32) * 3];
+    if (blockIdx.x > 0) {
+        // CTAs 1..J: dL/dw[j] = sum over the batch of gw_partial[b, j] (the launch pwr_reduce_partials would be)
+        const int j = blockIdx.x - 1;
+        float g = 0.f;
+        for (int b = threadIdx.x; b < B; b += kLossThreads) g += gw_partial[static_cast<size_t>(b) * J + j];
+        g = warp_sum(g);
+        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int wv = 0; wv < kLossThreads / 32; ++wv) t += scratch[wv];
+            gw_out[j] = t;
+        }
+        return;
+    }
     float v[3] = {0.f, 0.f, 0.f};
     for (int i = threadIdx.x; i < n_items; i += kLossThreads) {
         v[0] += loss_partial[i * 3 + 0];
@@ -1084,14 +1100,21 @@ stage_loss_kernel(const float* __restrict__ loss_partial, int n_items, float sca
 
 template <typename TZ>
 __global__ void __launch_bounds__(kThreads)
-scale_inplace_kernel(void* __restrict__ x, const float* __restrict__ scale, long long n4) {
+scale_inplace_kernel(void* __restrict__ x, void* __restrict__ x2, const float* __restrict__ scale, long long n4,
+                     float* __restrict__ small, int n_small) {
     const float s = *scale;
     if (s == 1.0f) return;
+    if (small != nullptr && blockIdx.x == 0 && threadIdx.x < n_small) small[threadIdx.x] *= s;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
     for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < n4; i += stride) {
         float4 v = MapIO<TZ>::ld(x, static_cast<size_t>(i) * 4);
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
         MapIO<TZ>::st(x, static_cast<size_t>(i) * 4, v);
+        if (x2 != nullptr) {
+            float4 u = MapIO<TZ>::ld(x2, static_cast<size_t>(i) * 4);
+            u.x *= s; u.y *= s; u.z *= s; u.w *= s;
+            MapIO<TZ>::st(x2, static_cast<size_t>(i) * 4, u);
+        }
     }
 }
 
@@ -1181,6 +1204,7 @@ struct FusedArgs {
     const float* heat_gt; const float* dmap_gt; const float* uvd_gt; const pwr_joint_taps* taps;
     LossCoef coef;
     float* H; float* uvd; void* gz; void* gD; float* gw_partial; float* loss_partial;
+    float* stats;              // [items,4] for a later backward (inner stage: forward + loss only), or NULL
     int J; int items;
 };
 
@@ -1417,6 +1441,7 @@ decoder_fused_kernel(FusedArgs a) {
         if (tid == 0) {
             float* o = a.uvd + static_cast<size_t>(it) * 3;
             o[0] = u; o[1] = v; o[2] = dcoord;
+            if (a.stats != nullptr) reinterpret_cast<float4*>(a.stats)[it] = make_float4(zext, inv_s, den, dcoord);
             if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr)
                 a.gw_partial[it] = sum_partials<kFusedWarps>(sb + 3 * kFusedWarps) - s1 * sum_partials<kFusedWarps>(sb + 4 * kFusedWarps);
             if (a.loss_partial != nullptr) {
@@ -1675,6 +1700,30 @@ static bool bad_dtype(int method, int map_dtype) {
         }                                                                                             \
     } while (0)
 
+// One launcher for the one-pass kernel: the last stage (forward + loss + backward), and - with no gradient
+// outputs and `stats` saved - the forward of an inner stage whose loss value is needed at forward time.
+static int launch_fused(const FusedArgs& a, int method, int map_dtype, cudaStream_t s) {
+    const bool sparse = a.taps != nullptr;
+    const int dev = current_device(), sms = sm_count(dev);
+    const int grid = a.items < sms * kFusedCtasPerSm ? a.items : sms * kFusedCtasPerSm;
+#define PWR_LAUNCH_FUSED(M, LS, TZ)                                                                          \
+    do {                                                                                                     \
+        PWR_ENSURE_DYN_SMEM(kFusedSmemBytes, dev, decoder_fused_kernel<M, LS, TZ>);                          \
+        decoder_fused_kernel<M, LS, TZ><<<grid, kFusedThreads, kFusedSmemBytes, s>>>(a);                     \
+    } while (0)
+#define PWR_FUSED_TZ(M, LS)                                                                                  \
+    do {                                                                                                     \
+        if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_FUSED(M, LS, float);                                 \
+        else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_FUSED(M, LS, __half);                                \
+        else                                 PWR_LAUNCH_FUSED(M, LS, __nv_bfloat16);                         \
+    } while (0)
+    if (method == PWR_METHOD_SOFTMAX) { if (sparse) PWR_FUSED_TZ(PWR_METHOD_SOFTMAX, LOSS_SPARSE); else PWR_FUSED_TZ(PWR_METHOD_SOFTMAX, LOSS_DENSE); }
+    else                              { if (sparse) PWR_FUSED_TZ(PWR_METHOD_SUM, LOSS_SPARSE); else PWR_FUSED_TZ(PWR_METHOD_SUM, LOSS_DENSE); }
+#undef PWR_FUSED_TZ
+#undef PWR_LAUNCH_FUSED
+    return launch_status();
+}
+
 extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, const float* L, const float* m,
                                const float* heat_gt, const float* dmap_gt, const float* uvd_gt,
                                const pwr_joint_taps* taps, float* H, float* uvd, float* stats, float* loss_partial,
@@ -1695,6 +1744,20 @@ extern "C" int pwr_decoder_fwd(const void* z, const float* w, const void* D, con
     }
     const int loss_mode = !loss ? LOSS_NONE : (taps != nullptr ? LOSS_SPARSE : LOSS_DENSE);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // Forward with the stage loss riding along (an inner stage, model.py:205-208 + train.py:197-199): the
+    // one-pass kernel without gradient outputs - z, D and the target maps arrive through its bulk-TMA ring
+    // instead of 24 direct loads per thread (measured B=4096 NYU: direct kernel 0.99 ms = 75 % of the copy
+    // peak on 5J + 2 maps in, J out).  `stats` is saved for the backward kernel.
+    if (loss && method != PWR_METHOD_GIVEN && !force_direct_fwd()) {
+        FusedArgs a;
+        a.coef.cu = a.coef.ch = a.coef.cd = 0.f; a.coef.scale_dev = nullptr;
+        a.z = z; a.w = w; a.D = D; a.L = L; a.m = m;
+        a.heat_gt = taps == nullptr ? heat_gt : nullptr; a.dmap_gt = taps == nullptr ? dmap_gt : nullptr;
+        a.uvd_gt = uvd_gt; a.taps = taps;
+        a.H = H; a.uvd = uvd; a.gz = nullptr; a.gD = nullptr; a.gw_partial = nullptr; a.loss_partial = loss_partial;
+        a.stats = stats; a.J = J; a.items = B * J;
+        return launch_fused(a, method, map_dtype, s);
+    }
     // No fused loss and the depth branch present -> persistent TMA-pipelined forward.
     // Measured (B200, f32): without the heat-map store 0.452 vs 0.576 ms (HAND17 B=4096, 6.5 TB/s); with it
     // the direct kernel below is already at 98 % of the copy peak and stays the default.
@@ -1878,27 +1941,8 @@ extern "C" int pwr_decoder_fwd_bwd_loss(const void* z, const float* w, const voi
     a.uvd_gt = uvd_gt; a.taps = map_terms ? taps : nullptr;
     a.H = H; a.uvd = uvd; a.gz = gz; a.gD = gD; a.gw_partial = gw_partial; a.loss_partial = loss_partial;
     a.J = J; a.items = B * J;
-    const bool sparse = a.taps != nullptr;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int dev = current_device(), sms = sm_count(dev);
-    const int grid = a.items < sms * kFusedCtasPerSm ? a.items : sms * kFusedCtasPerSm;
-#define PWR_LAUNCH_FUSED(M, LS, TZ)                                                                          \
-    do {                                                                                                     \
-        PWR_ENSURE_DYN_SMEM(kFusedSmemBytes, dev, decoder_fused_kernel<M, LS, TZ>);    \
-                                                               \
-        decoder_fused_kernel<M, LS, TZ><<<grid, kFusedThreads, kFusedSmemBytes, s>>>(a);                     \
-    } while (0)
-#define PWR_FUSED_TZ(M, LS)                                                                                  \
-    do {                                                                                                     \
-        if (map_dtype == PWR_DTYPE_F32)      PWR_LAUNCH_FUSED(M, LS, float);                                 \
-        else if (map_dtype == PWR_DTYPE_F16) PWR_LAUNCH_FUSED(M, LS, __half);                                \
-        else                                 PWR_LAUNCH_FUSED(M, LS, __nv_bfloat16);                         \
-    } while (0)
-    if (method == PWR_METHOD_SOFTMAX) { if (sparse) PWR_FUSED_TZ(PWR_METHOD_SOFTMAX, LOSS_SPARSE); else PWR_FUSED_TZ(PWR_METHOD_SOFTMAX, LOSS_DENSE); }
-    else                              { if (sparse) PWR_FUSED_TZ(PWR_METHOD_SUM, LOSS_SPARSE); else PWR_FUSED_TZ(PWR_METHOD_SUM, LOSS_DENSE); }
-#undef PWR_FUSED_TZ
-#undef PWR_LAUNCH_FUSED
-    return launch_status();
+    a.stats = nullptr;
+    return launch_fused(a, method, map_dtype, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, int C, void* stream) {
@@ -1909,30 +1953,34 @@ extern "C" int pwr_reduce_partials(const float* in, float* out, int B, int J, in
 }
 
 extern "C" int pwr_stage_loss(const float* loss_partial, int B, int J, float lambda_h, float lambda_d, float alpha,
-                              int n_mean, float* out4, void* stream) {
+                              int n_mean, float* out4, const float* gw_partial, float* gw_out, void* stream) {
     if (int rc = check_bj(B, J)) return rc;
     if (out4 == nullptr || (loss_partial == nullptr && B != 0)) return PWR_E_NULL;
+    if ((gw_partial == nullptr) != (gw_out == nullptr)) return PWR_E_NULL;
     const double n = n_mean > 0 ? static_cast<double>(n_mean) : static_cast<double>(B) * J;
-    stage_loss_kernel<<<1, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    stage_loss_kernel<<<1 + (gw_out != nullptr ? J : 0), kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         loss_partial, B * J, static_cast<float>(lambda_h / n), static_cast<float>(lambda_d / n),
-        static_cast<float>(1.0 / n), alpha, out4);
+        static_cast<float>(1.0 / n), alpha, out4, gw_partial, gw_out, B, J);
     return launch_status();
 }
 
-extern "C" int pwr_scale_inplace(void* x, const float* scale_dev, long long n, int map_dtype, void* stream) {
-    if (n < 0 || (n & 3) != 0) return PWR_E_SHAPE;            // whole maps only: n is a multiple of 4096
-    if (n == 0) return 0;
-    PWR_REQUIRE_PTR(x);
-    if (scale_dev == nullptr) return PWR_E_NULL;
+extern "C" int pwr_scale_inplace(void* x, void* x2, float* small, int n_small, const float* scale_dev, long long n,
+                                 int map_dtype, void* stream) {
+    if (n < 0 || (n & 3) != 0 || n_small < 0 || n_small > kThreads) return PWR_E_SHAPE;   // whole maps only
+    if (n == 0 && n_small == 0) return 0;
+    PWR_REQUIRE_PTR(x); PWR_OPTIONAL_PTR(x2);
+    if (scale_dev == nullptr || (n_small > 0 && small == nullptr)) return PWR_E_NULL;
     const long long n4 = n / 4;
     long long blocks = (n4 + kThreads - 1) / kThreads;
+    if (blocks < 1) blocks = 1;
     const long long cap = static_cast<long long>(sm_count(current_device())) * 16;
     if (blocks > cap) blocks = cap;
     const unsigned g = static_cast<unsigned>(blocks);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (map_dtype == PWR_DTYPE_F32)       scale_inplace_kernel<float><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
-    else if (map_dtype == PWR_DTYPE_F16)  scale_inplace_kernel<__half><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
-    else if (map_dtype == PWR_DTYPE_BF16) scale_inplace_kernel<__nv_bfloat16><<<g, kThreads, 0, s>>>(x, scale_dev, n4);
+    float* sm = n_small > 0 ? small : nullptr;
+    if (map_dtype == PWR_DTYPE_F32)       scale_inplace_kernel<float><<<g, kThreads, 0, s>>>(x, x2, scale_dev, n4, sm, n_small);
+    else if (map_dtype == PWR_DTYPE_F16)  scale_inplace_kernel<__half><<<g, kThreads, 0, s>>>(x, x2, scale_dev, n4, sm, n_small);
+    else if (map_dtype == PWR_DTYPE_BF16) scale_inplace_kernel<__nv_bfloat16><<<g, kThreads, 0, s>>>(x, x2, scale_dev, n4, sm, n_small);
     else return PWR_E_METHOD;
     return launch_status();
 }

@@ -339,30 +339,41 @@ __device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx
 template <typename T, int FMT, bool INTERIOR>
 __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __restrict__ frame, const SampleGeom& g,
                                                const TapX* ytap2, const TapX* xtap2, int pitch) {
+    // Phase A: all 16 tap loads of the block are issued before any of them is consumed (the kernel lives
+    // on loads in flight: with 8 + 8 interleaved with arithmetic it measured 8 % slower, r2).
+    float v[2][2][4];
+    TapX ty[2], tx[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) { ty[d] = ytap2[d]; tx[d] = xtap2[d]; }
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-        const TapX ty = ytap2[dy];
-        const int fr_a = g.fr0 + ty.s0, fr_b = g.fr0 + ty.s1;
+        const int fr_a = g.fr0 + ty[dy].s0, fr_b = g.fr0 + ty[dy].s1;
         const bool ra = INTERIOR || (fr_a >= g.pr0 && fr_a < g.pr1), rb = INTERIOR || (fr_b >= g.pr0 && fr_b < g.pr1);
         // element offsets inside the sample's pixel buffer (Hf*Wf < 2^31, checked on the host)
         const int row_a = (fr_a - g.org_r) * pitch - g.org_c, row_b = (fr_b - g.org_r) * pitch - g.org_c;
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-            const TapX tx = xtap2[dx];
-            const int fc_a = g.fc0 + tx.s0, fc_b = g.fc0 + tx.s1;
+            const int fc_a = g.fc0 + tx[dx].s0, fc_b = g.fc0 + tx[dx].s1;
             const bool ca = INTERIOR || (fc_a >= g.pc0 && fc_a < g.pc1), cb = INTERIOR || (fc_b >= g.pc0 && fc_b < g.pc1);
-            const float v00 = (ra && ca) ? load_px<FMT>(frame, row_a + fc_a) : 0.f;
-            const float v01 = (ra && cb) ? load_px<FMT>(frame, row_a + fc_b) : 0.f;
-            const float v10 = (rb && ca) ? load_px<FMT>(frame, row_b + fc_a) : 0.f;
-            const float v11 = (rb && cb) ? load_px<FMT>(frame, row_b + fc_b) : 0.f;
-            const T w00 = Arith<T>::window(static_cast<T>(v00), g);
-            const T w01 = Arith<T>::window(static_cast<T>(v01), g);
-            const T w10 = Arith<T>::window(static_cast<T>(v10), g);
-            const T w11 = Arith<T>::window(static_cast<T>(v11), g);
-            const T xa0 = static_cast<T>(tx.a0), xa1 = static_cast<T>(tx.a1);
+            v[dy][dx][0] = (ra && ca) ? load_px<FMT>(frame, row_a + fc_a) : 0.f;
+            v[dy][dx][1] = (ra && cb) ? load_px<FMT>(frame, row_a + fc_b) : 0.f;
+            v[dy][dx][2] = (rb && ca) ? load_px<FMT>(frame, row_b + fc_a) : 0.f;
+            v[dy][dx][3] = (rb && cb) ? load_px<FMT>(frame, row_b + fc_b) : 0.f;
+        }
+    }
+    // Phase B: window + centring per tap, horizontal then vertical lerp (cv::resize's order, un-fused)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const T w00 = Arith<T>::window(static_cast<T>(v[dy][dx][0]), g);
+            const T w01 = Arith<T>::window(static_cast<T>(v[dy][dx][1]), g);
+            const T w10 = Arith<T>::window(static_cast<T>(v[dy][dx][2]), g);
+            const T w11 = Arith<T>::window(static_cast<T>(v[dy][dx][3]), g);
+            const T xa0 = static_cast<T>(tx[dx].a0), xa1 = static_cast<T>(tx[dx].a1);
             const T top = Arith<T>::add(Arith<T>::mul(w00, xa0), Arith<T>::mul(w01, xa1));
             const T bot = Arith<T>::add(Arith<T>::mul(w10, xa0), Arith<T>::mul(w11, xa1));
-            px[dy][dx] = Arith<T>::add(Arith<T>::mul(top, static_cast<T>(ty.a0)), Arith<T>::mul(bot, static_cast<T>(ty.a1)));
+            px[dy][dx] = Arith<T>::add(Arith<T>::mul(top, static_cast<T>(ty[dy].a0)), Arith<T>::mul(bot, static_cast<T>(ty[dy].a1)));
         }
     }
 }
@@ -948,6 +959,71 @@ sfr_com_kernel(const float* __restrict__ frames, int Hf, int Wf, double* __restr
     }
 }
 
+// ---------------------------------------------------------------------------
+// HAND17 bounding-box loader, datasets.py:974-996 (process_mode='bb', test frames)
+// ---------------------------------------------------------------------------
+// Keep the annotated box, then drop everything deeper than 100 mm behind the mean depth of what is left, in
+// two passes (the reference's two np.mean over the frame).  Depths are integer sensor counts, so the sums are
+// exact in 64-bit integers whatever the order, and the means are one correctly rounded float64 division
+// each: bit-identical to NumPy.  One CTA per sample; the box (<= ~300 x 300 uint16) is re-read from L1/L2.
+constexpr int kBbThreads = 512;
+
+__device__ __forceinline__ void bb_block_sum(unsigned long long& sum, unsigned long long& cnt, unsigned long long* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                                   // scratch may still be read from the previous pass
+    if (lane == 0) { scratch[2 * warp] = sum; scratch[2 * warp + 1] = cnt; }
+    __syncthreads();
+    sum = 0; cnt = 0;
+    for (int wv = 0; wv < kBbThreads / 32; ++wv) { sum += scratch[2 * wv]; cnt += scratch[2 * wv + 1]; }
+}
+
+__global__ void __launch_bounds__(kBbThreads)
+sfr_bb_kernel(const unsigned short* __restrict__ raw, const double* __restrict__ boxes, float* __restrict__ out,
+              int Hf, int Wf) {
+    __shared__ unsigned long long scratch[2 * kBbThreads / 32];
+    const int b = blockIdx.x;
+    const unsigned short* frame = raw + static_cast<size_t>(b) * Hf * Wf;
+    float* dst = out + static_cast<size_t>(b) * Hf * Wf;
+    const double ustart = boxes[4 * b + 0], vstart = boxes[4 * b + 1], du = boxes[4 * b + 2], dv = boxes[4 * b + 3];
+    // MM[int(vstart):int(vstart+dv), int(ustart):int(ustart+du)] = 1, Python slice semantics
+    int r0, nr, c0, nc;
+    py_slice(py_int(vstart), py_int(__dadd_rn(vstart, dv)), Hf, r0, nr);
+    py_slice(py_int(ustart), py_int(__dadd_rn(ustart, du)), Wf, c0, nc);
+    const int npx = nr * nc;
+    // pass 1: mean of the positive pixels inside the box
+    unsigned long long sum = 0, cnt = 0;
+    for (int i = threadIdx.x; i < npx; i += kBbThreads) {
+        const unsigned int v = __ldg(frame + (r0 + i / nc) * Wf + c0 + i % nc);
+        if (v > 0u) { sum += v; cnt += 1; }
+    }
+    bb_block_sum(sum, cnt, scratch);
+    const double cut1 = __dadd_rn(__ddiv_rn(static_cast<double>(sum), static_cast<double>(cnt)), 100.0);
+    // pass 2: mean of what survives `> mean + 100 -> 0`
+    sum = 0; cnt = 0;
+    for (int i = threadIdx.x; i < npx; i += kBbThreads) {
+        const unsigned int v = __ldg(frame + (r0 + i / nc) * Wf + c0 + i % nc);
+        if (v > 0u && !(static_cast<double>(v) > cut1)) { sum += v; cnt += 1; }
+    }
+    bb_block_sum(sum, cnt, scratch);
+    const double cut2 = __dadd_rn(__ddiv_rn(static_cast<double>(sum), static_cast<double>(cnt)), 100.0);
+    // pass 3: the filtered frame (zero outside the box)
+    const int n = Hf * Wf;
+    for (int i = threadIdx.x; i < n; i += kBbThreads) {
+        const int r = i / Wf, c = i - r * Wf;
+        float o = 0.f;
+        if (r >= r0 && r < r0 + nr && c >= c0 && c < c0 + nc) {
+            const unsigned int v = __ldg(frame + i);
+            if (!(static_cast<double>(v) > cut2)) o = static_cast<float>(v);
+        }
+        dst[i] = o;
+    }
+}
+
 // workspace layout: [B] SampleGeom | [B*J] JointParam | [B] int joints_bad | [B] u32 gate | [B] WarpParam
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t workspace_bytes(int B, int J) {
@@ -1007,7 +1083,13 @@ static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t str
             return launch_status();
         }
     }
-    PWR_LAUNCH_SFR(kBandsLean);
+    // Without dense maps, 2 long bands per sample win at large batches (no zero-fill to overlap the prologue);
+    // a small batch (config 5 sweeps from 256) cannot fill 148 SMs x 6 CTAs with 2 CTAs per sample, so it takes
+    // the 8-band grid: 4x the CTAs, each a quarter as long.
+    if (static_cast<long long>(a.B) * kBandsLean < static_cast<long long>(sm_count(current_device())) * 12)
+        PWR_LAUNCH_SFR(kBandsDense);
+    else
+        PWR_LAUNCH_SFR(kBandsLean);
 #undef PWR_LAUNCH_SFR
     return launch_status();
 }
@@ -1113,5 +1195,14 @@ extern "C" int pwr_sfr_fetch(const void* frames, int frame_format, int Hf, int W
     FetchArgs a = {frames, elem, Hf, Wf, com, cube, aug, fx, fy, prefilter_margin, prefilter_umax, prefilter_vmax,
                    windows, win_h, win_w, reinterpret_cast<WinExtent*>(win_extent), fetched_bytes, status, B};
     sfr_fetch_kernel<<<static_cast<unsigned>(B) * kFetchGroups, kFetchThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
+}
+
+extern "C" int pwr_sfr_bb_filter(const uint16_t* raw, int Hf, int Wf, const double* boxes, float* frames_out, int B,
+                                 void* stream) {
+    if (int rc = check_frames(Hf, Wf, B)) return rc;
+    if (B == 0) return 0;
+    if (raw == nullptr || boxes == nullptr || frames_out == nullptr) return PWR_E_NULL;
+    sfr_bb_kernel<<<B, kBbThreads, 0, static_cast<cudaStream_t>(stream)>>>(raw, boxes, frames_out, Hf, Wf);
     return launch_status();
 }

@@ -78,7 +78,7 @@ def decoder_forward_raw(z, w, D, label_img, mask, method="softmax", store_heat=T
     if targets is not None:
         heat_gt, dmap_gt, uvd_gt, taps = _unpack_targets(targets, B, J)
         loss_partial = torch.empty(B, J, 3, device=z.device, dtype=torch.float32)
-    with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd"):
+    with _lib.launch(z.device, "pwr_decoder_fwd"):
         rc = lib.pwr_decoder_fwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
                                  ptr(uvd_gt), ptr(taps), ptr(H), ptr(uvd), ptr(stats), ptr(loss_partial), B, J,
                                  METHODS[method], map_dtype, stream_ptr(z.device))
@@ -109,7 +109,7 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
     label_img, mask, stats, uvd = as_f32(label_img), as_f32(mask), as_f32(stats), as_f32(uvd)
     scale_dev = as_f32(loss_scale_dev)
     s = stream_ptr(z.device)
-    with torch.cuda.device(z.device), _lib.timed("pwr_decoder_bwd" if targets is None else "pwr_decoder_bwd_loss"):
+    with _lib.launch(z.device, "pwr_decoder_bwd" if targets is None else "pwr_decoder_bwd_loss"):
         if targets is None:
             rc = lib.pwr_decoder_bwd(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask),
                                      ptr(stats), ptr(uvd), ptr(g_uvd), ptr(gH_up), ptr(gD_up), ptr(gz), ptr(gD),
@@ -149,7 +149,7 @@ def decoder_fused_raw(z, w, D, label_img, mask, targets, method="softmax", alpha
     gw_partial = torch.empty(B, J, **f32) if (want_grads and method == "softmax") else None
     loss_partial = torch.empty(B, J, 3, **f32)
     loss_scale_dev = as_f32(loss_scale_dev)
-    with torch.cuda.device(z.device), _lib.timed("pwr_decoder_fwd_bwd_loss"):
+    with _lib.launch(z.device, "pwr_decoder_fwd_bwd_loss"):
         rc = lib.pwr_decoder_fwd_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),
                                           ptr(uvd_gt), ptr(taps), float(alpha), float(lambda_h), float(lambda_d),
                                           float(loss_scale), ptr(loss_scale_dev), int(n_mean), ptr(H), ptr(uvd),
@@ -167,36 +167,44 @@ def reduce_partials(partial):
     B, J = partial.shape[0], partial.shape[1]
     C = partial.shape[2] if partial.dim() == 3 else 1
     out = torch.empty((J, C) if partial.dim() == 3 else (J,), device=partial.device, dtype=torch.float32)
-    with torch.cuda.device(partial.device):
+    with _lib.launch(partial.device):
         rc = _lib.load().pwr_reduce_partials(ptr(partial), ptr(out), B, J, C,
                                              stream_ptr(partial.device))
     check(rc, "pwr_reduce_partials")
     return out
 
 
-def scale_inplace_(x, scale):
-    """x *= scale, with `scale` a 0-dim CUDA tensor (no host sync; a no-op launch when scale == 1)."""
-    require_cuda(x, scale)
+def scale_inplace_(x, scale, x2=None, small=None):
+    """x *= scale (and x2, and the small float32 vector `small`), with `scale` a 0-dim CUDA tensor: no host sync,
+    one launch for all three, an early exit inside the kernel when scale == 1."""
+    require_cuda(x, scale, x2, small)
     scale = as_f32(scale)
-    with torch.cuda.device(x.device):
-        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(scale), x.numel(), _lib.MAP_DTYPES[x.dtype],
-                                           stream_ptr(x.device))
+    if x2 is not None and (x2.dtype != x.dtype or x2.numel() != x.numel()):
+        raise _lib.PwrError("scale_inplace_: x and x2 must have the same element type and size")
+    if small is not None and (small.dtype != torch.float32 or not small.is_contiguous() or small.numel() > 256):
+        raise _lib.PwrError("scale_inplace_: `small` must be a contiguous float32 tensor of at most 256 elements")
+    with _lib.launch(x.device):
+        rc = _lib.load().pwr_scale_inplace(ptr(x), ptr(x2), ptr(small), 0 if small is None else small.numel(), ptr(scale),
+                                           x.numel(), _lib.MAP_DTYPES[x.dtype], stream_ptr(x.device))
     check(rc, "pwr_scale_inplace")
     return x
 
 
-def stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean=0):
+def stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean=0, gw_partial=None):
     """train.py:197-205 from per-(b,j) sums of squares in one launch (pwr_stage_loss):
-    returns a [4] tensor (heatmap_loss, depthmap_loss, uvd_loss, combined loss)."""
-    require_cuda(loss_partial)
+    returns a [4] tensor (heatmap_loss, depthmap_loss, uvd_loss, combined loss); with `gw_partial` [B,J] also
+    dL/dw [J] summed over the batch by the same launch -> (out4, gw)."""
+    require_cuda(loss_partial, gw_partial)
     loss_partial = as_f32(loss_partial)
     B, J = loss_partial.shape[0], loss_partial.shape[1]
-    out = torch.empty(4, device=loss_partial.device, dtype=torch.float32)
-    with torch.cuda.device(loss_partial.device):
+    out = torch.empty(4 + (J if gw_partial is not None else 0), device=loss_partial.device, dtype=torch.float32)
+    gw = out[4:] if gw_partial is not None else None
+    gw_partial = as_f32(gw_partial)
+    with _lib.launch(loss_partial.device):
         rc = _lib.load().pwr_stage_loss(ptr(loss_partial), B, J, float(lambda_h), float(lambda_d), float(alpha),
-                                        int(n_mean), ptr(out), stream_ptr(loss_partial.device))
+                                        int(n_mean), ptr(out), ptr(gw_partial), ptr(gw), stream_ptr(loss_partial.device))
     check(rc, "pwr_stage_loss")
-    return out
+    return (out[:4], gw) if gw_partial is not None else out
 
 
 def stage_loss_from_partials(loss_partial, lambda_h, lambda_d, n_mean=0):
@@ -367,9 +375,12 @@ class DecoderLossFunction(torch.autograd.Function):
             gz, gD, gw_partial, loss_partial = decoder_backward_raw(
                 z, w, D, label_img, mask, stats, uvd, None, None, None, method, targets, alpha, lambda_h, lambda_d,
                 loss_scale=pre, n_mean=n_mean, want_loss=True, want_gz=need_grad, want_gD=need_grad)
-        out4 = stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean)
+        if need_grad and w is not None and gw_partial is not None:
+            out4, gw = stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean, gw_partial)    # loss + dL/dw: one launch
+            gw = gw.view_as(w)
+        else:
+            out4, gw = stage_loss(loss_partial, lambda_h, lambda_d, alpha, n_mean), None
         terms, total = out4[:3], out4[3]
-        gw = reduce_partials(gw_partial).view_as(w) if (need_grad and w is not None) else None
         # the eager gradients live on the node until its (single) backward consumes them
         ctx.grads = (gz, gD, gw)
         ctx.pre = pre
@@ -390,10 +401,7 @@ class DecoderLossFunction(torch.autograd.Function):
             return (None,) * 14
         if ctx.pre != 1.0:
             g_total = g_total.float() * (1.0 / ctx.pre)
-        scale_inplace_(gz, g_total)
-        scale_inplace_(gD, g_total)
-        if gw is not None:
-            gw = gw * g_total
+        scale_inplace_(gz, g_total, gD, gw)                 # one launch; a no-op when the upstream gradient is 1
         return (gz, gw, gD) + (None,) * 11
 
 
@@ -419,7 +427,7 @@ def recover_uvd(uvd_norm, box_size, com, cube_size, intrinsics=None):
     uvd_px = torch.empty_like(uvd_norm)
     xyz = torch.empty_like(uvd_norm) if intrinsics is not None else None
     fx, fy, hu, hv = intrinsics if intrinsics is not None else (1.0, 1.0, 0.0, 0.0)
-    with torch.cuda.device(uvd_norm.device):
+    with _lib.launch(uvd_norm.device):
         rc = _lib.load().pwr_recover_uvd(ptr(uvd_norm), ptr(box_size), ptr(cube_size),
                                          ptr(com), fx, fy, hu, hv, ptr(uvd_px), ptr(xyz), B, J,
                                          stream_ptr(uvd_norm.device))
@@ -437,7 +445,7 @@ def joint_error(uvd_pred, uvd_true, box_size, com, cube_size, intrinsics):
     fx, fy, hu, hv = intrinsics
     uvd_pred, uvd_true = as_f32(uvd_pred), as_f32(uvd_true)
     box_size, cube_size, com = as_f32(box_size), as_f32(cube_size), as_f32(com)
-    with torch.cuda.device(uvd_pred.device):
+    with _lib.launch(uvd_pred.device):
         rc = _lib.load().pwr_joint_error(ptr(uvd_pred), ptr(uvd_true), ptr(box_size),
                                          ptr(cube_size), ptr(com), fx, fy, hu, hv, ptr(err), B, J,
                                          stream_ptr(uvd_pred.device))

@@ -56,10 +56,30 @@ def center_of_mass(frames):
     frames = frames.contiguous()
     B, Hf, Wf = frames.shape
     com = torch.empty(B, 3, device=frames.device, dtype=torch.float64)
-    with torch.cuda.device(frames.device):
+    with _lib.launch(frames.device):
         rc = _lib.load().pwr_sfr_com(ptr(frames), Hf, Wf, ptr(com), B, stream_ptr(frames.device))
     check(rc, "pwr_sfr_com")
     return com
+
+
+def load_bb(raw, boxes):
+    """HAND17 `process_mode='bb'` loader on the GPU (datasets.py:974-996): raw [B,Hf,Wf] uint16 CUDA frames,
+    boxes [B,4] = (ustart, vstart, du, dv) -> float32 frames with everything outside the box and everything
+    deeper than mean + 100 mm (two-pass mean) zeroed.  Continue as the reference does for this mode
+    (datasets.py:203-214): `build_sfr(frames, None, cube, test_only=True, frame_f64=True, fx=.., fy=..)`."""
+    require_cuda(raw)
+    if raw.dtype != torch.uint16 or raw.dim() != 3:
+        raise _lib.PwrError("raw must be a [B, Hf, Wf] uint16 tensor")
+    raw = raw.contiguous()
+    B, Hf, Wf = raw.shape
+    boxes = _f64(boxes, raw.device)
+    if tuple(boxes.shape) != (B, 4):
+        raise _lib.PwrError("boxes must be [B, 4] = (ustart, vstart, du, dv)")
+    out = torch.empty(B, Hf, Wf, device=raw.device, dtype=torch.float32)
+    with _lib.launch(raw.device):
+        rc = _lib.load().pwr_sfr_bb_filter(ptr(raw), Hf, Wf, ptr(boxes), ptr(out), B, stream_ptr(raw.device))
+    check(rc, "pwr_sfr_bb_filter")
+    return out
 
 
 _FRAME_DTYPES = {"f32": torch.float32, "nyu_gb16": torch.uint16, "u16": torch.uint16}
@@ -150,7 +170,7 @@ def fetch_windows(frames, com, cube, *, fx, fy, frame_format="f32", prefilter=No
     pf = (-1.0, 0.0, 0.0) if prefilter is None else (float(prefilter[0]), 2.0 * prefilter[1], 2.0 * prefilter[2])
     com = com.to(torch.float64).contiguous()
     cube = cube.to(torch.float64).contiguous()
-    with torch.cuda.device(dev), _lib.timed("pwr_sfr_fetch"):
+    with _lib.launch(dev, "pwr_sfr_fetch"):
         rc = lib.pwr_sfr_fetch(ptr(frames), _lib.FRAME_FORMATS[frame_format], Hf, Wf, ptr(com), ptr(cube), ptr(aug_dev),
                                float(fx), float(fy), pf[0], pf[1], pf[2], ptr(fw.windows), win_h, win_w, ptr(fw.extent),
                                ptr(fw.fetched_bytes), ptr(fw.status), B, stream_ptr(dev))
@@ -265,7 +285,7 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     if test_only:
         if augment is not None:
             raise _lib.PwrError("you can not transform the test data")     # datasets.py:64-65
-        with torch.cuda.device(dev), _lib.timed("pwr_sfr_crop"):
+        with _lib.launch(dev, "pwr_sfr_crop"):
             rc = lib.pwr_sfr_crop(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), float(fx), float(fy), int(frame_f64),
                                   pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size), ptr(com_out),
                                   ptr(valid), ptr(workspace), ws_bytes, ptr(win_extent), win_h, win_w, B, s)
@@ -281,7 +301,7 @@ def build_sfr(frames, com, cube, uvd=None, *, fx, fy, frame_f64=False, test_only
     if augment is not None:
         aug_dev = augment if (isinstance(augment, torch.Tensor) and augment.is_cuda and tuple(augment.shape) == (B, 8)) \
             else _aug_device_params(augment, B, dev)
-    with torch.cuda.device(dev), _lib.timed("pwr_sfr_build"):
+    with _lib.launch(dev, "pwr_sfr_build"):
         rc = lib.pwr_sfr_build(ptr(frames), fmt, Hf, Wf, ptr(com), ptr(cube), ptr(uvd), ptr(aug_dev), float(fx), float(fy),
                                int(frame_f64), pf[0], pf[1], pf[2], ptr(img), ptr(label_img), ptr(mask), ptr(box_size), ptr(cube_size),
                                ptr(com_out), ptr(uvd_norm), ptr(heatmaps), ptr(dmap), ptr(taps), ptr(valid),

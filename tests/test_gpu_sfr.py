@@ -247,3 +247,29 @@ def test_gpu_hand17_bb_frames_match_reference_golden():
     got = {k: v.cpu().numpy() for k, v in out._asdict().items()}
     ref = {n: g["ref_" + n] for n in SFR_FIELDS[:6]}
     assert_sfr_matches(got, ref, SFR_FIELDS[:6], np.ones(len(frames32), np.uint8), prefix="bb:")
+
+
+def test_gpu_hand17_bb_loader_matches_reference_golden():
+    """The bounding-box loader itself on the GPU (pwr_sfr_bb_filter): box mask + two-pass "mean + 100 mm" background
+    removal from the raw uint16 frame == the reference's load_from_text_bb, bit for bit; and the whole `bb` branch
+    (loader -> CoM fallback -> test-only SFR with float64 frame semantics) == the reference's process_single_data."""
+    g = load_golden("sfr_hand17_bb")
+    shape = golden_shape(g)
+    raw = torch.from_numpy(g["raw"]).cuda()
+    frames = sfr.load_bb(raw, g["boxes"])
+    torch.cuda.synchronize()
+    assert np.array_equal(frames.cpu().numpy().astype(np.float64), g["ref_frames"])
+    out = sfr.build_sfr(frames, None, float(shape.cube), fx=shape.fx, fy=shape.fy, frame_f64=True, test_only=True)
+    got = {k: v.cpu().numpy() for k, v in out._asdict().items()}
+    ref = {n: g["ref_" + n] for n in SFR_FIELDS[:6]}
+    assert_sfr_matches(got, ref, SFR_FIELDS[:6], np.ones(len(g["raw"]), np.uint8), prefix="bb loader:")
+    # Python slice semantics of the box (negative start wraps, oversize stop clips) against the oracle
+    boxes = np.array([[-30.5, 100.2, 200.0, 150.0], [500.0, 400.0, 400.0, 300.0], [10.0, 10.0, 0.5, 50.0]])
+    raw3 = torch.from_numpy(g["raw"][:1]).cuda().expand(3, -1, -1).contiguous()
+    got3 = sfr.load_bb(raw3, boxes).cpu().numpy()
+    import warnings
+    for b in range(3):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_b = so.load_bb(g["raw"][0], *boxes[b])
+        assert np.array_equal(got3[b].astype(np.float64), ref_b), b

@@ -554,11 +554,17 @@ def run_b200(args):
             t = nxt
         fetched = hf.fetched_bytes(t)
         barrier()
+        host_ms = [0.0, 0.0, 0.0]                            # host time in submit / consume / waiting for the results
         t0 = time.perf_counter()
         for _ in range(n_e2e):
+            ta = time.perf_counter()
             nxt = submit()                                   # batch k+1 starts crossing PCIe
+            tb = time.perf_counter()
             consume(t)                                       # batch k: build + decode + loss + backward + D2H
+            tc = time.perf_counter()
             done.synchronize()                               # the host holds loss and joints of batch k
+            td = time.perf_counter()
+            host_ms[0] += (tb - ta) * 1e3; host_ms[1] += (tc - tb) * 1e3; host_ms[2] += (td - tc) * 1e3
             t = nxt
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -569,6 +575,8 @@ def run_b200(args):
         res = {"value": B * world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": out_host.numel() * 4, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
                "pcie_gbs_per_gpu": h2d / (dt / n_e2e) / 1e9, "window_hw": list(hf.win_hw), "loss_read_back": loss_host,
+               "host_ms_per_step": {"submit": host_ms[0] / n_e2e, "consume": host_ms[1] / n_e2e,
+                                    "wait_for_results": host_ms[2] / n_e2e},
                "frames_in_host_memory_bytes": host_frames.numel() * host_frames.element_size(),
                "note": "per rank and step: com + cube + uvd (%d B) copied from pinned host memory and the crop windows of "
                        "the raw %s frames (%d B of the %d B the frames occupy) pulled over PCIe by pwr_sfr_fetch on a "

@@ -320,10 +320,17 @@ struct SfrArgs {
 //   FMT_U16   16-bit grey PNG (ICVL :632, HAND17 :940): (v/65535)*65535 == v exactly for all 65536 values
 enum { FMT_F32 = 0, FMT_GB16 = 1, FMT_U16 = 2 };
 
+// One pixel as it sits in memory (float bits for FMT_F32, the 16-bit sample otherwise) and its decode: split so
+// that a block of taps can issue all its loads before any decode arithmetic (loads in flight are what the
+// gather lives on).
 template <int FMT>
-__device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx) {
-    if (FMT == FMT_F32) return __ldg(static_cast<const float*>(frame) + idx);
-    const unsigned int v = __ldg(static_cast<const unsigned short*>(frame) + idx);
+__device__ __forceinline__ unsigned int load_raw(const void* __restrict__ frame, int idx) {
+    if (FMT == FMT_F32) return __float_as_uint(__ldg(static_cast<const float*>(frame) + idx));
+    return __ldg(static_cast<const unsigned short*>(frame) + idx);
+}
+template <int FMT>
+__device__ __forceinline__ float decode_px(unsigned int v) {
+    if (FMT == FMT_F32) return __uint_as_float(v);
     if (FMT == FMT_U16) return static_cast<float>(v);
     // x / 255 correctly rounded through the reciprocal (exact for x = 0..255, checked exhaustively)
     const float rc = 0x1.010102p-8f;                     // RN(1/255)
@@ -332,16 +339,34 @@ __device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx
     float bl = __fmul_rn(bq, rc); bl = __fmaf_rn(__fmaf_rn(-bl, 255.f, bq), rc, bl);
     return __fmul_rn(__fadd_rn(__fmul_rn(g, 256.f), bl), 255.f);
 }
+template <int FMT>
+__device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx) {
+    return decode_px<FMT>(load_raw<FMT>(frame, idx));
+}
 
 // Bilinear taps of one 2x2 image block (one label pixel), gathered from the frame with the
 // depth window + centring applied per tap.  INTERIOR: every source row / column of this band
 // lies inside the frame, so no bounds predicates are needed.
-template <typename T, int FMT, bool INTERIOR>
+// Raw 16-bit frames: inside the depth window a sample takes at most 2*cube + 1 distinct raw values, so decode
+// (datasets.py:810 / :940) + window + centring (:312-315) of a tap collapse into one shared-memory lookup,
+// tab[raw - base] (0 outside the table = outside the window).  Each CTA fills the table for its sample with the
+// very functions the per-tap path uses, so the values are bit-identical; what goes away is the per-tap
+// float32 -> float64 -> float32 round trip (XU pipe: 27 % busy in the float32-frame kernel, ncu r1) and the
+// PNG decode arithmetic (which made the raw-frame build SLOWER than the float32 one in r1: 0.59 vs 0.54 ms).
+constexpr int kWinTab = 768;                       // covers cube <= 380 mm; larger cubes use the per-tap arithmetic
+struct WinTab { const float* tab; int base; int n; };
+__device__ __forceinline__ float tab_lookup(unsigned int raw, const WinTab& t) {
+    const unsigned int i = raw - static_cast<unsigned int>(t.base);
+    return i < static_cast<unsigned int>(t.n) ? t.tab[i] : 0.f;
+}
+
+template <typename T, int FMT, bool INTERIOR, bool TAB = false>
 __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __restrict__ frame, const SampleGeom& g,
-                                               const TapX* ytap2, const TapX* xtap2, int pitch) {
+                                               const TapX* ytap2, const TapX* xtap2, int pitch,
+                                               const WinTab& wt = WinTab{nullptr, 0, 0}) {
     // Phase A: all 16 tap loads of the block are issued before any of them is consumed (the kernel lives
     // on loads in flight: with 8 + 8 interleaved with arithmetic it measured 8 % slower, r2).
-    float v[2][2][4];
+    unsigned int v[2][2][4];                       // raw samples; 0 decodes to 0.f in every format
     TapX ty[2], tx[2];
 #pragma unroll
     for (int d = 0; d < 2; ++d) { ty[d] = ytap2[d]; tx[d] = xtap2[d]; }
@@ -355,10 +380,10 @@ __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __rest
         for (int dx = 0; dx < 2; ++dx) {
             const int fc_a = g.fc0 + tx[dx].s0, fc_b = g.fc0 + tx[dx].s1;
             const bool ca = INTERIOR || (fc_a >= g.pc0 && fc_a < g.pc1), cb = INTERIOR || (fc_b >= g.pc0 && fc_b < g.pc1);
-            v[dy][dx][0] = (ra && ca) ? load_px<FMT>(frame, row_a + fc_a) : 0.f;
-            v[dy][dx][1] = (ra && cb) ? load_px<FMT>(frame, row_a + fc_b) : 0.f;
-            v[dy][dx][2] = (rb && ca) ? load_px<FMT>(frame, row_b + fc_a) : 0.f;
-            v[dy][dx][3] = (rb && cb) ? load_px<FMT>(frame, row_b + fc_b) : 0.f;
+            v[dy][dx][0] = (ra && ca) ? load_raw<FMT>(frame, row_a + fc_a) : 0u;
+            v[dy][dx][1] = (ra && cb) ? load_raw<FMT>(frame, row_a + fc_b) : 0u;
+            v[dy][dx][2] = (rb && ca) ? load_raw<FMT>(frame, row_b + fc_a) : 0u;
+            v[dy][dx][3] = (rb && cb) ? load_raw<FMT>(frame, row_b + fc_b) : 0u;
         }
     }
     // Phase B: window + centring per tap, horizontal then vertical lerp (cv::resize's order, un-fused)
@@ -366,10 +391,16 @@ __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __rest
     for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-            const T w00 = Arith<T>::window(static_cast<T>(v[dy][dx][0]), g);
-            const T w01 = Arith<T>::window(static_cast<T>(v[dy][dx][1]), g);
-            const T w10 = Arith<T>::window(static_cast<T>(v[dy][dx][2]), g);
-            const T w11 = Arith<T>::window(static_cast<T>(v[dy][dx][3]), g);
+            T w00, w01, w10, w11;
+            if (TAB) {
+                w00 = static_cast<T>(tab_lookup(v[dy][dx][0], wt)); w01 = static_cast<T>(tab_lookup(v[dy][dx][1], wt));
+                w10 = static_cast<T>(tab_lookup(v[dy][dx][2], wt)); w11 = static_cast<T>(tab_lookup(v[dy][dx][3], wt));
+            } else {
+                w00 = Arith<T>::window(static_cast<T>(decode_px<FMT>(v[dy][dx][0])), g);
+                w01 = Arith<T>::window(static_cast<T>(decode_px<FMT>(v[dy][dx][1])), g);
+                w10 = Arith<T>::window(static_cast<T>(decode_px<FMT>(v[dy][dx][2])), g);
+                w11 = Arith<T>::window(static_cast<T>(decode_px<FMT>(v[dy][dx][3])), g);
+            }
             const T xa0 = static_cast<T>(tx[dx].a0), xa1 = static_cast<T>(tx[dx].a1);
             const T top = Arith<T>::add(Arith<T>::mul(w00, xa0), Arith<T>::mul(w01, xa1));
             const T bot = Arith<T>::add(Arith<T>::mul(w10, xa0), Arith<T>::mul(w11, xa1));
@@ -535,6 +566,8 @@ sfr_build_kernel(SfrArgs a) {
     __shared__ int band_list[TRAIN ? PWR_MAX_JOINTS : 1];   // joints whose footprint touches this band
     __shared__ int band_list_n;
     __shared__ int band_flags[2];                           // [0] mask count, [1] NaN seen (this CTA)
+    constexpr bool kTab = (FMT != FMT_F32) && sizeof(T) == 4;      // raw 16-bit frames: window lookup table
+    __shared__ float wtab[kTab ? kWinTab : 1];
 
     const int band = blockIdx.x % kBands;
     const int b = blockIdx.x / kBands;
@@ -573,6 +606,18 @@ sfr_build_kernel(SfrArgs a) {
     }
     __syncthreads();
     const SampleGeom g = geom;
+    WinTab wt = {wtab, 0, 0};
+    if (kTab && g.ok) {
+        // raw values that can decode into (lo, hi): [floor(lo) - 2, ceil(hi) + 2] (the decode is within 0.02 of the
+        // raw value); every other raw value windows to 0
+        const float lo_f = floorf(g.lo_dn), hi_f = ceilf(g.hi_up);
+        if (lo_f > -1.0e9f && hi_f < 1.0e9f) {
+            const int b0 = max(static_cast<int>(lo_f) - 2, 0), n = static_cast<int>(hi_f) + 3 - b0;
+            if (n > 0 && n <= kWinTab) { wt.base = b0; wt.n = n; }
+        }
+        for (int i = tid; i < wt.n; i += kThreads)
+            wtab[i] = Arith<float>::window(decode_px<FMT>(static_cast<unsigned int>(wt.base + i)), g);
+    }
     if (g.ok) {
         if (tid < kImage) xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);
         else if (tid < kImage + 2 * kBandRows)
@@ -605,8 +650,13 @@ sfr_build_kernel(SfrArgs a) {
         float2 o0 = make_float2(0.f, 0.f), o1 = o0;
         if (g.ok) {
             T px[2][2];
-            if (interior) resample_block<T, FMT, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch);
-            else          resample_block<T, FMT, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch);
+            if (kTab && wt.n > 0) {
+                if (interior) resample_block<T, FMT, true, kTab>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch, wt);
+                else          resample_block<T, FMT, false, kTab>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch, wt);
+            } else {
+                if (interior) resample_block<T, FMT, true>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch);
+                else          resample_block<T, FMT, false>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch);
+            }
             // 2x2 mean (cv::resize reroutes an exact 2x INTER_LINEAR shrink to the area path)
             lab = Arith<T>::mul(Arith<T>::add(Arith<T>::add(px[0][0], px[0][1]), Arith<T>::add(px[1][0], px[1][1])),
                                 T(0.25));
@@ -831,6 +881,9 @@ sfr_aug_kernel(SfrArgs a) {
 // call - into a compact [B, win_h, win_w] buffer the builder then reads in "window mode".  One CTA per
 // (sample, row group); thread 0 re-derives the crop geometry with the builder's own code, so the two agree
 // bit for bit.  The same kernel works on device-resident frames (then it is a plain gather in HBM).
+#ifndef PWR_FETCH_ALIGN_BYTES
+#define PWR_FETCH_ALIGN_BYTES 16
+#endif
 constexpr int kFetchThreads = 256;
 constexpr int kFetchGroups = 4;              // CTAs per sample
 constexpr int kFetchUnroll = 4;              // 16-byte loads in flight per thread
@@ -875,8 +928,10 @@ sfr_fetch_kernel(FetchArgs a) {
                 else { r0 = q0; r1 = q1; c0 = p0; c1 = p1; }
             }
         }
-        c0 = c0 / per16 * per16;                          // outwards to 16 bytes (Wf * elem % 16 == 0)
-        c1 = min((c1 + per16 - 1) / per16 * per16, a.Wf);
+        // outwards to 16 bytes (Wf * elem % 16 == 0); PWR_FETCH_ALIGN_BYTES > 16 widens to whole PCIe read bursts
+        const int al = PWR_FETCH_ALIGN_BYTES / a.elem;
+        c0 = c0 / al * al;
+        c1 = min((c1 + al - 1) / al * al, a.Wf);
         int rows = r1 - r0, cols = c1 - c0;
         if (rows > a.win_h || cols > a.win_w) {           // the caller sized the windows too small
             if (a.status != nullptr) atomicOr(a.status, 1);

@@ -273,3 +273,30 @@ def test_gpu_hand17_bb_loader_matches_reference_golden():
             warnings.simplefilter("ignore")
             ref_b = so.load_bb(g["raw"][0], *boxes[b])
         assert np.array_equal(got3[b].astype(np.float64), ref_b), b
+
+
+@pytest.mark.parametrize("cube", [150.0, 420.0])
+@pytest.mark.parametrize("fmt", ["u16", "nyu_gb16"])
+def test_raw_frame_window_table_equals_per_tap_arithmetic(cube, fmt):
+    """Raw 16-bit frames are windowed through a per-sample lookup table (decode + window + centring of every raw
+    value that can fall inside the window, filled with the per-tap functions); cube = 420 exceeds the table and
+    takes the per-tap arithmetic.  Both must equal the build from the DECODED float32 frames bit for bit."""
+    shape = synth.NYU
+    d = synth.make_frames(shape, 12, seed=13, mixed_cube=False)
+    raw = np.clip(np.rint(d["frames"]), 0, 65535).astype(np.uint16)
+    if fmt == "u16":
+        decoded = np.stack([so.decode_u16(r) for r in raw])
+    else:
+        # oracle.decode_nyu takes one frame of RGB PNG samples: G in channel 1, B in channel 2
+        rgb = np.zeros(raw.shape + (3,), np.uint8)
+        rgb[..., 1], rgb[..., 2] = raw >> 8, raw & 255
+        decoded = np.stack([so.decode_nyu(f) for f in rgb])
+    cubes = np.full(12, cube)
+    kw = dict(fx=shape.fx, fy=shape.fy, prefilter=(40.0, shape.halfu, shape.halfv))
+    a = sfr.build_sfr(torch.from_numpy(raw).cuda(), d["com"], cubes, d["uvd"], frame_format=fmt, targets="both", **kw)
+    b = sfr.build_sfr(torch.from_numpy(np.ascontiguousarray(decoded, dtype=np.float32)).cuda(), d["com"], cubes, d["uvd"],
+                      targets="both", **kw)
+    torch.cuda.synchronize()
+    for name, x, y in zip(a._fields, a, b):
+        assert torch.equal(x, y), "%s differs between the raw-frame and the decoded-frame build (cube %g)" % (name, cube)
+    assert bool(a.valid.any())

@@ -120,7 +120,7 @@ class option:
 
 
 LAUNCHES = {}          # entry point -> number of kernels launched through it
-KERNELS_PER_CALL = {"pwr_sfr_build": 2, "pwr_sfr_crop": 2, "pwr_sfr_fetch": 1}    # prep + main; every other entry point is one kernel
+KERNELS_PER_CALL = {"pwr_sfr_build": 2, "pwr_sfr_crop": 2, "pwr_sfr_fetch": 2}    # prep + main; every other entry point is one kernel
 PROFILE = None         # when a list: (entry point, start event, end event) per launch
 
 

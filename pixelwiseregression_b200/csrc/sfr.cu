@@ -78,7 +78,9 @@ struct SampleGeom {
                                // mode additionally clipped to the part of the frame that was fetched
     int org_r, org_c;          // frame row / column of element (0,0) of this sample's pixel buffer: (0,0) for
                                // whole frames, the window origin written by pwr_sfr_fetch in window mode
+    int pad;                   // explicit tail padding (the struct is copied word by word; keeps initcheck clean)
 };
+static_assert(sizeof(SampleGeom) == 112, "no implicit padding");
 
 // Part of frame b that pwr_sfr_fetch copied into windows[b]: rows [row0, row0+rows) x cols [col0, col0+cols).
 struct WinExtent { int row0, col0, rows, cols; };
@@ -88,7 +90,9 @@ struct JointParam {
     double cd;                 // centred depth  uvd_z - com_z
     int tx0, tx1, ty0, ty1;    // wrapped heat-map indices of the four taps
     int ok;
+    int pad[3];                // explicit tail padding, see SampleGeom
 };
+static_assert(sizeof(JointParam) == 72, "no implicit padding");
 
 struct TapX { int s0, s1; float a0, a1; };
 
@@ -121,7 +125,7 @@ __device__ void sample_geometry(SampleGeom& g, const double* com, double cube, d
                                 double pf_margin, double pf_umax, double pf_vmax) {
     const double cu = com[0], cv = com[1], z = com[2];
     g.z = z; g.cube = cube; g.ok = 0;
-    g.org_r = 0; g.org_c = 0;
+    g.org_r = 0; g.org_c = 0; g.pad = 0;
     g.pr0 = 0; g.pr1 = Hf; g.pc0 = 0; g.pc1 = Wf;
     g.fr0 = g.fc0 = 0; g.nrows = g.ncols = 0; g.r0 = g.c0 = 0;
     g.scale_x = g.scale_y = 1.0;
@@ -214,7 +218,7 @@ __device__ void joint_param(JointParam& p, float* uvd_norm_out, const double* uv
     const double ku = __dadd_rn(__dmul_rn(__ddiv_rn(ru, 127.0), 63.0), 32.0);
     const double kv = __dadd_rn(__dmul_rn(__ddiv_rn(rv, 127.0), 63.0), 32.0);
     p.cd = cd;
-    p.ok = 0;
+    p.ok = 0; p.pad[0] = p.pad[1] = p.pad[2] = 0;
     p.tx0 = p.tx1 = p.ty0 = p.ty1 = 0;
     p.tap[0] = p.tap[1] = p.tap[2] = p.tap[3] = 0.0;
     const double nu = __ddiv_rn(ru, 127.0), nv = __ddiv_rn(rv, 127.0), nd = __ddiv_rn(cd, g.cube);
@@ -467,7 +471,7 @@ __device__ bool prep_joints(const SfrArgs& a, int b, int lane, const SampleGeom&
         if (g.ok) {
             joint_param(jp, un, a.uvd + (static_cast<size_t>(b) * a.J + j) * 3, g, rot);
         } else {
-            jp.ok = 0; jp.cd = 0.0; jp.tx0 = jp.tx1 = jp.ty0 = jp.ty1 = 0;
+            jp.ok = 0; jp.cd = 0.0; jp.tx0 = jp.tx1 = jp.ty0 = jp.ty1 = 0; jp.pad[0] = jp.pad[1] = jp.pad[2] = 0;
             jp.tap[0] = jp.tap[1] = jp.tap[2] = jp.tap[3] = 0.0;
             un[0] = 0.f; un[1] = 0.f; un[2] = 0.f;
         }
@@ -878,12 +882,13 @@ sfr_aug_kernel(SfrArgs a) {
 // 480x640 image although the builder reads only the crop box (176-352 px at NYU depths) inside the hand
 // rectangle.  Here the frames stay in pinned (device-mapped) host memory and this kernel pulls, per sample,
 // exactly that region over PCIe with coalesced 16-byte reads - no host-side repacking, no per-sample memcpy
-// call - into a compact [B, win_h, win_w] buffer the builder then reads in "window mode".  One CTA per
-// (sample, row group); thread 0 re-derives the crop geometry with the builder's own code, so the two agree
-// bit for bit.  The same kernel works on device-resident frames (then it is a plain gather in HBM).
-#ifndef PWR_FETCH_ALIGN_BYTES
-#define PWR_FETCH_ALIGN_BYTES 16
+// call - into a compact [B, win_h, win_w] buffer the builder then reads in "window mode".  A plan kernel
+// re-derives the crop geometry with the builder's own code (so the two agree bit for bit); a small persistent
+// copy kernel moves the bytes.  The same kernels work on device-resident frames (a plain gather in HBM).
+#ifndef PWR_FETCH_GRID
+#define PWR_FETCH_GRID 32
 #endif
+constexpr int kFetchGrid = PWR_FETCH_GRID;      // CTAs of the copy kernel in total (NOT per SM), see below
 constexpr int kFetchThreads = 256;
 constexpr int kFetchGroups = 4;              // CTAs per sample
 constexpr int kFetchUnroll = 4;              // 16-byte loads in flight per thread
@@ -905,68 +910,81 @@ __device__ __forceinline__ void needed_region(const SampleGeom& g, int& r0, int&
     if (r1 <= r0 || c1 <= c0) r0 = r1 = c0 = c1 = 0;
 }
 
-__global__ void __launch_bounds__(kFetchThreads)
-sfr_fetch_kernel(FetchArgs a) {
-    __shared__ WinExtent ext;
-    const int b = blockIdx.x / kFetchGroups, grp = blockIdx.x % kFetchGroups;
+// plan: one thread per sample derives the region with the builder's own geometry code
+__global__ void __launch_bounds__(128)
+sfr_fetch_plan_kernel(FetchArgs a) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= a.B) return;
     const int per16 = 16 / a.elem;                       // elements per 16-byte chunk
-    if (threadIdx.x == 0) {
-        SampleGeom g;
-        int r0, r1, c0, c1;
-        sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
-        needed_region(g, r0, r1, c0, c1);
-        if (a.aug != nullptr) {
-            // the augmented branch crops around the shifted centre (datasets.py:236-246) and falls back to
-            // the plain branch when it raises: fetch the union of both regions
-            const double* au = a.aug + 8 * static_cast<size_t>(b);
-            const double com2[3] = {__dadd_rn(a.com[3 * b + 0], au[1]), __dadd_rn(a.com[3 * b + 1], au[2]), a.com[3 * b + 2]};
-            int q0, q1, p0, p1;
-            sample_geometry(g, com2, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
-            needed_region(g, q0, q1, p0, p1);
-            if (q1 > q0) {
-                if (r1 > r0) { r0 = min(r0, q0); r1 = max(r1, q1); c0 = min(c0, p0); c1 = max(c1, p1); }
-                else { r0 = q0; r1 = q1; c0 = p0; c1 = p1; }
-            }
-        }
-        // outwards to 16 bytes (Wf * elem % 16 == 0); PWR_FETCH_ALIGN_BYTES > 16 widens to whole PCIe read bursts
-        const int al = PWR_FETCH_ALIGN_BYTES / a.elem;
-        c0 = c0 / al * al;
-        c1 = min((c1 + al - 1) / al * al, a.Wf);
-        int rows = r1 - r0, cols = c1 - c0;
-        if (rows > a.win_h || cols > a.win_w) {           // the caller sized the windows too small
-            if (a.status != nullptr) atomicOr(a.status, 1);
-            rows = min(rows, a.win_h); cols = min(cols, a.win_w / per16 * per16);
-        }
-        ext.row0 = r0; ext.col0 = c0; ext.rows = rows; ext.cols = cols;
-        if (grp == 0) {
-            a.extent[b] = ext;
-            if (a.fetched_bytes != nullptr)
-                atomicAdd(a.fetched_bytes, static_cast<unsigned long long>(rows) * cols * a.elem);
+    SampleGeom g;
+    int r0, r1, c0, c1;
+    sample_geometry(g, a.com + 3 * b, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+    needed_region(g, r0, r1, c0, c1);
+    if (a.aug != nullptr) {
+        // the augmented branch crops around the shifted centre (datasets.py:236-246) and falls back to
+        // the plain branch when it raises: fetch the union of both regions
+        const double* au = a.aug + 8 * static_cast<size_t>(b);
+        const double com2[3] = {__dadd_rn(a.com[3 * b + 0], au[1]), __dadd_rn(a.com[3 * b + 1], au[2]), a.com[3 * b + 2]};
+        int q0, q1, p0, p1;
+        sample_geometry(g, com2, a.cube[b], a.fx, a.fy, a.Hf, a.Wf, a.pf_margin, a.pf_umax, a.pf_vmax);
+        needed_region(g, q0, q1, p0, p1);
+        if (q1 > q0) {
+            if (r1 > r0) { r0 = min(r0, q0); r1 = max(r1, q1); c0 = min(c0, p0); c1 = max(c1, p1); }
+            else { r0 = q0; r1 = q1; c0 = p0; c1 = p1; }
         }
     }
-    __syncthreads();
-    const WinExtent e = ext;
-    const int cpr = e.cols / per16;                       // 16-byte chunks per row
-    const int total = e.rows * cpr;
-    const int per = (total + kFetchGroups - 1) / kFetchGroups;
-    const int lo = grp * per, hi = min(total, lo + per);
-    const unsigned char* src = static_cast<const unsigned char*>(a.frames) +
-                               (static_cast<size_t>(b) * a.Hf * a.Wf + static_cast<size_t>(e.row0) * a.Wf + e.col0) * a.elem;
-    unsigned char* dst = static_cast<unsigned char*>(a.windows) + static_cast<size_t>(b) * a.win_h * a.win_w * a.elem;
-    const size_t src_pitch = static_cast<size_t>(a.Wf) * a.elem, dst_pitch = static_cast<size_t>(a.win_w) * a.elem;
-    for (int i = lo + threadIdx.x; i < hi; i += kFetchThreads * kFetchUnroll) {
-        uint4 v[kFetchUnroll];
-        int rr[kFetchUnroll], cc[kFetchUnroll];
+    // outwards to 16 bytes (Wf * elem % 16 == 0).  Wider alignment was measured and lost: 64 / 128 bytes raise the
+    // PCIe rate from 44 to 49 / 51 GB/s but move 13 / 30 % more bytes (tools/ab_fetch.py, r2).
+    c0 = c0 / per16 * per16;
+    c1 = min((c1 + per16 - 1) / per16 * per16, a.Wf);
+    int rows = r1 - r0, cols = c1 - c0;
+    if (rows > a.win_h || cols > a.win_w) {               // the caller sized the windows too small
+        if (a.status != nullptr) atomicOr(a.status, 1);
+        rows = min(rows, a.win_h); cols = min(cols, a.win_w / per16 * per16);
+    }
+    WinExtent ext = {r0, c0, rows, cols};
+    a.extent[b] = ext;
+    if (a.fetched_bytes != nullptr) atomicAdd(a.fetched_bytes, static_cast<unsigned long long>(rows) * cols * a.elem);
+}
+
+// copy: a SMALL persistent grid (kFetchGrid = 32 CTAs in total) walks the (sample, row group) items.  The kernel is
+// PCIe-bound - 32 x 256 threads x 4 x 16 B = 0.5 MB in flight is more than the link needs - and it runs next to the
+// compute stream's kernels for most of a step.  Its loads are system-memory reads with microseconds of latency: on
+// every SM that hosts a fetch CTA they fill the load/store unit's miss queues, and a concurrent kernel that gathers
+// with ordinary loads (the SFR build) crawls on that SM.  Measured (r2, B = 4096 NYU raw frames, tools/ab_e2e.py): one
+// CTA per item (16 384 CTAs) or even ONE CTA on each of the 148 SMs delayed the concurrent SFR build from 0.51 to
+// 6.1 ms (the whole transfer) -> 7.6 ms per step; 32 CTAs confine the damage to 32 SMs -> SFR build 0.63 ms, step
+// 6.07 ms = the transfer itself (grid 8 / 16 / 32 / 64: 7.27 / 6.17 / 6.07 / 6.08 ms per step).  The bulk-TMA
+// decoder kernels never were affected (their loads do not go through the LSU).
+__global__ void __launch_bounds__(kFetchThreads)
+sfr_fetch_copy_kernel(FetchArgs a) {
+    const int per16 = 16 / a.elem;
+    const long long items = static_cast<long long>(a.B) * kFetchGroups;
+    for (long long w = blockIdx.x; w < items; w += gridDim.x) {
+        const int b = static_cast<int>(w / kFetchGroups), grp = static_cast<int>(w % kFetchGroups);
+        const WinExtent e = a.extent[b];
+        const int cpr = e.cols / per16;                   // 16-byte chunks per row
+        const int total = e.rows * cpr;
+        const int per = (total + kFetchGroups - 1) / kFetchGroups;
+        const int lo = grp * per, hi = min(total, lo + per);
+        const unsigned char* src = static_cast<const unsigned char*>(a.frames) +
+                                   (static_cast<size_t>(b) * a.Hf * a.Wf + static_cast<size_t>(e.row0) * a.Wf + e.col0) * a.elem;
+        unsigned char* dst = static_cast<unsigned char*>(a.windows) + static_cast<size_t>(b) * a.win_h * a.win_w * a.elem;
+        const size_t src_pitch = static_cast<size_t>(a.Wf) * a.elem, dst_pitch = static_cast<size_t>(a.win_w) * a.elem;
+        for (int i = lo + threadIdx.x; i < hi; i += kFetchThreads * kFetchUnroll) {
+            uint4 v[kFetchUnroll];
+            int rr[kFetchUnroll], cc[kFetchUnroll];
 #pragma unroll
-        for (int u = 0; u < kFetchUnroll; ++u) {
-            const int k = i + u * kFetchThreads;
-            rr[u] = k / cpr; cc[u] = k - rr[u] * cpr;
-            if (k < hi) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + rr[u] * src_pitch + cc[u] * 16));
-        }
+            for (int u = 0; u < kFetchUnroll; ++u) {
+                const int k = i + u * kFetchThreads;
+                rr[u] = k / cpr; cc[u] = k - rr[u] * cpr;
+                if (k < hi) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + rr[u] * src_pitch + cc[u] * 16));
+            }
 #pragma unroll
-        for (int u = 0; u < kFetchUnroll; ++u) {
-            const int k = i + u * kFetchThreads;
-            if (k < hi) *reinterpret_cast<uint4*>(dst + rr[u] * dst_pitch + cc[u] * 16) = v[u];
+            for (int u = 0; u < kFetchUnroll; ++u) {
+                const int k = i + u * kFetchThreads;
+                if (k < hi) *reinterpret_cast<uint4*>(dst + rr[u] * dst_pitch + cc[u] * 16) = v[u];
+            }
         }
     }
 }
@@ -1249,7 +1267,12 @@ extern "C" int pwr_sfr_fetch(const void* frames, int frame_format, int Hf, int W
     if (static_cast<long long>(B) * kFetchGroups > 0x7fffffffLL) return PWR_E_SHAPE;
     FetchArgs a = {frames, elem, Hf, Wf, com, cube, aug, fx, fy, prefilter_margin, prefilter_umax, prefilter_vmax,
                    windows, win_h, win_w, reinterpret_cast<WinExtent*>(win_extent), fetched_bytes, status, B};
-    sfr_fetch_kernel<<<static_cast<unsigned>(B) * kFetchGroups, kFetchThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    sfr_fetch_plan_kernel<<<(B + 127) / 128, 128, 0, s>>>(a);
+    if (int rc = launch_status()) return rc;
+    const long long items = static_cast<long long>(B) * kFetchGroups;
+    const long long cap = kFetchGrid;
+    sfr_fetch_copy_kernel<<<static_cast<unsigned>(items < cap ? items : cap), kFetchThreads, 0, s>>>(a);
     return launch_status();
 }
 

@@ -50,8 +50,8 @@ class HostFeed:
         self.test_only, self.targets, self.augment = test_only, targets, augment
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.win_hw = win_hw
-        # high priority: when an SM has a free slot the fetch CTAs (tiny, PCIe-latency-bound) go first, so the
-        # compute kernels of the batch in flight do not starve the transfer of the next one
+        # high priority: the fetch grid is small (2 CTAs per SM) and PCIe-latency-bound; it must get its few slots
+        # as soon as they free up so the compute kernels of the batch in flight do not starve the next transfer
         self.copy_stream = torch.cuda.Stream(self.device, priority=-1)
         self.slots = [_Slot() for _ in range(max(int(depth), 1))]
         self.n = 0

@@ -69,8 +69,9 @@ const char* pwr_error_string(int rc);
 #define PWR_OPT_FWD_DIRECT  1   /* 1: one-CTA-per-item forward even without the heat-map store  */
 #define PWR_OPT_FWD_PIPE    2   /* 1: pipelined forward even with the heat-map store            */
 #define PWR_OPT_BWD_NO_LEAN 3   /* 1: 1-CTA/SM pipelined backward where the lean one would run  */
-#define PWR_OPT_SFR_GATHER  4   /* 1: SFR build gathers its taps from HBM instead of staging the
-                                      source rows in shared memory                               */
+#define PWR_OPT_SFR_STAGED  4   /* 1: SFR build stages the source rows of a band in shared memory
+                                      (bulk-TMA row copies) instead of gathering its taps from HBM;
+                                      measured slower, kept for A/B runs     */
 #define PWR_OPT_COUNT       5
 int pwr_set_option(int option, int value);
 

@@ -45,6 +45,8 @@
 
 namespace pwr {
 
+int get_option(int option);      // dispatch overrides, defined in decoder.cu (pwr_set_option)
+
 // CTAs (horizontal bands of the label image) per sample.  With dense maps a CTA's band of all 2J maps
 // is zero-filled while the taps are fetched, and 8 bands measured best (2/4/8/16: 0.60/0.59/0.54/0.55 ms
 // at B=4096 NYU); without them (test-only SFR, compact targets) nothing overlaps that prologue and
@@ -57,7 +59,15 @@ namespace pwr {
 #endif
 constexpr int kBandsDense = PWR_SFR_BANDS;
 constexpr int kBandsLean = PWR_SFR_BANDS_LEAN;
-constexpr int kBandsMax = kBandsDense > kBandsLean ? kBandsDense : kBandsLean;
+#ifndef PWR_SFR_BANDS_STAGED_U16
+#define PWR_SFR_BANDS_STAGED_U16 8
+#endif
+#ifndef PWR_SFR_BANDS_STAGED_F32
+#define PWR_SFR_BANDS_STAGED_F32 16
+#endif
+constexpr int kBandsStagedU16 = PWR_SFR_BANDS_STAGED_U16;
+constexpr int kBandsStagedF32 = PWR_SFR_BANDS_STAGED_F32;
+constexpr int kBandsMax = 16;
 
 // cv::getGaussianKernel(7, 1.5, CV_64F), OpenCV 4.13.0 (softdouble, exact bits)
 __constant__ double kGauss7[7] = {0x1.2c18a51a3e5e7p-5, 0x1.c7ce552574441p-4, 0x1.bbe4f897eb627p-3,
@@ -327,8 +337,12 @@ enum { FMT_F32 = 0, FMT_GB16 = 1, FMT_U16 = 2 };
 // One pixel as it sits in memory (float bits for FMT_F32, the 16-bit sample otherwise) and its decode: split so
 // that a block of taps can issue all its loads before any decode arithmetic (loads in flight are what the
 // gather lives on).
-template <int FMT>
+template <int FMT, bool SMEM = false>
 __device__ __forceinline__ unsigned int load_raw(const void* __restrict__ frame, int idx) {
+    if (SMEM) {     // staged source rows: ordinary (shared-memory) loads
+        if (FMT == FMT_F32) return static_cast<const unsigned int*>(frame)[idx];
+        return static_cast<const unsigned short*>(frame)[idx];
+    }
     if (FMT == FMT_F32) return __float_as_uint(__ldg(static_cast<const float*>(frame) + idx));
     return __ldg(static_cast<const unsigned short*>(frame) + idx);
 }
@@ -364,7 +378,7 @@ __device__ __forceinline__ float tab_lookup(unsigned int raw, const WinTab& t) {
     return i < static_cast<unsigned int>(t.n) ? t.tab[i] : 0.f;
 }
 
-template <typename T, int FMT, bool INTERIOR, bool TAB = false>
+template <typename T, int FMT, bool INTERIOR, bool TAB = false, bool SMEM = false>
 __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __restrict__ frame, const SampleGeom& g,
                                                const TapX* ytap2, const TapX* xtap2, int pitch,
                                                const WinTab& wt = WinTab{nullptr, 0, 0}) {
@@ -384,10 +398,10 @@ __device__ __forceinline__ void resample_block(T (&px)[2][2], const void* __rest
         for (int dx = 0; dx < 2; ++dx) {
             const int fc_a = g.fc0 + tx[dx].s0, fc_b = g.fc0 + tx[dx].s1;
             const bool ca = INTERIOR || (fc_a >= g.pc0 && fc_a < g.pc1), cb = INTERIOR || (fc_b >= g.pc0 && fc_b < g.pc1);
-            v[dy][dx][0] = (ra && ca) ? load_raw<FMT>(frame, row_a + fc_a) : 0u;
-            v[dy][dx][1] = (ra && cb) ? load_raw<FMT>(frame, row_a + fc_b) : 0u;
-            v[dy][dx][2] = (rb && ca) ? load_raw<FMT>(frame, row_b + fc_a) : 0u;
-            v[dy][dx][3] = (rb && cb) ? load_raw<FMT>(frame, row_b + fc_b) : 0u;
+            v[dy][dx][0] = (ra && ca) ? load_raw<FMT, SMEM>(frame, row_a + fc_a) : 0u;
+            v[dy][dx][1] = (ra && cb) ? load_raw<FMT, SMEM>(frame, row_a + fc_b) : 0u;
+            v[dy][dx][2] = (rb && ca) ? load_raw<FMT, SMEM>(frame, row_b + fc_a) : 0u;
+            v[dy][dx][3] = (rb && cb) ? load_raw<FMT, SMEM>(frame, row_b + fc_b) : 0u;
         }
     }
     // Phase B: window + centring per tap, horizontal then vertical lerp (cv::resize's order, un-fused)
@@ -556,7 +570,44 @@ sfr_prep_kernel(SfrArgs a) {
 // ---------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------
-template <typename T, int FMT, bool TRAIN, int kBands>
+// mbarrier / bulk-TMA helpers (same forms as decoder.cu)
+__device__ __forceinline__ uint32_t sfr_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sfr_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sfr_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sfr_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sfr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sfr_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "SFR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra SFR_DONE;\n"
+        "bra SFR_WAIT;\n"
+        "SFR_DONE:\n"
+        "}" ::"r"(sfr_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sfr_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sfr_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sfr_smem_u32(bar)) : "memory");
+}
+
+// STAGED (dispatch option PWR_OPT_SFR_STAGED, off by default): the source rows of the band (the crop box rows its taps
+// touch, clipped to the non-zero rectangle, columns rounded outwards to 16 bytes) are brought into shared memory with
+// one 1-D bulk-TMA copy per row, all in flight at once and independent of registers / occupancy; the resample then
+// gathers from shared memory.  A band whose rows do not fit kStageBytes (large crop boxes) keeps the direct gather.
+// Bit-identical to the gather (tests/test_gpu_sfr.py) and measured SLOWER on B200 at B = 4096 (r2, ms per build,
+// gather -> staged): NYU float32 dense 0.546 -> 0.669, compact 0.244 -> 0.421; raw uint16 dense 0.511 -> 0.574,
+// compact 0.243 -> 0.355; HAND17 test-only 0.222 -> 0.362 (float32), 0.220 -> 0.304 (uint16).  Why: the gather kernels
+// are not waiting for bytes - the dense one moves its real DRAM traffic at 92 % of the copy peak, the compact ones
+// issue 2.3 instructions per clock per SM - so staging only adds what it costs: 36 KB per CTA (4 CTAs per SM instead
+// of 5-6), a full-CTA wait on the row copies, and bands short enough to fit the stage (8 / 16 per sample), each of
+// which repeats the per-sample prologue (x-tap table in float64, window table).
+constexpr int kStageBytes = 36 * 1024;
+
+template <typename T, int FMT, bool TRAIN, int kBands, bool STAGED = false>
 __global__ void __launch_bounds__(kThreads)
 sfr_build_kernel(SfrArgs a) {
     constexpr int kBandRows = kLabel / kBands;                    // label rows per CTA
@@ -572,6 +623,8 @@ sfr_build_kernel(SfrArgs a) {
     __shared__ int band_flags[2];                           // [0] mask count, [1] NaN seen (this CTA)
     constexpr bool kTab = (FMT != FMT_F32) && sizeof(T) == 4;      // raw 16-bit frames: window lookup table
     __shared__ float wtab[kTab ? kWinTab : 1];
+    extern __shared__ __align__(128) unsigned char stage_raw[];    // STAGED: kStageBytes of source rows
+    __shared__ __align__(8) uint64_t stage_bar;
 
     const int band = blockIdx.x % kBands;
     const int b = blockIdx.x / kBands;
@@ -589,7 +642,13 @@ sfr_build_kernel(SfrArgs a) {
             const int words = a.J * static_cast<int>(sizeof(JointParam) / 4);
             for (int i = tid; i < words; i += kThreads) reinterpret_cast<uint32_t*>(joints)[i] = __ldcg(js + i);
         }
-        if (tid == 0) { band_list_n = 0; band_flags[0] = 0; band_flags[1] = 0; }
+        if (tid == 0) {
+            band_list_n = 0; band_flags[0] = 0; band_flags[1] = 0;
+            if (STAGED) {
+                sfr_mbar_init(&stage_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+        }
     }
     // ... while pass A of phase 2 streams the zeros: a heat map is zero outside the <= 8x8
     // footprint of the blurred 4-tap splat, and so is the depth map, so every map band is
@@ -610,6 +669,33 @@ sfr_build_kernel(SfrArgs a) {
     }
     __syncthreads();
     const SampleGeom g = geom;
+    constexpr int kElem = (FMT == FMT_F32) ? 4 : 2;
+    const unsigned char* frame_bytes = static_cast<const unsigned char*>(a.frames) +
+                                       static_cast<size_t>(b) * a.frame_stride * kElem;
+    // ---- STAGED: plan + issue the row copies first, so they fly while the tap tables are built
+    bool staged = false;
+    int st_rlo = 0, st_c0 = 0, st_pitch = 0;       // frame row of staged row 0; buffer column of staged column 0; elements per staged row
+    if (STAGED && g.ok) {
+        constexpr int per16 = 16 / kElem;
+        const TapX t0 = linear_tap(band * 2 * kBandRows, g.nrows, g.scale_y);
+        const TapX t1 = linear_tap(band * 2 * kBandRows + 2 * kBandRows - 1, g.nrows, g.scale_y);
+        const int rlo = max(g.fr0 + t0.s0, g.pr0), rhi = min(g.fr0 + t1.s1 + 1, g.pr1);
+        const int c_lo = max(g.fc0, g.pc0) - g.org_c, c_hi = min(g.fc0 + g.ncols, g.pc1) - g.org_c;     // buffer columns
+        const int c_lo_al = c_lo / per16 * per16, c_hi_al = min((c_hi + per16 - 1) / per16 * per16, a.pitch);
+        const int n_rows = rhi - rlo, seg = c_hi_al - c_lo_al;
+        if (n_rows > 0 && seg > 0 && c_lo >= 0 && n_rows * seg * kElem <= kStageBytes) {
+            staged = true; st_rlo = rlo; st_c0 = c_lo_al; st_pitch = seg;
+            if (tid < 32) {
+                const uint32_t seg_bytes = static_cast<uint32_t>(seg) * kElem;
+                if (tid == 0) sfr_mbar_expect_tx(&stage_bar, seg_bytes * static_cast<uint32_t>(n_rows));
+                __syncwarp();
+                for (int r = tid; r < n_rows; r += 32)
+                    sfr_bulk_g2s(stage_raw + static_cast<size_t>(r) * seg_bytes,
+                                 frame_bytes + (static_cast<size_t>(rlo + r - g.org_r) * a.pitch + c_lo_al) * kElem,
+                                 seg_bytes, &stage_bar);
+            }
+        }
+    }
     WinTab wt = {wtab, 0, 0};
     if (kTab && g.ok) {
         // raw values that can decode into (lo, hi): [floor(lo) - 2, ceil(hi) + 2] (the decode is within 0.02 of the
@@ -638,12 +724,18 @@ sfr_build_kernel(SfrArgs a) {
     float* img_b = a.img + static_cast<size_t>(b) * kImage * kImage;
     float* lab_b = a.label_img + static_cast<size_t>(b) * kMap;
     float* msk_b = a.mask + static_cast<size_t>(b) * kMap;
-    const void* frame = static_cast<const unsigned char*>(a.frames) +
-                        static_cast<size_t>(b) * a.frame_stride * (FMT == FMT_F32 ? 4 : 2);
+    const void* frame = frame_bytes;
     const T cube_t = static_cast<T>(g.cube);
     const T cube_r = Arith<T>::rcp(cube_t);
     const bool interior = g.ok && g.fc0 >= g.pc0 && g.fc0 + g.ncols <= g.pc1 && g.fr0 + ytap[0].s0 >= g.pr0 &&
                           g.fr0 + ytap[2 * kBandRows - 1].s1 < g.pr1;
+    // staged rows: the same tap arithmetic on a "pixel buffer" that is the shared-memory stage (origin = first
+    // staged row / column, pitch = staged row length); the bounds predicates are the frame's, unchanged
+    SampleGeom gs = g;
+    if (STAGED && staged) {
+        gs.org_r = st_rlo; gs.org_c = g.org_c + st_c0;
+        sfr_mbar_wait(&stage_bar, 0);
+    }
     int my_count = 0, my_nan = 0;
 #pragma unroll 2
     for (int it = 0; it < kLabelIters; ++it) {
@@ -654,7 +746,15 @@ sfr_build_kernel(SfrArgs a) {
         float2 o0 = make_float2(0.f, 0.f), o1 = o0;
         if (g.ok) {
             T px[2][2];
-            if (kTab && wt.n > 0) {
+            if (STAGED && staged) {
+                if (kTab && wt.n > 0) {
+                    if (interior) resample_block<T, FMT, true, kTab, true>(px, stage_raw, gs, &ytap[2 * lrow], &xtap[2 * lx], st_pitch, wt);
+                    else          resample_block<T, FMT, false, kTab, true>(px, stage_raw, gs, &ytap[2 * lrow], &xtap[2 * lx], st_pitch, wt);
+                } else {
+                    if (interior) resample_block<T, FMT, true, false, true>(px, stage_raw, gs, &ytap[2 * lrow], &xtap[2 * lx], st_pitch);
+                    else          resample_block<T, FMT, false, false, true>(px, stage_raw, gs, &ytap[2 * lrow], &xtap[2 * lx], st_pitch);
+                }
+            } else if (kTab && wt.n > 0) {
                 if (interior) resample_block<T, FMT, true, kTab>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch, wt);
                 else          resample_block<T, FMT, false, kTab>(px, frame, g, &ytap[2 * lrow], &xtap[2 * lx], a.pitch, wt);
             } else {
@@ -1150,11 +1250,28 @@ static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t str
         else if (fmt == FMT_GB16) sfr_build_kernel<float, FMT_GB16, TRAIN, NB><<<grid, kThreads, 0, stream>>>(a);  \
         else                      sfr_build_kernel<float, FMT_U16, TRAIN, NB><<<grid, kThreads, 0, stream>>>(a);   \
     } while (0)
-    if constexpr (TRAIN) {
-        if (a.heatmaps != nullptr) {
-            PWR_LAUNCH_SFR(kBandsDense);
-            return launch_status();
-        }
+    // staged (bulk-TMA) variant: source rows of a band in kStageBytes of dynamic shared memory
+#define PWR_LAUNCH_SFR_STAGED(T, F, NB)                                                                            \
+    do {                                                                                                           \
+        PWR_ENSURE_DYN_SMEM(kStageBytes, dev, sfr_build_kernel<T, F, TRAIN, NB, true>);                            \
+        sfr_build_kernel<T, F, TRAIN, NB, true><<<static_cast<unsigned>(a.B) * NB, kThreads, kStageBytes, stream>>>(a); \
+    } while (0)
+    const int elem = fmt == FMT_F32 ? 4 : 2;
+    const bool can_stage = get_option(PWR_OPT_SFR_STAGED) != 0 && (static_cast<long long>(a.pitch) * elem) % 16 == 0 &&
+                           !misaligned(a.frames);
+    const bool dense_maps = TRAIN && a.heatmaps != nullptr;
+    if (can_stage) {
+        const int dev = current_device();
+        // 2-byte samples: 8 bands (<= 46 source rows of <= 368 px); 4-byte samples: 16 bands (half the rows)
+        if (frame_f64)            PWR_LAUNCH_SFR_STAGED(double, FMT_F32, kBandsStagedF32);
+        else if (fmt == FMT_F32)  PWR_LAUNCH_SFR_STAGED(float, FMT_F32, kBandsStagedF32);
+        else if (fmt == FMT_GB16) PWR_LAUNCH_SFR_STAGED(float, FMT_GB16, kBandsStagedU16);
+        else                      PWR_LAUNCH_SFR_STAGED(float, FMT_U16, kBandsStagedU16);
+        return launch_status();
+    }
+    if (dense_maps) {
+        PWR_LAUNCH_SFR(kBandsDense);
+        return launch_status();
     }
     // Without dense maps, 2 long bands per sample win at large batches (no zero-fill to overlap the prologue);
     // a small batch (config 5 sweeps from 256) cannot fill 148 SMs x 6 CTAs with 2 CTAs per sample, so it takes
@@ -1163,6 +1280,7 @@ static int launch_sfr(const SfrArgs& a, int frame_f64, int fmt, cudaStream_t str
         PWR_LAUNCH_SFR(kBandsDense);
     else
         PWR_LAUNCH_SFR(kBandsLean);
+#undef PWR_LAUNCH_SFR_STAGED
 #undef PWR_LAUNCH_SFR
     return launch_status();
 }

@@ -300,3 +300,43 @@ def test_raw_frame_window_table_equals_per_tap_arithmetic(cube, fmt):
     for name, x, y in zip(a._fields, a, b):
         assert torch.equal(x, y), "%s differs between the raw-frame and the decoded-frame build (cube %g)" % (name, cube)
     assert bool(a.valid.any())
+
+
+@pytest.mark.parametrize("shape_name,fmt", [("NYU", "f32"), ("NYU", "nyu_gb16"), ("HAND17", "u16"), ("MSRA", "f32")])
+def test_staged_source_rows_equal_the_direct_gather(shape_name, fmt):
+    """The builder gathers its taps straight from HBM (default) or stages the source rows of a band in shared memory
+    with bulk-TMA copies (dispatch option `sfr_staged`; inside that kernel, bands whose rows do not fit the stage
+    still gather): bit-identical outputs, including boxes over the frame corners, a box larger than the frame (no band
+    fits: gather inside the staged kernel) and a tiny far-away hand (a handful of source rows)."""
+    from pixelwiseregression_b200 import _lib
+    shape = synth.SHAPES[shape_name]
+    B = 20
+    d = synth.make_frames(shape, B, seed=23)
+    d["com"][0, :2] = (2.2, 3.7)
+    d["com"][1, :2] = (shape.width - 1.5, shape.height - 2.5)
+    d["com"][2, 2] = 140.0                             # box far larger than the frame
+    d["com"][3, 2] = 4000.0                            # box of ~40 px: upsampling, few source rows
+    frames = d["frames"] if fmt == "f32" else np.clip(np.rint(d["frames"]), 0, 65535).astype(np.uint16)
+    kw = dict(fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64)
+    if fmt != "f32":
+        kw.update(frame_format=fmt, prefilter=(40.0, shape.halfu, shape.halfv), frame_f64=False)
+    com = None if shape.com_from_frame else d["com"]
+    fr = torch.from_numpy(frames).cuda()
+    for mode in (dict(targets="both"), dict(targets="sparse"), dict(test_only=True)):
+        uvd = None if mode.get("test_only") else d["uvd"]
+        gather = sfr.build_sfr(fr, com, d["cube"], uvd, **kw, **mode)
+        with _lib.option("sfr_staged", 1):
+            staged = sfr.build_sfr(fr, com, d["cube"], uvd, **kw, **mode)
+        torch.cuda.synchronize()
+        for name, x, y in zip(staged._fields, staged, gather):
+            assert (x is None and y is None) or torch.equal(x, y), "%s differs (staged vs gather, %s)" % (name, mode)
+    # window mode (fetched crop windows) through the staged kernel as well
+    if com is not None:
+        comd, cubed = torch.from_numpy(d["com"]).cuda(), torch.from_numpy(d["cube"]).cuda()
+        wkw = {k: v for k, v in kw.items() if k != "frame_f64"}
+        fw = sfr.fetch_windows(fr, comd, cubed, win_hw=(shape.height, shape.width), **wkw)
+        with _lib.option("sfr_staged", 1):
+            a = sfr.build_sfr(fw, comd, cubed, d["uvd"], **kw)
+        b = sfr.build_sfr(fr, comd, cubed, d["uvd"], **kw)
+        for name, x, y in zip(a._fields, a, b):
+            assert (x is None and y is None) or torch.equal(x, y), "%s differs (window mode, staged)" % name

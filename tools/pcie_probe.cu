@@ -56,6 +56,43 @@ __global__ void fetch_windows(const uint16_t* __restrict__ frames, int Hf, int W
     }
 }
 
+
+// ---- bulk-TMA variant: one warp per CTA, every lane moves one window row at a time host -> shared -> HBM
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__global__ void __launch_bounds__(32)
+fetch_windows_tma(const uint16_t* __restrict__ frames, int Hf, int Wf, const Win* __restrict__ wins,
+                  uint16_t* __restrict__ out, int WR, int WC, int B) {
+    extern __shared__ __align__(128) unsigned char ring[];          // [32][slot_bytes]
+    __shared__ __align__(8) uint64_t bars[32];
+    const int lane = threadIdx.x;
+    const int slot_bytes = WC * 2;
+    unsigned char* slot = ring + static_cast<size_t>(lane) * slot_bytes;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[lane])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t parity = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const Win w = wins[b];
+        const uint32_t bytes = static_cast<uint32_t>(w.cols) * 2;
+        const uint16_t* src = frames + static_cast<size_t>(b) * Hf * Wf + static_cast<size_t>(w.r0) * Wf + w.c0;
+        uint16_t* dst = out + static_cast<size_t>(b) * WR * WC;
+        for (int r = lane; r < w.rows; r += 32) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[lane])), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(slot)), "l"(src + static_cast<size_t>(r) * Wf), "r"(bytes), "r"(smem_u32(&bars[lane])) : "memory");
+            asm volatile(
+                "{\n.reg .pred P1;\nW1:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra D1;\nbra W1;\nD1:\n}" ::"r"(
+                    smem_u32(&bars[lane])), "r"(parity) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<size_t>(r) * WC),
+                         "r"(smem_u32(slot)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            parity ^= 1;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 static float time_ms(cudaStream_t s, int reps, void (*fn)(void*), void* ctx) {
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -184,6 +221,18 @@ int main(int argc, char** argv) {
                    win_bytes / ms / 1e6, B / ms * 1e3);
         }
     }
+
+    // bulk-TMA gather: rows host -> shared -> HBM, one row per lane in flight
+    for (int grid : {32, 64, 148, 592}) {
+        c.groups = grid;
+        CK(cudaFuncSetAttribute(fetch_windows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * c.WC * 2));
+        ms = time_ms(c.s, 3, [](void* p) { Ctx& c = *static_cast<Ctx*>(p);
+            fetch_windows_tma<<<c.groups, 32, 32 * c.WC * 2, c.s>>>(c.host, c.Hf, c.Wf, c.wins_d, c.out, c.WR, c.WC, c.B); }, &c);
+        CK(cudaGetLastError());
+        printf(", \"tma_windows_grid%d\": {\"ms\": %.3f, \"gbs_useful\": %.2f, \"samples_per_s\": %.0f}", grid, ms,
+               win_bytes / ms / 1e6, B / ms * 1e3);
+    }
+    // LDG gather with a small persistent-like grid for comparison (groups = 1, few CTAs is not expressible here: B*groups CTAs)
     // same kernel on device-resident frames (upper bound without PCIe)
     c.groups = 4;
     ms = time_ms(c.s, 3, [](void* p) { Ctx& c = *static_cast<Ctx*>(p);

@@ -471,7 +471,7 @@ def run_b200(args):
         g_arena = sfr.SfrArena()
         zd, Dd, wd = z.detach(), D.detach(), w.detach()
 
-        def raw_step():
+        def graph_body():
             bt = sfr.build_sfr(frames, com, cube, uvd, arena=g_arena, **sfr_kw)
             H, uvd_o, gz, gD, gwp, lp = ops.decoder_fused_raw(zd, wd, Dd, bt.label_img, bt.mask,
                                                              (bt.heatmaps, bt.depthmaps, bt.uvd), "softmax", alpha,
@@ -483,11 +483,11 @@ def run_b200(args):
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            raw_step()
+            graph_body()
         torch.cuda.current_stream().wait_stream(side)
         cuda_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cuda_graph):
-            g_out = raw_step()
+            g_out = graph_body()
         for _ in range(3):
             cuda_graph.replay()
         barrier()

@@ -89,6 +89,9 @@ def run_training(shape, batch, steps, warmup, decoder="fused", features=128, lev
     def step():
         b = sfr.build_sfr(d["frames"], None if shape.com_from_frame else d["com"], d["cube"], d["uvd"],
                           fx=shape.fx, fy=shape.fy, frame_f64=shape.frame_f64, arena=arena)
+        # the reference raises on samples it cannot build (datasets.py:323-327, 362-365, 385-390), so they never
+        # reach the loss; here they are flagged and dropped before the model (a no-op when all are valid)
+        b = sfr.select_valid(b)
         optim.zero_grad(set_to_none=True)
         if decoder == "fused":
             loss = model(b.img, b.label_img, b.mask, b.uvd, b.heatmaps, b.depthmaps, alpha, lambda_h, lambda_d)

@@ -138,8 +138,8 @@ def window_size(com, cube, fx, fy, Hf, Wf, frame_format="f32", augment=False):
 def fetch_windows(frames, com, cube, *, fx, fy, frame_format="f32", prefilter=None, augment=None, win_hw=None,
                   out=None):
     """Host -> device feed (pwr_sfr_fetch): `frames` [B,Hf,Wf] in PINNED host memory (torch `pin_memory()`;
-    device-addressable under UVA) or on the device; `com` [B,3], `cube` [B] float64 ON THE DEVICE (they are a few
-    KB: copy them first).  Copies, per sample, only the crop box AND hand rectangle the builder will read into a
+    device-addressable under UVA) or on the device; `com` [B,3], `cube` [B] float64 (device tensors, or host arrays
+    that are copied first: they are a few KB).  Copies, per sample, only the crop box AND hand rectangle the builder will read into a
     compact window buffer and returns FrameWindows for `build_sfr(frames=...)`.  Enqueued on the current stream.
     `win_hw`: window size; default from `window_size` (needs host copies of com / cube -> pass it explicitly
     when they only exist on the device).  `out`: a previous FrameWindows of the same shape to overwrite."""
@@ -150,9 +150,16 @@ def fetch_windows(frames, com, cube, *, fx, fy, frame_format="f32", prefilter=No
         raise _lib.PwrError("fetch_windows reads the frames from the GPU: host frames must be pinned (pin_memory())")
     if not frames.is_contiguous():
         raise _lib.PwrError("frames must be contiguous")
-    require_cuda(com, cube)
-    dev = com.device
+    if not torch.cuda.is_available():
+        raise _lib.PwrError("fetch_windows needs a CUDA device (there is no CPU fallback)")
+    dev = frames.device if frames.is_cuda else (com.device if isinstance(com, torch.Tensor) and com.is_cuda
+                                                else torch.device("cuda", torch.cuda.current_device()))
+    com, cube = _f64(com, dev), _f64(cube, dev)           # a few KB: host arrays are copied, device tensors pass through
     B, Hf, Wf = frames.shape
+    if cube.dim() == 0:
+        cube = cube.expand(B).contiguous()
+    if tuple(com.shape) != (B, 3) or tuple(cube.shape) != (B,):
+        raise _lib.PwrError("com must be [B,3] and cube [B]")
     lib = _lib.load()
     aug_dev = None
     if augment is not None:

@@ -294,6 +294,8 @@ def run_b200(args):
     pending = {"work": False}
     arenas = {}
 
+    store_heat = {"on": True}      # False: the last stage as model.forward_loss runs it (heat maps never leave the kernel)
+
     def step(frames_, com_, cube_, uvd_, z_, D_, kw=None, key="main"):
         """The public-API call sequence a training loop makes for this path."""
         kw = kw or sfr_kw
@@ -305,7 +307,7 @@ def run_b200(args):
             pending["work"] = False
         total, terms, uvd_out = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, heat_t,
                                                        batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
-                                                       lambda_h=lambda_h, lambda_d=lambda_d, store_heat=True)[:3]
+                                                       lambda_h=lambda_h, lambda_d=lambda_d, store_heat=store_heat["on"])[:3]
         z_.grad = D_.grad = w.grad = None
         total.backward()
         if world > 1:
@@ -415,7 +417,7 @@ def run_b200(args):
                 "step_roofline_frac": sample_bytes * B / (ms_v * 1e-3) / 1e9 / peak,
                 "kernels": kernel_table(prof_v, bytes_table), "note": note}
 
-    two_kernel = sparse = raw_step = None
+    two_kernel = sparse = raw_step = no_heat = None
     if not args.no_sparse:
         # (1) SURVEY 8d's own accounting: forward kernel, then backward+loss kernel (the logits are read twice)
         two_kernel = timed_variant(
@@ -433,6 +435,19 @@ def run_b200(args):
             roofline.step_one_pass_bytes(J, sparse=True),
             "same step, same results; targets handed to the loss kernel as 64-byte taps per joint instead of two "
             "dense 16 KiB maps (sfr.build_sfr(targets='sparse'))", "sparse")
+        # (2b) the last stage exactly as PixelwiseRegression.forward_loss runs it: nothing but the loss consumes its heat
+        # maps, so they are not stored (6J + 2 maps instead of 7J + 2)
+        store_heat["on"] = False
+        try:
+            no_heat = timed_variant(
+                frames, None, True,
+                {"pwr_sfr_build": roofline.sfr_build_bytes(J),
+                 "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, store_heat=False)},
+                roofline.sfr_build_bytes(J) + roofline.decoder_fused_bytes(J, store_heat=False),
+                "same step without the heat-map store of the last stage (store_heat=False, what model.forward_loss "
+                "does: train.py:192-207 only feeds the last stage's heat maps to the loss)", "noheat")
+        finally:
+            store_heat["on"] = True
         # (3) the step fed with the raw 16-bit sensor frames (half the source bytes; PNG decode + hand rectangle of
         # load_from_text inside the SFR kernel), dense targets, against SURVEY 8d's bytes
         if raw_frames is not None and args.frame_format == "f32" and not args.augment:
@@ -765,6 +780,7 @@ def run_b200(args):
             "two_kernel_step": two_kernel,
             "sparse_targets": sparse,
             "raw_frames_step": raw_step,
+            "no_heat_store_step": no_heat,
             "inner_stage": inner,
             "two_stage_decoder": two_stage,
             "graph_step": graph_step,

@@ -72,10 +72,7 @@ const char* pwr_error_string(int rc);
 #define PWR_OPT_SFR_STAGED  4   /* 1: SFR build stages the source rows of a band in shared memory
                                       (bulk-TMA row copies) instead of gathering its taps from HBM;
                                       measured slower, kept for A/B runs     */
-#define PWR_OPT_FETCH_TMA   5   /* 1: pwr_sfr_fetch copies with bulk-TMA row copies (host -> shared
-                                      -> HBM) instead of 16-byte loads / stores; same PCIe rate,
-                                      measured 3 % slower per step            */
-#define PWR_OPT_COUNT       6
+#define PWR_OPT_COUNT       5
 int pwr_set_option(int option, int value);
 
 /* ------------------------------------------------------------------------ *

@@ -50,10 +50,10 @@ SIGNATURES = {
 }
 
 ABI_VERSION = 200      # PWR_VERSION of include/pwr.h this binding is written against
-OPTIONS = {"bwd_direct": 0, "fwd_direct": 1, "fwd_pipe": 2, "bwd_no_lean": 3, "sfr_staged": 4, "fetch_tma": 5}
+OPTIONS = {"bwd_direct": 0, "fwd_direct": 1, "fwd_pipe": 2, "bwd_no_lean": 3, "sfr_staged": 4}
 _ENV_OPTIONS = {"PWR_BWD_DIRECT": ("bwd_direct", "1"), "PWR_FWD_DIRECT": ("fwd_direct", "1"),
                 "PWR_FWD_PIPE": ("fwd_pipe", "1"), "PWR_BWD_LEAN": ("bwd_no_lean", "0"),
-                "PWR_SFR_STAGED": ("sfr_staged", "1"), "PWR_FETCH_TMA": ("fetch_tma", "1")}
+                "PWR_SFR_STAGED": ("sfr_staged", "1")}
 
 _lib = None
 

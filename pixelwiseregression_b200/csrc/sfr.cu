@@ -683,14 +683,16 @@ sfr_build_kernel(SfrArgs a) {
         const int c_lo = max(g.fc0, g.pc0) - g.org_c, c_hi = min(g.fc0 + g.ncols, g.pc1) - g.org_c;     // buffer columns
         const int c_lo_al = c_lo / per16 * per16, c_hi_al = min((c_hi + per16 - 1) / per16 * per16, a.pitch);
         const int n_rows = rhi - rlo, seg = c_hi_al - c_lo_al;
-        if (n_rows > 0 && seg > 0 && c_lo >= 0 && n_rows * seg * kElem <= kStageBytes) {
-            staged = true; st_rlo = rlo; st_c0 = c_lo_al; st_pitch = seg;
+        // staged rows start on 128-byte boundaries: no two bulk copies ever write the same shared-memory line
+        const int stride = (seg * kElem + 127) / 128 * 128;
+        if (n_rows > 0 && seg > 0 && c_lo >= 0 && n_rows * stride <= kStageBytes) {
+            staged = true; st_rlo = rlo; st_c0 = c_lo_al; st_pitch = stride / kElem;
             if (tid < 32) {
                 const uint32_t seg_bytes = static_cast<uint32_t>(seg) * kElem;
                 if (tid == 0) sfr_mbar_expect_tx(&stage_bar, seg_bytes * static_cast<uint32_t>(n_rows));
                 __syncwarp();
                 for (int r = tid; r < n_rows; r += 32)
-                    sfr_bulk_g2s(stage_raw + static_cast<size_t>(r) * seg_bytes,
+                    sfr_bulk_g2s(stage_raw + static_cast<size_t>(r) * stride,
                                  frame_bytes + (static_cast<size_t>(rlo + r - g.org_r) * a.pitch + c_lo_al) * kElem,
                                  seg_bytes, &stage_bar);
             }
@@ -989,10 +991,6 @@ sfr_aug_kernel(SfrArgs a) {
 #define PWR_FETCH_GRID 32
 #endif
 constexpr int kFetchGrid = PWR_FETCH_GRID;      // CTAs of the copy kernel in total (NOT per SM), see below
-#ifndef PWR_FETCH_GRID_TMA
-#define PWR_FETCH_GRID_TMA 64
-#endif
-constexpr int kFetchGridTma = PWR_FETCH_GRID_TMA;  // one-warp CTAs of the bulk-TMA copy kernel
 constexpr int kFetchThreads = 256;
 constexpr int kFetchGroups = 4;              // CTAs per sample
 constexpr int kFetchUnroll = 4;              // 16-byte loads in flight per thread
@@ -1059,7 +1057,10 @@ sfr_fetch_plan_kernel(FetchArgs a) {
 // CTA per item (16 384 CTAs) or even ONE CTA on each of the 148 SMs delayed the concurrent SFR build from 0.51 to
 // 6.1 ms (the whole transfer) -> 7.6 ms per step; 32 CTAs confine the damage to 32 SMs -> SFR build 0.63 ms, step
 // 6.07 ms = the transfer itself (grid 8 / 16 / 32 / 64: 7.27 / 6.17 / 6.07 / 6.08 ms per step).  The bulk-TMA
-// decoder kernels never were affected (their loads do not go through the LSU).
+// decoder kernels never were affected (their loads do not go through the LSU).  A bulk-TMA form of this copy (rows
+// host -> shared -> HBM with cp.async.bulk both ways, one row per lane in flight; tools/pcie_probe.cu keeps it) was
+// built and measured: the same 40-45 GB/s - the PCIe rate follows the fragment size, not who issues the reads - and
+// 6.27 ms per step; it was removed again rather than shipped as a slower option.
 __global__ void __launch_bounds__(kFetchThreads)
 sfr_fetch_copy_kernel(FetchArgs a) {
     const int per16 = 16 / a.elem;
@@ -1091,45 +1092,6 @@ sfr_fetch_copy_kernel(FetchArgs a) {
             }
         }
     }
-}
-
-// copy, bulk-TMA form (dispatch option PWR_OPT_FETCH_TMA, off by default): one warp per CTA; every lane moves one
-// window row at a time host -> shared memory -> HBM with cp.async.bulk in both directions (a 32-slot ring, one
-// mbarrier per lane).  Measured (r2): on 490-byte row fragments it matches the load/store form run on the whole GPU
-// (45 GB/s; tools/pcie_probe.cu) from 32-64 warps in total; on the 350-byte fragments of the prefiltered NYU
-// windows it reaches 40.2 GB/s against 42.2 for the 32-CTA load/store kernel, 6.27 vs 6.07 ms per e2e step - the
-// PCIe rate is set by the fragment size (a whole-frame cudaMemcpy reaches 55.6 GB/s), not by who issues the reads.
-__global__ void __launch_bounds__(32)
-sfr_fetch_copy_tma_kernel(FetchArgs a) {
-    extern __shared__ __align__(128) unsigned char fetch_ring[];          // [32][win_w * elem]
-    __shared__ __align__(8) uint64_t bars[32];
-    const int lane = threadIdx.x;
-    const uint32_t slot_bytes = static_cast<uint32_t>(a.win_w) * a.elem;
-    unsigned char* slot = fetch_ring + static_cast<size_t>(lane) * slot_bytes;
-    sfr_mbar_init(&bars[lane], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-    uint32_t parity = 0;
-    const size_t src_pitch = static_cast<size_t>(a.Wf) * a.elem, dst_pitch = static_cast<size_t>(a.win_w) * a.elem;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        const WinExtent e = a.extent[b];
-        const uint32_t bytes = static_cast<uint32_t>(e.cols) * a.elem;
-        if (bytes == 0) continue;
-        const unsigned char* src = static_cast<const unsigned char*>(a.frames) +
-                                   (static_cast<size_t>(b) * a.Hf * a.Wf + static_cast<size_t>(e.row0) * a.Wf + e.col0) * a.elem;
-        unsigned char* dst = static_cast<unsigned char*>(a.windows) + static_cast<size_t>(b) * a.win_h * a.win_w * a.elem;
-        for (int r = lane; r < e.rows; r += 32) {
-            sfr_mbar_expect_tx(&bars[lane], bytes);
-            sfr_bulk_g2s(slot, src + r * src_pitch, bytes, &bars[lane]);
-            sfr_mbar_wait(&bars[lane], parity);
-            parity ^= 1;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + r * dst_pitch),
-                         "r"(sfr_smem_u32(slot)), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the slot may be overwritten
-        }
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -1431,18 +1393,6 @@ extern "C" int pwr_sfr_fetch(const void* frames, int frame_format, int Hf, int W
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     sfr_fetch_plan_kernel<<<(B + 127) / 128, 128, 0, s>>>(a);
     if (int rc = launch_status()) return rc;
-    const size_t ring_bytes = static_cast<size_t>(32) * win_w * elem;
-    if (ring_bytes <= 160 * 1024 && get_option(PWR_OPT_FETCH_TMA) != 0) {
-        const int dev = current_device();
-        static std::atomic<int> ring_max[64];                  // largest dynamic-smem opt-in made so far, per device
-        if (static_cast<int>(ring_bytes) > ring_max[dev & 63].load(std::memory_order_relaxed)) {
-            cudaFuncSetAttribute(sfr_fetch_copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring_bytes));
-            ring_max[dev & 63].store(static_cast<int>(ring_bytes), std::memory_order_relaxed);
-        }
-        const int grid = B < kFetchGridTma ? B : kFetchGridTma;
-        sfr_fetch_copy_tma_kernel<<<grid, 32, ring_bytes, s>>>(a);
-        return launch_status();
-    }
     const long long items = static_cast<long long>(B) * kFetchGroups;
     const long long cap = kFetchGrid;
     sfr_fetch_copy_kernel<<<static_cast<unsigned>(items < cap ? items : cap), kFetchThreads, 0, s>>>(a);

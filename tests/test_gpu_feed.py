@@ -44,14 +44,10 @@ def test_window_mode_is_bit_identical_to_whole_frames(shape_name, fmt, prefilter
     cube = torch.from_numpy(d["cube"]).to(DEV)
     src = frames.pin_memory() if where == "pinned" else frames.to(DEV)
     fw = sfr.fetch_windows(src, com, cube, **kw)                # 16-byte loads / stores (default)
-    with _lib.option("fetch_tma", 1):                           # the bulk-TMA form must fetch exactly the same
-        fw_ldg = sfr.fetch_windows(src, com, cube, **kw)
     torch.cuda.synchronize()
-    assert torch.equal(fw.extent, fw_ldg.extent) and int(fw.fetched_bytes) == int(fw_ldg.fetched_bytes)
     ext0 = fw.extent.cpu().numpy()
-    for bi in range(B):
+    for bi in range(B):                                          # every window holds exactly its region of the frame
         r, c = int(ext0[bi, 2]), int(ext0[bi, 3])
-        assert torch.equal(fw.windows[bi, :r, :c], fw_ldg.windows[bi, :r, :c]), bi
         if r and c:
             r0, c0 = int(ext0[bi, 0]), int(ext0[bi, 1])
             assert torch.equal(fw.windows[bi, :r, :c].cpu(), frames[bi, r0:r0 + r, c0:c0 + c])

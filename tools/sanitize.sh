@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over the one-pass last-stage kernel (all 12 instantiations, ~7 items per CTA so every
 # ring slot is re-used; also as the inner-stage forward), the six-slot backward, the compact-target comparison,
-# fetch (load/store and bulk-TMA forms) + window mode, the raw-frame window table, the optional staged SFR
+# fetch + window mode, the raw-frame window table, the optional staged SFR
 # builder, the bb loader and smoke().
 #   gpurun --timeout 1500 -- 'bash tools/sanitize.sh r2'
 # Logs land in gpurun_out/<tag>_sanitizer_<tool>.log; copy the summaries into profiles/.

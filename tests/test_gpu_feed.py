@@ -186,3 +186,31 @@ def test_select_valid_drops_what_the_reference_raises_on():
     assert kept.img.shape[0] == 3 and kept.heatmaps.shape[0] == 3 and bool(kept.valid.all())
     assert torch.equal(kept.img[1], batch.img[2])
     assert sfr.select_valid(kept) is kept
+
+
+def test_host_feed_test_only_and_augmented_modes():
+    """HostFeed in the two other modes of process_single_data: the 6-tuple of test frames (HAND17, raw 16-bit grey
+    samples) and augmented training batches (per-submit draws; the fetch covers the shifted crop and its fallback)."""
+    shape = synth.HAND17
+    B = 10
+    d = synth.make_frames(shape, B, seed=61)
+    raw = torch.from_numpy(raw_of(d["frames"])).pin_memory()
+    kw = dict(frame_format="u16", prefilter=(40.0, shape.halfu, shape.halfv))
+    hf = feed.HostFeed(shape, B, test_only=True, **kw)
+    got = hf.build(hf.submit(raw, d["com"], d["cube"]))
+    ref = sfr.build_sfr(raw.to(DEV), d["com"], d["cube"], fx=shape.fx, fy=shape.fy, test_only=True, **kw)
+    torch.cuda.synchronize()
+    same(got, ref, "test-only feed")
+    assert isinstance(got, sfr.SFRTestBatch)
+    # augmented NYU batches, float32 frames: two submits with different draws through the same slots
+    shape = synth.NYU
+    d = synth.make_frames(shape, B, seed=62)
+    frames = torch.from_numpy(d["frames"]).pin_memory()
+    hf = feed.HostFeed(shape, B, augment=True, depth=1)
+    for seed in (1, 2):
+        aug = sfr.draw_augmentation(B, np.random.default_rng(seed))
+        got = hf.build(hf.submit(frames, d["com"], d["cube"], d["uvd"], augment=aug))
+        ref = sfr.build_sfr(frames.to(DEV), d["com"], d["cube"], d["uvd"], fx=shape.fx, fy=shape.fy, augment=aug)
+        torch.cuda.synchronize()
+        same(got, ref, "augmented feed, draw %d" % seed)
+        hf.fetched_bytes(0 if seed == 1 else 1)            # raises if a region did not fit its window

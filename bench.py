@@ -267,6 +267,7 @@ def run_b200(args):
     B, J = args.batch, shape.joints
     alpha, lambda_h, lambda_d = args.alpha, 1.0, 0.01
     peak, peak_src = measured_peak()
+    errors = {}                    # extras that failed (the main line is printed regardless)
 
     # ---- synthetic inputs, resident in HBM (seed = rank: every rank owns different samples) ----
     d = synth.make_frames_device(shape, B, seed=rank, device=dev)
@@ -417,47 +418,6 @@ def run_b200(args):
                 "step_roofline_frac": sample_bytes * B / (ms_v * 1e-3) / 1e9 / peak,
                 "kernels": kernel_table(prof_v, bytes_table), "note": note}
 
-    two_kernel = sparse = raw_step = no_heat = None
-    if not args.no_sparse:
-        # (1) SURVEY 8d's own accounting: forward kernel, then backward+loss kernel (the logits are read twice)
-        two_kernel = timed_variant(
-            frames, None, False,
-            {"pwr_sfr_build": roofline.sfr_build_bytes(J), "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J),
-             "pwr_decoder_bwd_loss": roofline.decoder_bwd_bytes(J)}, roofline.step_bytes(J),
-            "SURVEY 8d accounting: pwr_decoder_fwd then pwr_decoder_bwd_loss (ops.ONE_PASS_LAST_STAGE = False), "
-            "622 780 + 721 120 + 1 409 024 B/sample", "two")
-        # (2) compact targets: the SFR builder emits 64 B of taps per joint instead of two dense maps and the
-        # loss kernel evaluates the heat-map / depth-map targets on the fly
-        sparse = timed_variant(
-            frames, dict(sfr_kw, targets="sparse"), True,
-            {"pwr_sfr_build": roofline.sfr_build_sparse_bytes(J),
-             "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, sparse=True)},
-            roofline.step_one_pass_bytes(J, sparse=True),
-            "same step, same results; targets handed to the loss kernel as 64-byte taps per joint instead of two "
-            "dense 16 KiB maps (sfr.build_sfr(targets='sparse'))", "sparse")
-        # (2b) the last stage exactly as PixelwiseRegression.forward_loss runs it: nothing but the loss consumes its heat
-        # maps, so they are not stored (6J + 2 maps instead of 7J + 2)
-        store_heat["on"] = False
-        try:
-            no_heat = timed_variant(
-                frames, None, True,
-                {"pwr_sfr_build": roofline.sfr_build_bytes(J),
-                 "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, store_heat=False)},
-                roofline.sfr_build_bytes(J) + roofline.decoder_fused_bytes(J, store_heat=False),
-                "same step without the heat-map store of the last stage (store_heat=False, what model.forward_loss "
-                "does: train.py:192-207 only feeds the last stage's heat maps to the loss)", "noheat")
-        finally:
-            store_heat["on"] = True
-        # (3) the step fed with the raw 16-bit sensor frames (half the source bytes; PNG decode + hand rectangle of
-        # load_from_text inside the SFR kernel), dense targets, against SURVEY 8d's bytes
-        if raw_frames is not None and args.frame_format == "f32" and not args.augment:
-            raw_step = timed_variant(
-                raw_frames, raw_kw, True,
-                {"pwr_sfr_build": roofline.sfr_build_bytes(J), "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J)},
-                roofline.step_one_pass_bytes(J),
-                "same step on raw uint16 %s frames resident in HBM, decoded inside the SFR kernel with the "
-                "load_from_text hand rectangle (SURVEY 8f-1)" % raw_fmt, "raw")
-
     # ---- the kernels of an INNER stage (north_star's training is 2 stages, model.py:200-210): forward with the
     # loss riding along, and the backward with dense upstream gradients on the heat maps and depth maps ----
     def time_launch(fn, iters):
@@ -477,112 +437,165 @@ def run_b200(args):
         return {"avg_ms": ms, "algorithmic_bytes_per_sample": bytes_per_sample, "achieved_gbs": gbs, "frac": gbs / peak,
                 "what": what}
 
+    two_kernel = sparse = raw_step = no_heat = None
+    try:
+        if not args.no_sparse:
+            # (1) SURVEY 8d's own accounting: forward kernel, then backward+loss kernel (the logits are read twice)
+            two_kernel = timed_variant(
+                frames, None, False,
+                {"pwr_sfr_build": roofline.sfr_build_bytes(J), "pwr_decoder_fwd": roofline.decoder_fwd_bytes(J),
+                 "pwr_decoder_bwd_loss": roofline.decoder_bwd_bytes(J)}, roofline.step_bytes(J),
+                "SURVEY 8d accounting: pwr_decoder_fwd then pwr_decoder_bwd_loss (ops.ONE_PASS_LAST_STAGE = False), "
+                "622 780 + 721 120 + 1 409 024 B/sample", "two")
+            # (2) compact targets: the SFR builder emits 64 B of taps per joint instead of two dense maps and the
+            # loss kernel evaluates the heat-map / depth-map targets on the fly
+            sparse = timed_variant(
+                frames, dict(sfr_kw, targets="sparse"), True,
+                {"pwr_sfr_build": roofline.sfr_build_sparse_bytes(J),
+                 "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, sparse=True)},
+                roofline.step_one_pass_bytes(J, sparse=True),
+                "same step, same results; targets handed to the loss kernel as 64-byte taps per joint instead of two "
+                "dense 16 KiB maps (sfr.build_sfr(targets='sparse'))", "sparse")
+            # (2b) the last stage exactly as PixelwiseRegression.forward_loss runs it: nothing but the loss consumes its heat
+            # maps, so they are not stored (6J + 2 maps instead of 7J + 2)
+            store_heat["on"] = False
+            try:
+                no_heat = timed_variant(
+                    frames, None, True,
+                    {"pwr_sfr_build": roofline.sfr_build_bytes(J),
+                     "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, store_heat=False)},
+                    roofline.sfr_build_bytes(J) + roofline.decoder_fused_bytes(J, store_heat=False),
+                    "same step without the heat-map store of the last stage (store_heat=False, what model.forward_loss "
+                    "does: train.py:192-207 only feeds the last stage's heat maps to the loss)", "noheat")
+            finally:
+                store_heat["on"] = True
+            # (3) the step fed with the raw 16-bit sensor frames (half the source bytes; PNG decode + hand rectangle of
+            # load_from_text inside the SFR kernel), dense targets, against SURVEY 8d's bytes
+            if raw_frames is not None and args.frame_format == "f32" and not args.augment:
+                raw_step = timed_variant(
+                    raw_frames, raw_kw, True,
+                    {"pwr_sfr_build": roofline.sfr_build_bytes(J), "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J)},
+                    roofline.step_one_pass_bytes(J),
+                    "same step on raw uint16 %s frames resident in HBM, decoded inside the SFR kernel with the "
+                    "load_from_text hand rectangle (SURVEY 8f-1)" % raw_fmt, "raw")
+
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['variants'] = repr(exc)
+        sys.stderr.write("bench.py: variants failed: %r\n" % (exc,))
     # ---- the same step captured once and replayed as a CUDA graph: the library never allocates or synchronises, so
     # SFR build + one-pass last stage + loss / dL/dw reduction + the (unit) upstream scale replay with ~10 us of host
     # work per step; `host_issue_ms_per_step` above is the price of issuing the same launches from Python ----
     graph_step = None
-    if not args.no_extras:
-        ones = torch.ones((), device=dev)
-        g_arena = sfr.SfrArena()
-        zd, Dd, wd = z.detach(), D.detach(), w.detach()
+    try:
+        if not args.no_extras:
+            ones = torch.ones((), device=dev)
+            g_arena = sfr.SfrArena()
+            zd, Dd, wd = z.detach(), D.detach(), w.detach()
 
-        def graph_body():
-            bt = sfr.build_sfr(frames, com, cube, uvd, arena=g_arena, **sfr_kw)
-            H, uvd_o, gz, gD, gwp, lp = ops.decoder_fused_raw(zd, wd, Dd, bt.label_img, bt.mask,
-                                                             (bt.heatmaps, bt.depthmaps, bt.uvd), "softmax", alpha,
-                                                             lambda_h, lambda_d)
-            out4, gw = ops.stage_loss(lp, lambda_h, lambda_d, alpha, 0, gwp)
-            ops.scale_inplace_(gz, ones, gD, gw)
-            return out4, gw, uvd_o, gz, gD
+            def graph_body():
+                bt = sfr.build_sfr(frames, com, cube, uvd, arena=g_arena, **sfr_kw)
+                H, uvd_o, gz, gD, gwp, lp = ops.decoder_fused_raw(zd, wd, Dd, bt.label_img, bt.mask,
+                                                                 (bt.heatmaps, bt.depthmaps, bt.uvd), "softmax", alpha,
+                                                                 lambda_h, lambda_d)
+                out4, gw = ops.stage_loss(lp, lambda_h, lambda_d, alpha, 0, gwp)
+                ops.scale_inplace_(gz, ones, gD, gw)
+                return out4, gw, uvd_o, gz, gD
 
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            graph_body()
-        torch.cuda.current_stream().wait_stream(side)
-        cuda_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cuda_graph):
-            g_out = graph_body()
-        for _ in range(3):
-            cuda_graph.replay()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        t_h = time.perf_counter()
-        for _ in range(args.steps):
-            cuda_graph.replay()
-        host_ms = (time.perf_counter() - t_h) * 1e3 / args.steps
-        s1.record()
-        barrier()
-        ms_g = max_over_ranks(s0.elapsed_time(s1)) / args.steps
-        # calls without per-kernel profiling events, for the plain host-issue figure
-        for _ in range(3):
-            step(frames, com, cube, uvd, z, D)
-        barrier()
-        t_h = time.perf_counter()
-        for _ in range(args.steps):
-            step(frames, com, cube, uvd, z, D)
-        host_calls_ms = (time.perf_counter() - t_h) * 1e3 / args.steps
-        barrier()
-        graph_step = {"value": B * world / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
-                      "host_issue_ms_per_step": host_ms, "host_issue_ms_per_step_calls": host_calls_ms,
-                      "loss": float(g_out[0][3]),
-                      "note": "sfr.build_sfr(arena=) -> ops.decoder_fused_raw -> ops.stage_loss(+ dL/dw) -> ops.scale_inplace_ "
-                              "captured once with torch.cuda.graph and replayed; `host_issue_ms_per_step_calls` = the autograd "
-                              "step of the main region issued call by call with the per-kernel profiling events off"}
-        del cuda_graph, g_out, g_arena
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph_body()
+            torch.cuda.current_stream().wait_stream(side)
+            cuda_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cuda_graph):
+                g_out = graph_body()
+            for _ in range(3):
+                cuda_graph.replay()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            t_h = time.perf_counter()
+            for _ in range(args.steps):
+                cuda_graph.replay()
+            host_ms = (time.perf_counter() - t_h) * 1e3 / args.steps
+            s1.record()
+            barrier()
+            ms_g = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+            # calls without per-kernel profiling events, for the plain host-issue figure
+            for _ in range(3):
+                step(frames, com, cube, uvd, z, D)
+            barrier()
+            t_h = time.perf_counter()
+            for _ in range(args.steps):
+                step(frames, com, cube, uvd, z, D)
+            host_calls_ms = (time.perf_counter() - t_h) * 1e3 / args.steps
+            barrier()
+            graph_step = {"value": B * world / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                          "host_issue_ms_per_step": host_ms, "host_issue_ms_per_step_calls": host_calls_ms,
+                          "loss": float(g_out[0][3]),
+                          "note": "sfr.build_sfr(arena=) -> ops.decoder_fused_raw -> ops.stage_loss(+ dL/dw) -> ops.scale_inplace_ "
+                                  "captured once with torch.cuda.graph and replayed; `host_issue_ms_per_step_calls` = the autograd "
+                                  "step of the main region issued call by call with the per-kernel profiling events off"}
+            del cuda_graph, g_out, g_arena
 
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['graph_step'] = repr(exc)
+        sys.stderr.write("bench.py: graph_step failed: %r\n" % (exc,))
     inner = two_stage = None
-    if not args.no_extras:
-        sampler.section("inner_stage")
-        batch = sfr.build_sfr(frames, com, cube, uvd, **sfr_kw)
-        zd, Dd, wd = z.detach(), D.detach(), w.detach()
-        dense_t = (batch.heatmaps, batch.depthmaps, batch.uvd)
-        gH_up = torch.randn(B, J, 64, 64, device=dev, generator=g) * 1e-4
-        gD_up = torch.randn(B, J, 64, 64, device=dev, generator=g) * 1e-4
-        g_uvd = torch.randn(B, J, 3, device=dev, generator=g) * 1e-3
-        one = torch.ones((), device=dev)
-        it = max(10, args.steps // 2)
-        _, uvd_f, stats_f, _ = ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t)
-        ms_fwd = time_launch(lambda: ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t), it)
-        ms_bwd_a1 = time_launch(lambda: ops.decoder_backward_raw(
-            zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, g_uvd, gH_up, gD_up, targets=dense_t, alpha=1.0,
-            loss_scale_dev=one), it)
-        ms_bwd_a05 = time_launch(lambda: ops.decoder_backward_raw(
-            zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, g_uvd, gH_up, gD_up, targets=dense_t, alpha=0.5,
-            loss_scale_dev=one), it)
-        inner = {
-            "pwr_decoder_fwd+loss": entry(ms_fwd, roofline.decoder_fwd_bytes(J, with_targets=True),
-                                          "inner-stage forward, H stored, loss value from dense targets (decoder_fwd_kernel)"),
-            "pwr_decoder_bwd_loss alpha=1": entry(ms_bwd_a1, roofline.decoder_bwd_bytes(J, with_targets=False, upstream_maps=True),
-                                                  "inner-stage backward, dense gH_up / gD_up, map targets carry no weight "
-                                                  "and are not read (train.py default alpha = 1): 6J + 2 maps"),
-            "pwr_decoder_bwd_loss alpha=0.5": entry(ms_bwd_a05, roofline.decoder_bwd_bytes(J, with_targets=True, upstream_maps=True),
-                                                    "inner-stage backward, dense targets AND dense gH_up / gD_up: SURVEY 8d's "
-                                                    "131 072 J + 32 768 B (six-slot pipelined kernel)"),
-            "clocks": sampler.end_section("inner_stage"),
-        }
-        # the decoder work of one 2-stage training step, in forward_loss's order (model.py:200-210, train.py:192-207):
-        # stage-0 forward+loss, last stage in one pass, stage-0 backward with the dense gradients the next stage's
-        # conv would hand back (synthetic here: the conv backbone is out of scope)
-        sampler.section("two_stage_decoder")
+    try:
+        if not args.no_extras:
+            sampler.section("inner_stage")
+            batch = sfr.build_sfr(frames, com, cube, uvd, **sfr_kw)
+            zd, Dd, wd = z.detach(), D.detach(), w.detach()
+            dense_t = (batch.heatmaps, batch.depthmaps, batch.uvd)
+            gH_up = torch.randn(B, J, 64, 64, device=dev, generator=g) * 1e-4
+            gD_up = torch.randn(B, J, 64, 64, device=dev, generator=g) * 1e-4
+            g_uvd = torch.randn(B, J, 3, device=dev, generator=g) * 1e-3
+            one = torch.ones((), device=dev)
+            it = max(10, args.steps // 2)
+            _, uvd_f, stats_f, _ = ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t)
+            ms_fwd = time_launch(lambda: ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t), it)
+            ms_bwd_a1 = time_launch(lambda: ops.decoder_backward_raw(
+                zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, g_uvd, gH_up, gD_up, targets=dense_t, alpha=1.0,
+                loss_scale_dev=one), it)
+            ms_bwd_a05 = time_launch(lambda: ops.decoder_backward_raw(
+                zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, g_uvd, gH_up, gD_up, targets=dense_t, alpha=0.5,
+                loss_scale_dev=one), it)
+            inner = {
+                "pwr_decoder_fwd+loss": entry(ms_fwd, roofline.decoder_fwd_bytes(J, with_targets=True),
+                                              "inner-stage forward, H stored, loss value from dense targets (decoder_fwd_kernel)"),
+                "pwr_decoder_bwd_loss alpha=1": entry(ms_bwd_a1, roofline.decoder_bwd_bytes(J, with_targets=False, upstream_maps=True),
+                                                      "inner-stage backward, dense gH_up / gD_up, map targets carry no weight "
+                                                      "and are not read (train.py default alpha = 1): 6J + 2 maps"),
+                "pwr_decoder_bwd_loss alpha=0.5": entry(ms_bwd_a05, roofline.decoder_bwd_bytes(J, with_targets=True, upstream_maps=True),
+                                                        "inner-stage backward, dense targets AND dense gH_up / gD_up: SURVEY 8d's "
+                                                        "131 072 J + 32 768 B (six-slot pipelined kernel)"),
+                "clocks": sampler.end_section("inner_stage"),
+            }
+            # the decoder work of one 2-stage training step, in forward_loss's order (model.py:200-210, train.py:192-207):
+            # stage-0 forward+loss, last stage in one pass, stage-0 backward with the dense gradients the next stage's
+            # conv would hand back (synthetic here: the conv backbone is out of scope)
+            sampler.section("two_stage_decoder")
 
-        def two_stage_pass():
-            ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t)
-            ops.decoder_fused_raw(zd, wd, Dd, batch.label_img, batch.mask, dense_t, "softmax", alpha, store_heat=False)
-            ops.decoder_backward_raw(zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, None, gH_up, gD_up,
-                                     targets=dense_t, alpha=alpha, loss_scale_dev=one)
+            def two_stage_pass():
+                ops.decoder_forward_raw(zd, wd, Dd, batch.label_img, batch.mask, targets=dense_t)
+                ops.decoder_fused_raw(zd, wd, Dd, batch.label_img, batch.mask, dense_t, "softmax", alpha, store_heat=False)
+                ops.decoder_backward_raw(zd, wd, Dd, batch.label_img, batch.mask, stats_f, uvd_f, None, gH_up, gD_up,
+                                         targets=dense_t, alpha=alpha, loss_scale_dev=one)
 
-        ms_two = time_launch(two_stage_pass, it)
-        bytes_two = (roofline.decoder_fwd_bytes(J, with_targets=True) + roofline.decoder_fused_bytes(J, store_heat=False) +
-                     roofline.decoder_bwd_bytes(J, with_targets=(alpha != 1.0), upstream_maps=True))
-        two_stage = entry(ms_two, bytes_two, "decoder kernels of a 2-stage training step at alpha = %g: stage-0 forward+loss, "
-                          "last stage in one pass (no H store), stage-0 backward with dense upstream maps" % alpha)
-        two_stage["samples_per_s"] = B * world / (ms_two * 1e-3)
-        two_stage["clocks"] = sampler.end_section("two_stage_decoder")
-        del batch, gH_up, gD_up, stats_f, uvd_f
-        torch.cuda.empty_cache()
+            ms_two = time_launch(two_stage_pass, it)
+            bytes_two = (roofline.decoder_fwd_bytes(J, with_targets=True) + roofline.decoder_fused_bytes(J, store_heat=False) +
+                         roofline.decoder_bwd_bytes(J, with_targets=(alpha != 1.0), upstream_maps=True))
+            two_stage = entry(ms_two, bytes_two, "decoder kernels of a 2-stage training step at alpha = %g: stage-0 forward+loss, "
+                              "last stage in one pass (no H store), stage-0 backward with dense upstream maps" % alpha)
+            two_stage["samples_per_s"] = B * world / (ms_two * 1e-3)
+            two_stage["clocks"] = sampler.end_section("two_stage_decoder")
+            del batch, gH_up, gD_up, stats_f, uvd_f
+            torch.cuda.empty_cache()
 
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['inner_stage'] = repr(exc)
+        sys.stderr.write("bench.py: inner_stage failed: %r\n" % (exc,))
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region ----
     def run_e2e():
         """Public feed API: raw uint16 frames + annotations live in pinned host memory; every step the annotations are
@@ -693,70 +706,86 @@ def run_b200(args):
                         "from pinned host memory every step (no overlap, no windows)" % args.frame_format}
 
     e2e = e2e_r1 = None
-    if not args.no_e2e:
-        sampler.section("e2e")
-        e2e = run_e2e()
-        e2e["clocks"] = sampler.end_section("e2e")
-        if not args.no_extras:
-            e2e_r1 = run_e2e_whole_frames()
+    try:
+        if not args.no_e2e:
+            sampler.section("e2e")
+            e2e = run_e2e()
+            e2e["clocks"] = sampler.end_section("e2e")
+            if not args.no_extras:
+                e2e_r1 = run_e2e_whole_frames()
 
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['e2e'] = repr(exc)
+        sys.stderr.write("bench.py: e2e failed: %r\n" % (exc,))
     # ---- GPU baseline of configs[1] ("vs reference PyTorch path"): the reference's decoder + loss
     # lines as plain eager PyTorch ops on the same GPU and inputs (the SFR builder has no GPU
     # reference: upstream it is CPU-only) ----
     gpu_eager = None
-    if rank == 0 and world == 1 and not args.no_gpu_eager:
-        batch = sfr.build_sfr(frames, com, cube, uvd, **sfr_kw)
-        gpu_eager = eager_decoder_baseline(z, D, w, batch, alpha, lambda_h, lambda_d)
-        gpu_eager["fused_ms"] = sum(v["avg_ms"] for k_, v in kernels.items() if k_.startswith("pwr_decoder"))
-        gpu_eager["speedup"] = gpu_eager["ms"] / gpu_eager["fused_ms"]
-        del batch
-        torch.cuda.empty_cache()
+    try:
+        if rank == 0 and world == 1 and not args.no_gpu_eager:
+            batch = sfr.build_sfr(frames, com, cube, uvd, **sfr_kw)
+            gpu_eager = eager_decoder_baseline(z, D, w, batch, alpha, lambda_h, lambda_d)
+            gpu_eager["fused_ms"] = sum(v["avg_ms"] for k_, v in kernels.items() if k_.startswith("pwr_decoder"))
+            gpu_eager["speedup"] = gpu_eager["ms"] / gpu_eager["fused_ms"]
+            del batch
+            torch.cuda.empty_cache()
 
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['gpu_eager_decoder'] = repr(exc)
+        sys.stderr.write("bench.py: gpu_eager_decoder failed: %r\n" % (exc,))
     # ---- the records of BASELINE configs[2], [3], [4] ----
     train_step = train_msra = sweep = None
-    if not args.no_extras:
-        del frames, raw_frames, z, D, d
-        arenas.clear()
-        torch.cuda.empty_cache()
-        from examples import train_synthetic as ts
-        from tools import sweep_inference
-        # configs[2]: NYU-shape end-to-end training step (train.py:158-208), batch 128 per GPU, DDP over NCCL when
-        # N > 1; the same step with the decoder + loss as the reference writes them (eager), with the drop-in
-        # model (fused decoder kernels, reference loss lines), and with the fused criterion
-        sampler.section("train_step")
-        train_step = {"config": "configs[2]: NYU shape (J=14), batch 128 per GPU, 2 stages, features 128, level 4, "
-                                "InstanceNorm, AdamW; on-GPU SFR build + cuDNN backbone + decoder + loss; DDP over NCCL "
-                                "when n_gpus > 1", "n_gpus": world, "batch_per_gpu": 128}
-        for mode in ("eager", "dropin", "fused"):
-            train_step[mode] = ts.run_training(synth.NYU, 128, args.train_steps, 3, mode, world=world, rank=rank,
-                                               local=local_rank)
-        train_step["speedup_fused_over_eager"] = train_step["eager"]["ms_per_step"] / train_step["fused"]["ms_per_step"]
-        train_step["clocks"] = sampler.end_section("train_step")
-        # configs[3]: MSRA shape (J = 21, 240x320 float64-semantics frames, centre-of-mass fallback, cube 125)
-        sampler.section("train_msra")
-        train_msra = {"config": "configs[3]: MSRA shape (J=21, float64 frame semantics, CoM from the frame), batch 128 per "
-                                "GPU, fused criterion, DDP over NCCL when n_gpus > 1", "n_gpus": world, "batch_per_gpu": 128}
-        train_msra["fused"] = ts.run_training(synth.MSRA, 128, args.train_steps, 3, "fused", world=world, rank=rank,
-                                              local=local_rank)
-        train_msra["clocks"] = sampler.end_section("train_msra")
-        # configs[4]: HAND17-shape inference sweep (test.py:93-124 around the backbone), every rank its own replica
-        sampler.section("sweep")
-        rows = sweep_inference.sweep(synth.HAND17, [int(b) for b in args.sweep_batches.split(",")], 10, 3, world, rank,
-                                     local_rank, peak)
-        sweep = {"config": "configs[4]: HAND17 shape (J=21), test-only SFR + decoder forward without the heat-map store + "
-                           "recover_uvd, per-replica batch swept, %d independent replica(s)" % world,
-                 "rows": [{k: r[k] for k in ("batch_per_gpu", "ms_calls", "ms_graph", "samples_per_s_calls",
-                                             "samples_per_s_graph", "roofline_frac_calls", "roofline_frac_graph",
-                                             "graph_equals_calls")} for r in rows],
-                 "clocks": sampler.end_section("sweep")}
+    try:
+        if not args.no_extras:
+            del frames, raw_frames, z, D, d
+            arenas.clear()
+            torch.cuda.empty_cache()
+            from examples import train_synthetic as ts
+            from tools import sweep_inference
+            # configs[2]: NYU-shape end-to-end training step (train.py:158-208), batch 128 per GPU, DDP over NCCL when
+            # N > 1; the same step with the decoder + loss as the reference writes them (eager), with the drop-in
+            # model (fused decoder kernels, reference loss lines), and with the fused criterion
+            sampler.section("train_step")
+            train_step = {"config": "configs[2]: NYU shape (J=14), batch 128 per GPU, 2 stages, features 128, level 4, "
+                                    "InstanceNorm, AdamW; on-GPU SFR build + cuDNN backbone + decoder + loss; DDP over NCCL "
+                                    "when n_gpus > 1", "n_gpus": world, "batch_per_gpu": 128}
+            for mode in ("eager", "dropin", "fused"):
+                train_step[mode] = ts.run_training(synth.NYU, 128, args.train_steps, 3, mode, world=world, rank=rank,
+                                                   local=local_rank)
+            train_step["speedup_fused_over_eager"] = train_step["eager"]["ms_per_step"] / train_step["fused"]["ms_per_step"]
+            train_step["clocks"] = sampler.end_section("train_step")
+            # configs[3]: MSRA shape (J = 21, 240x320 float64-semantics frames, centre-of-mass fallback, cube 125)
+            sampler.section("train_msra")
+            train_msra = {"config": "configs[3]: MSRA shape (J=21, float64 frame semantics, CoM from the frame), batch 128 per "
+                                    "GPU, fused criterion, DDP over NCCL when n_gpus > 1", "n_gpus": world, "batch_per_gpu": 128}
+            train_msra["fused"] = ts.run_training(synth.MSRA, 128, args.train_steps, 3, "fused", world=world, rank=rank,
+                                                  local=local_rank)
+            train_msra["clocks"] = sampler.end_section("train_msra")
+            # configs[4]: HAND17-shape inference sweep (test.py:93-124 around the backbone), every rank its own replica
+            sampler.section("sweep")
+            rows = sweep_inference.sweep(synth.HAND17, [int(b) for b in args.sweep_batches.split(",")], 10, 3, world, rank,
+                                         local_rank, peak)
+            sweep = {"config": "configs[4]: HAND17 shape (J=21), test-only SFR + decoder forward without the heat-map store + "
+                               "recover_uvd, per-replica batch swept, %d independent replica(s)" % world,
+                     "rows": [{k: r[k] for k in ("batch_per_gpu", "ms_calls", "ms_graph", "samples_per_s_calls",
+                                                 "samples_per_s_graph", "roofline_frac_calls", "roofline_frac_graph",
+                                                 "graph_equals_calls")} for r in rows],
+                     "clocks": sampler.end_section("sweep")}
 
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['configs_2_3_4'] = repr(exc)
+        sys.stderr.write("bench.py: configs_2_3_4 failed: %r\n" % (exc,))
     # ---- CPU baseline: oracle port on the host cores (rank 0, N = 1 only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline
-        res = cpu_baseline.time_path(shape, args.cpu_samples, seed=0, repeats=2)
-        cpu = {"value": res["samples_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
-               "sample": res["sample"] + "; best of 2 passes"}
+    try:
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_baseline
+            res = cpu_baseline.time_path(shape, args.cpu_samples, seed=0, repeats=2)
+            cpu = {"value": res["samples_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                   "sample": res["sample"] + "; best of 2 passes"}
+    except Exception as exc:      # an extra must never cost the main JSON line
+        errors['cpu_baseline'] = repr(exc)
+        sys.stderr.write("bench.py: cpu_baseline failed: %r\n" % (exc,))
     sampler.stop()
 
     if rank == 0:
@@ -800,6 +829,7 @@ def run_b200(args):
             "between_kernels_ms_per_step": gap_ms,
             "cpu_baseline": cpu,
             "gpu_eager_decoder": gpu_eager,
+            "errors": errors or None,
         }
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(traffic_file):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PWR_VERSION 200          /* 0.2.0: bumped on every ABI change; the binding asserts it */
+#define PWR_VERSION 201          /* 0.2.0: bumped on every ABI change; the binding asserts it */
 
 #define PWR_LABEL_SIZE 64
 #define PWR_IMAGE_SIZE 128
@@ -72,7 +72,8 @@ const char* pwr_error_string(int rc);
 #define PWR_OPT_SFR_STAGED  4   /* 1: SFR build stages the source rows of a band in shared memory
                                       (bulk-TMA row copies) instead of gathering its taps from HBM;
                                       measured slower, kept for A/B runs     */
-#define PWR_OPT_COUNT       5
+#define PWR_OPT_FUSED_NO_LEAN 5 /* 1: two-CTA/SM one-pass kernel where the lean three-CTA/SM one would run */
+#define PWR_OPT_COUNT       6
 int pwr_set_option(int option, int value);
 
 /* ------------------------------------------------------------------------ *

@@ -49,8 +49,8 @@ SIGNATURES = {
     "pwr_joint_error": [_P, _P, _P, _P, _P, _D, _D, _D, _D, _P, _I, _I, _P],
 }
 
-ABI_VERSION = 200      # PWR_VERSION of include/pwr.h this binding is written against
-OPTIONS = {"bwd_direct": 0, "fwd_direct": 1, "fwd_pipe": 2, "bwd_no_lean": 3, "sfr_staged": 4}
+ABI_VERSION = 201      # PWR_VERSION of include/pwr.h this binding is written against
+OPTIONS = {"bwd_direct": 0, "fwd_direct": 1, "fwd_pipe": 2, "bwd_no_lean": 3, "sfr_staged": 4, "fused_no_lean": 5}
 _ENV_OPTIONS = {"PWR_BWD_DIRECT": ("bwd_direct", "1"), "PWR_FWD_DIRECT": ("fwd_direct", "1"),
                 "PWR_FWD_PIPE": ("fwd_pipe", "1"), "PWR_BWD_LEAN": ("bwd_no_lean", "0"),
                 "PWR_SFR_STAGED": ("sfr_staged", "1")}

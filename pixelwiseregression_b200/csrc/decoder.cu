@@ -1454,6 +1454,307 @@ decoder_fused_kernel(FusedArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// one-pass last stage, lean variant: no dense target map is visited (compact targets, or uvd-only loss)
+// ---------------------------------------------------------------------------
+// With compact targets an item moves only 32 KB in and up to 48 KB out, and decoder_fused_kernel stops being
+// bandwidth-bound: ncu r2 shows 632 M warp instructions issued at 2.1 per clock per SM from 16 resident warps,
+// barrier + short-scoreboard stalls on top, DRAM at 56 % (1.05 ms where the bytes need 0.74).  Its 118-128
+// registers (z, e, gp, L, m of 16 pixels per thread = 80 of them) pin it at two CTAs per SM.  Here the per-pixel
+// state between the phases lives in the ring instead of in registers: the forward pass only accumulates the
+// sums; the backward pass re-reads z, D from the item's slots, recomputes e (one more ex2 per pixel on an idle
+// XU pipe) and writes gp over z and p over D IN PLACE (every thread rewrites exactly the 16-byte chunks it has
+// just read); the dL/dz pass after the block sums reads them back.  L, m stay register-resident across the J
+// items of a sample.  That fits 80 registers -> three CTAs (24 warps) per SM, each with a ring of two (z, D)
+// pairs.  The slots of item k are therefore busy until its last pass; they are handed back to the producer
+// after the first block barrier of item k + 1 (every thread has executed fence.proxy.async after its last
+// generic access to them).  float32 maps only: half-precision logits are 8 KB per slot and cannot take the
+// float32 gp / p of the same pixels in place; those keep decoder_fused_kernel.
+#ifndef PWR_FL_THREADS
+#define PWR_FL_THREADS 256
+#endif
+#ifndef PWR_FL_CTAS
+#define PWR_FL_CTAS 3
+#endif
+#ifndef PWR_FL_PAIRS
+#define PWR_FL_PAIRS 2
+#endif
+#ifndef PWR_FL_FOLD
+#define PWR_FL_FOLD 0          // 1: extremum of item k + 1 rides on the backward barrier of item k (needs >= 3 pairs)
+#endif
+constexpr int kFLThreads = PWR_FL_THREADS;
+constexpr int kFLWarps = kFLThreads / 32;
+constexpr int kFLVec = kMap / 4 / kFLThreads;
+constexpr int kFLPairs = PWR_FL_PAIRS;
+constexpr int kFLCtasPerSm = PWR_FL_CTAS;
+constexpr bool kFLFold = PWR_FL_FOLD != 0;
+constexpr int kFLSmemBytes = kFLPairs * 2 * kSlotBytes + 64;
+static_assert(kFLWarps % 4 == 0 && kFLThreads >= 128, "per-warp partials are read as float4; 121 footprint threads");
+static_assert(kFLVec * 4 <= 32 && kFLVec >= 1, "one z > 0 bit per pixel of a thread");
+static_assert(kFLCtasPerSm * (kFLSmemBytes + 3072) <= 227 * 1024, "shared memory of the resident CTAs");
+static_assert(!kFLFold || kFLPairs >= 3, "the folded extremum reads item k + 1 while item k + 2 is in flight");
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int METHOD, int LOSS>
+__global__ void __launch_bounds__(kFLThreads, kFLCtasPerSm)
+decoder_fused_lean_kernel(FusedArgs a) {
+    static_assert(LOSS != LOSS_NONE && METHOD != PWR_METHOD_GIVEN, "last stage with a loss");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slots = reinterpret_cast<float*>(smem_raw);                                    // [pairs][2][4096]
+    uint64_t* full = reinterpret_cast<uint64_t*>(slots + kFLPairs * 2 * kMap);            // [pairs][2]
+    __shared__ __align__(16) float scr_e[2][kFLWarps];
+    __shared__ __align__(16) float scr_f[2][5 * kFLWarps];        // forward sums
+    __shared__ __align__(16) float scr_b[2][5 * kFLWarps];        // backward sums
+    __shared__ __align__(16) uint32_t scal[2][32];                // 10-12 uvd_gt, 16-31 taps (one item ahead)
+    __shared__ float fp[LOSS == LOSS_SPARSE ? kFootprint : 1];
+    constexpr bool sparse = (LOSS == LOSS_SPARSE);
+
+    const int tid = threadIdx.x;
+    const long long first = static_cast<long long>(a.items) * blockIdx.x / gridDim.x;
+    const long long last = static_cast<long long>(a.items) * (blockIdx.x + 1) / gridDim.x;
+    if (first >= last) return;
+    if (a.coef.scale_dev != nullptr) {
+        const float up = *a.coef.scale_dev;
+        a.coef.cu *= up; a.coef.ch *= up; a.coef.cd *= up;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kFLPairs * 2; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto scalar_word = [&](long long it, int wd) -> uint32_t {
+        const size_t bj = static_cast<size_t>(it);
+        if (wd >= 10 && wd < 13) return __float_as_uint(a.uvd_gt[bj * 3 + wd - 10]);
+        if (wd >= 16 && sparse) return reinterpret_cast<const uint32_t*>(a.taps + bj)[wd - 16];
+        return 0u;
+    };
+    if (tid < 32) scal[0][tid] = scalar_word(first, tid);
+    __syncthreads();
+
+    // producer (thread 0): item n of this CTA -> pair n % kFLPairs, one barrier per map
+    auto issue = [&](long long it, int n) {
+        if (it >= last) return;
+        const int pr = n % kFLPairs;
+        float* dst = slots + pr * 2 * kMap;
+        const size_t off = static_cast<size_t>(it) * kMap;
+        mbar_expect_tx(&full[2 * pr], kSlotBytes);
+        bulk_g2s(dst, static_cast<const float*>(a.z) + off, kSlotBytes, &full[2 * pr]);
+        mbar_expect_tx(&full[2 * pr + 1], kSlotBytes);
+        bulk_g2s(dst + kMap, static_cast<const float*>(a.D) + off, kSlotBytes, &full[2 * pr + 1]);
+    };
+    if (tid == 0) {
+        for (int n = 0; n < kFLPairs; ++n) issue(first + n, n);
+    }
+
+    int b_cur = static_cast<int>(first / a.J);
+    int j_cur = static_cast<int>(first - static_cast<long long>(b_cur) * a.J);
+    const float xs = static_cast<float>(static_cast<int>((tid & 15) * 4) - 32);
+    const float ys0 = static_cast<float>(static_cast<int>(tid >> 4) - 32);     // row of chunk i: + (kFLThreads/16)*i
+    float4 lv[kFLVec], mv[kFLVec];
+    int b_loaded = -1;
+    float w_next = (METHOD == PWR_METHOD_SOFTMAX) ? a.w[j_cur] : 1.f;
+
+    // block extremum of the logits in slot `sz` in the direction of sign(c): per-warp results -> se[warp]
+    auto warp_extremum = [&](const float* sz, bool want_max, float* se) {
+        float e = want_max ? -INFINITY : INFINITY;
+#pragma unroll
+        for (int i = 0; i < kFLVec; ++i) {
+            const float4 z4 = reinterpret_cast<const float4*>(sz)[tid + i * kFLThreads];
+            if (want_max) e = fmaxf(fmaxf(fmaxf(e, z4.x), fmaxf(z4.y, z4.z)), z4.w);
+            else          e = fminf(fminf(fminf(e, z4.x), fminf(z4.y, z4.z)), z4.w);
+        }
+        e = want_max ? warp_max(e) : warp_min(e);
+        if ((tid & 31) == 0) se[tid >> 5] = e;
+    };
+    if (kFLFold && METHOD == PWR_METHOD_SOFTMAX) {       // first item: nobody computed its extremum yet
+        mbar_wait(&full[0], 0);
+        warp_extremum(slots, w_next * kLog2e >= 0.f, scr_e[0]);
+        __syncthreads();
+    }
+
+    int k = 0;
+    for (long long it = first; it < last; ++it, ++k) {
+        const float wj = w_next;
+        const float c = wj * kLog2e;
+        if (b_cur != b_loaded) {                      // label and mask stay in registers for the J items of a sample
+            b_loaded = b_cur;
+            const size_t offb = static_cast<size_t>(b_cur) * kMap + tid * 4;
+#pragma unroll
+            for (int i = 0; i < kFLVec; ++i) mv[i] = ld_keep(a.m + offb + i * (kFLThreads * 4));
+#pragma unroll
+            for (int i = 0; i < kFLVec; ++i) lv[i] = ld_keep(a.L + offb + i * (kFLThreads * 4));
+        }
+        int j_next = j_cur + 1, b_next = b_cur;
+        if (j_next == a.J) { j_next = 0; ++b_next; }
+        if (METHOD == PWR_METHOD_SOFTMAX && it + 1 < last) w_next = a.w[j_next];
+        const uint32_t next_word = (tid < 32 && it + 1 < last) ? scalar_word(it + 1, tid) : 0u;
+        const float* sc = reinterpret_cast<const float*>(scal[k & 1]);
+        TapsIdx tp;
+        if (sparse) {
+            tp = taps_index(scal[k & 1] + 16);
+            if (tid < kFootprint) fp[tid] = footprint_entry(scal[k & 1] + 16, tid);   // published by the barriers below
+        }
+        const int pr = k % kFLPairs;
+        const uint32_t ph = (k / kFLPairs) & 1;
+        float* sz = slots + pr * 2 * kMap;
+        float* sD = sz + kMap;
+        bool handed_back = false;                     // the slots of item k - 1 go back after this item's first barrier
+        auto hand_back = [&]() {
+            if (!handed_back && tid == 0 && k > 0) issue(it - 1 + kFLPairs, k - 1 + kFLPairs);
+            handed_back = true;
+        };
+
+        // ---- forward: extremum, five sums (decoder_fwd_kernel's arithmetic); nothing per pixel is kept ----
+        mbar_wait(&full[2 * pr], ph);
+        float shift = 0.f, zext = 0.f;
+        if (METHOD == PWR_METHOD_SOFTMAX) {
+            const bool want_max = c >= 0.f;
+            float* se = scr_e[k & 1];
+            if (!kFLFold) {
+                warp_extremum(sz, want_max, se);
+                __syncthreads();
+                hand_back();
+            }
+            zext = se[0];
+#pragma unroll
+            for (int wv = 1; wv < kFLWarps; ++wv) zext = want_max ? fmaxf(zext, se[wv]) : fminf(zext, se[wv]);
+            shift = zext * c;
+        }
+        mbar_wait(&full[2 * pr + 1], ph);
+        float accf[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum e, e*(x-32), e*(y-32), e*m, e*m*m*(D+L)
+#pragma unroll
+        for (int i = 0; i < kFLVec; ++i) {
+            const float4 z4 = reinterpret_cast<const float4*>(sz)[tid + i * kFLThreads];
+            const float4 d4 = reinterpret_cast<const float4*>(sD)[tid + i * kFLThreads];
+            const float ys = ys0 + static_cast<float>(kFLThreads / 16) * i;
+            float rowsum = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float e = heat_raw<METHOD>(comp(z4, kk), c, shift);
+                const float mk = comp(mv[i], kk);
+                const float em = e * mk;
+                rowsum += e;
+                accf[1] = fmaf(e, xs + static_cast<float>(kk), accf[1]);
+                accf[3] += em;
+                accf[4] = fmaf(em, mk * (comp(d4, kk) + comp(lv[i], kk)), accf[4]);
+            }
+            accf[0] += rowsum;
+            accf[2] = fmaf(rowsum, ys, accf[2]);
+        }
+        float* sf = scr_f[k & 1];
+        store_scattered5<kFLWarps>(warp_sum5_scattered(accf), sf);
+        __syncthreads();
+        hand_back();
+        const float inv_s = 1.f / sum_partials<kFLWarps>(sf);
+        const float den = fmaf(sum_partials<kFLWarps>(sf + 3 * kFLWarps), inv_s, kEps);
+        const float dcoord = (sum_partials<kFLWarps>(sf + 4 * kFLWarps) * inv_s) / den;
+        const float u = sum_partials<kFLWarps>(sf + kFLWarps) * inv_s / 63.f;
+        const float v = sum_partials<kFLWarps>(sf + 2 * kFLWarps) * inv_s / 63.f;
+
+        // ---- loss on the coordinates: the upstream of the backward ----
+        const float eu = u - sc[10], ev = v - sc[11], ed = dcoord - sc[12];
+        const float gu = a.coef.cu * eu, gvv = a.coef.cu * ev, gd = a.coef.cu * ed;
+        const float lu = eu * eu + ev * ev + ed * ed;
+        const float gu63 = gu * (1.f / 63.f), gv63 = gvv * (1.f / 63.f);
+        const float gdd = __fdividef(gd, den);
+
+        // ---- backward pass (decoder_fused_kernel's arithmetic): gp over z, p over D, heat maps stored on the way ----
+        float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum gp*p, sum (p-Hgt)^2, sum (D-Dgt)^2, T1, T2
+        const bool keep = a.gz != nullptr;
+#pragma unroll
+        for (int i = 0; i < kFLVec; ++i) {
+            const int cidx = tid + i * kFLThreads;
+            const float4 z4 = reinterpret_cast<const float4*>(sz)[cidx];
+            const float4 d4 = reinterpret_cast<const float4*>(sD)[cidx];
+            const float4 l4 = lv[i], m4 = mv[i];
+            float4 t2 = make_float4(0.f, 0.f, 0.f, 0.f), t3 = t2;
+            if (sparse) sparse_lookup(tp, fp, cidx >> 4, (cidx & 15) * 4, l4, m4, t2, t3);
+            const float gyrow = gv63 * (ys0 + static_cast<float>(kFLThreads / 16) * i);
+            float4 gd4, p4, gp4, q4;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float zk = comp(z4, kk);
+                const float p = heat_raw<METHOD>(zk, c, shift) * inv_s;
+                const float mk = comp(m4, kk), dk = comp(d4, kk);
+                const float rec = mk * (dk + comp(l4, kk));
+                float gp = fmaf(gu63, xs + static_cast<float>(kk), gyrow);
+                gp = fmaf(gdd * mk, rec - dcoord, gp);
+                float gdk = gdd * p * mk * mk;
+                if (sparse) {
+                    const float eh = p - comp(t2, kk), edm = dk - comp(t3, kk);
+                    gp = fmaf(a.coef.ch, eh, gp);
+                    gdk = fmaf(a.coef.cd, edm, gdk);
+                    acc[1] = fmaf(eh, eh, acc[1]);
+                    acc[2] = fmaf(edm, edm, acc[2]);
+                }
+                const float pg = gp * p;
+                acc[0] += pg;
+                if (METHOD == PWR_METHOD_SOFTMAX) {
+                    const float dz = zk - zext;
+                    acc[3] = fmaf(pg, dz, acc[3]);
+                    acc[4] = fmaf(p, dz, acc[4]);
+                }
+                set_comp(p4, kk, p);
+                set_comp(gp4, kk, gp);
+                set_comp(gd4, kk, gdk);
+                // what the dL/dz pass multiplies (gp - s1) with: p (softmax) or [z > 0] / sum (relu-sum)
+                set_comp(q4, kk, METHOD == PWR_METHOD_SOFTMAX ? p : (zk > 0.f ? inv_s : 0.f));
+            }
+            if (a.H != nullptr) st_stream(a.H + static_cast<size_t>(it) * kMap + cidx * 4, p4);
+            if (a.gD != nullptr) st_stream(static_cast<float*>(a.gD) + static_cast<size_t>(it) * kMap + cidx * 4, gd4);
+            if (keep) {
+                reinterpret_cast<float4*>(sz)[cidx] = gp4;
+                reinterpret_cast<float4*>(sD)[cidx] = q4;
+            }
+        }
+        // next item's scalars: parked before the barrier below, read after it
+        if (tid < 32 && it + 1 < last) scal[(k + 1) & 1][tid] = next_word;
+        if (kFLFold && METHOD == PWR_METHOD_SOFTMAX && it + 1 < last) {
+            const int prn = (k + 1) % kFLPairs;
+            mbar_wait(&full[2 * prn], ((k + 1) / kFLPairs) & 1);
+            warp_extremum(slots + prn * 2 * kMap, w_next * kLog2e >= 0.f, scr_e[(k + 1) & 1]);
+        }
+        float* sb = scr_b[k & 1];
+        store_scattered5<kFLWarps>(warp_sum5_scattered(acc), sb);
+        __syncthreads();
+        j_cur = j_next; b_cur = b_next;
+
+        const float s1 = sum_partials<kFLWarps>(sb);
+        if (keep) {
+#pragma unroll
+            for (int i = 0; i < kFLVec; ++i) {
+                const int cidx = tid + i * kFLThreads;
+                const float4 gp4 = reinterpret_cast<const float4*>(sz)[cidx];
+                const float4 q4 = reinterpret_cast<const float4*>(sD)[cidx];
+                float4 g4;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    float g;
+                    if (METHOD == PWR_METHOD_SOFTMAX) g = wj * (comp(q4, kk) * (comp(gp4, kk) - s1));
+                    else g = comp(q4, kk) != 0.f ? (comp(gp4, kk) - s1) * comp(q4, kk) : 0.f;
+                    set_comp(g4, kk, g);
+                }
+                st_stream(static_cast<float*>(a.gz) + static_cast<size_t>(it) * kMap + cidx * 4, g4);
+            }
+            fence_proxy_async_smem();      // the next accesses to these slots are the producer's bulk copies
+        }
+        if (tid == 0) {
+            float* o = a.uvd + static_cast<size_t>(it) * 3;
+            o[0] = u; o[1] = v; o[2] = dcoord;
+            if (a.stats != nullptr) reinterpret_cast<float4*>(a.stats)[it] = make_float4(zext, inv_s, den, dcoord);
+            if (METHOD == PWR_METHOD_SOFTMAX && a.gw_partial != nullptr)
+                a.gw_partial[it] = sum_partials<kFLWarps>(sb + 3 * kFLWarps) - s1 * sum_partials<kFLWarps>(sb + 4 * kFLWarps);
+            if (a.loss_partial != nullptr) {
+                a.loss_partial[it * 3 + 0] = sum_partials<kFLWarps>(sb + kFLWarps);
+                a.loss_partial[it * 3 + 1] = sum_partials<kFLWarps>(sb + 2 * kFLWarps);
+                a.loss_partial[it * 3 + 2] = lu;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // backward, lean pipelined variant: no dense target / upstream-gradient maps
 // ---------------------------------------------------------------------------
 // With compact (pwr_joint_taps) targets, or with no map terms at all, an item moves only 32 KB in
@@ -1666,6 +1967,7 @@ static bool force_direct_bwd() { return g_options[PWR_OPT_BWD_DIRECT].load(std::
 static bool force_direct_fwd() { return g_options[PWR_OPT_FWD_DIRECT].load(std::memory_order_relaxed) != 0; }
 static bool force_pipe_fwd() { return g_options[PWR_OPT_FWD_PIPE].load(std::memory_order_relaxed) != 0; }
 static bool no_lean_bwd() { return g_options[PWR_OPT_BWD_NO_LEAN].load(std::memory_order_relaxed) != 0; }
+static bool no_lean_fused() { return g_options[PWR_OPT_FUSED_NO_LEAN].load(std::memory_order_relaxed) != 0; }
 static bool bad_method(int method) {
     return method != PWR_METHOD_SOFTMAX && method != PWR_METHOD_SUM && method != PWR_METHOD_GIVEN;
 }
@@ -1705,6 +2007,20 @@ static bool bad_dtype(int method, int map_dtype) {
 static int launch_fused(const FusedArgs& a, int method, int map_dtype, cudaStream_t s) {
     const bool sparse = a.taps != nullptr;
     const int dev = current_device(), sms = sm_count(dev);
+    // No dense target map to visit (compact targets, or the uvd term alone) and float32 logits: the lean
+    // variant (three CTAs per SM, per-pixel state in the ring).  Measured B=4096 NYU in DESIGN.md section 4.
+    if ((sparse || a.heat_gt == nullptr) && map_dtype == PWR_DTYPE_F32 && !no_lean_fused()) {
+        const int lgrid = a.items < sms * kFLCtasPerSm ? a.items : sms * kFLCtasPerSm;
+#define PWR_LAUNCH_FL(M, LS)                                                                                 \
+    do {                                                                                                     \
+        PWR_ENSURE_DYN_SMEM(kFLSmemBytes, dev, decoder_fused_lean_kernel<M, LS>);                            \
+        decoder_fused_lean_kernel<M, LS><<<lgrid, kFLThreads, kFLSmemBytes, s>>>(a);                         \
+    } while (0)
+        if (method == PWR_METHOD_SOFTMAX) { if (sparse) PWR_LAUNCH_FL(PWR_METHOD_SOFTMAX, LOSS_SPARSE); else PWR_LAUNCH_FL(PWR_METHOD_SOFTMAX, LOSS_DENSE); }
+        else                              { if (sparse) PWR_LAUNCH_FL(PWR_METHOD_SUM, LOSS_SPARSE); else PWR_LAUNCH_FL(PWR_METHOD_SUM, LOSS_DENSE); }
+#undef PWR_LAUNCH_FL
+        return launch_status();
+    }
     const int grid = a.items < sms * kFusedCtasPerSm ? a.items : sms * kFusedCtasPerSm;
 #define PWR_LAUNCH_FUSED(M, LS, TZ)                                                                          \
     do {                                                                                                     \

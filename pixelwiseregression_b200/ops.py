@@ -130,9 +130,11 @@ def decoder_backward_raw(z, w, D, label_img, mask, stats, uvd, g_uvd=None, gH_up
 
 
 def decoder_fused_raw(z, w, D, label_img, mask, targets, method="softmax", alpha=1.0, lambda_h=1.0, lambda_d=0.01,
-                      loss_scale=1.0, loss_scale_dev=None, n_mean=0, store_heat=True, want_grads=True):
+                      loss_scale=1.0, loss_scale_dev=None, n_mean=0, store_heat=True, want_grads=True,
+                      want_loss=True):
     """One launch of pwr_decoder_fwd_bwd_loss: last-stage forward + stage loss + backward with z, D and
-    the targets read once.  Returns (H or None, uvd, gz, gD, gw_partial or None, loss_partial [B,J,3])."""
+    the targets read once.  Returns (H or None, uvd, gz, gD, gw_partial or None, loss_partial [B,J,3] or None).
+    `want_loss=False` skips the logged loss terms; with alpha = 1 the target maps are then not read at all."""
     require_cuda(z, w, D, label_img, mask)
     lib = _lib.load()
     z, D, map_dtype = _conv_maps(z, D, method)
@@ -147,7 +149,7 @@ def decoder_fused_raw(z, w, D, label_img, mask, targets, method="softmax", alpha
     gz = torch.empty_like(z) if want_grads else None
     gD = torch.empty_like(z) if want_grads else None
     gw_partial = torch.empty(B, J, **f32) if (want_grads and method == "softmax") else None
-    loss_partial = torch.empty(B, J, 3, **f32)
+    loss_partial = torch.empty(B, J, 3, **f32) if want_loss else None
     loss_scale_dev = as_f32(loss_scale_dev)
     with _lib.launch(z.device, "pwr_decoder_fwd_bwd_loss"):
         rc = lib.pwr_decoder_fwd_bwd_loss(ptr(z), ptr(wv), ptr(D), ptr(label_img), ptr(mask), ptr(heat_gt), ptr(dmap_gt),

@@ -42,7 +42,7 @@ def test_signature_arity_matches_header():
 
 
 def test_version_and_error_strings(lib):
-    assert lib.pwr_version() == _lib.ABI_VERSION == 200
+    assert lib.pwr_version() == _lib.ABI_VERSION == 201
     assert lib.pwr_error_string(0) == b"ok"
     assert b"NULL" in lib.pwr_error_string(-1)
     assert b"aligned" in lib.pwr_error_string(-3)

@@ -357,3 +357,58 @@ def test_inner_stage_forward_loss_through_the_one_pass_kernel_equals_the_direct_
     tol = 2e-5 if dtype == torch.float32 else 1e-2
     assert_close("gz", a[0].float().cpu().numpy(), b[0].float().cpu().numpy(), tol)
     assert_close("gD", a[1].float().cpu().numpy(), b[1].float().cpu().numpy(), tol)
+
+
+@pytest.mark.parametrize("method", ["softmax", "sum"])
+@pytest.mark.parametrize("B,J", [(1, 1), (2, 3), (300, 14)])
+def test_lean_one_pass_kernel_equals_the_two_cta_one_pass_kernel(method, B, J):
+    """Without a dense target map to visit (compact targets, or the uvd term alone) and float32 logits,
+    pwr_decoder_fwd_bwd_loss runs decoder_fused_lean_kernel: three CTAs per SM, gp / p parked in the ring slots of
+    z / D instead of in registers.  Same arithmetic and summation order as decoder_fused_kernel (option
+    `fused_no_lean`) up to the compiler's choice of fused multiply-adds (measured: identical or 1 ulp apart), and
+    bitwise reproducible from run to run; B = 300, J = 14 gives ~9.5 items per CTA at grid 444
+    (each of the two slot pairs re-used four times, sample boundaries inside a CTA's range); (1, 1) and (2, 3)
+    leave most of the ring unused.  tools/sanitize.sh runs this test under racecheck / memcheck / initcheck."""
+    from pixelwiseregression_b200 import _lib
+    shape = synth.NYU
+    d = synth.make_frames_device(shape, B, seed=33 + B, device=DEV)
+    batch = sfr.build_sfr(d["frames"], d["com"], d["cube"], d["uvd"][:, :J].contiguous(), fx=shape.fx, fy=shape.fy,
+                          targets="both")
+    g = torch.Generator(device=DEV).manual_seed(B + J)
+    z = torch.randn(B, J, 64, 64, device=DEV, generator=g) * 2
+    D = torch.randn(B, J, 64, 64, device=DEV, generator=g)
+    w = None
+    if method == "softmax":
+        w = torch.rand(J, 1, device=DEV, generator=g) + 0.5
+        w[::3] *= -1.0                                  # negative temperatures take the minimum as the extremum
+    L, m = batch.label_img, batch.mask
+    compact = ops.SparseTargets(batch.taps, batch.uvd)
+    dense = (batch.heatmaps, batch.depthmaps, batch.uvd)
+    cases = [(compact, dict(alpha=0.5)), (compact, dict(alpha=1.0, store_heat=False)),
+             (compact, dict(alpha=0.3, want_grads=False)),            # forward + loss only (gz = gD = NULL)
+             (dense, dict(alpha=1.0, want_loss=False)),               # uvd term only: the target maps are not visited
+             (compact, dict(alpha=1.0, want_loss=False, store_heat=False))]
+    for targets, kw in cases:
+        lean = ops.decoder_fused_raw(z, w, D, L, m, targets, method, **kw)
+        again = ops.decoder_fused_raw(z, w, D, L, m, targets, method, **kw)
+        with _lib.option("fused_no_lean", 1):
+            ref = ops.decoder_fused_raw(z, w, D, L, m, targets, method, **kw)
+        torch.cuda.synchronize()
+        for name, x, y, x2 in zip(("H", "uvd", "gz", "gD", "gw_partial", "loss_partial"), lean, ref, again):
+            assert (x is None) == (y is None), name
+            if x is not None:
+                assert_close("%s %s" % (name, kw), x.cpu().numpy(), y.cpu().numpy(), 2e-6)
+                assert torch.equal(x, x2), ("run-to-run", name, kw)
+    # and against the float64 oracle (uvd-only loss, alpha = 1)
+    H, uvd, gz, gD, gwp, _ = ops.decoder_fused_raw(z, w, D, L, m, compact, method, alpha=1.0)
+    t64 = lambda a: a.detach().cpu().to(torch.float64)
+    w64 = t64(w) if w is not None else None
+    p_ref, _, uvd_ref = do.decoder_forward(t64(z), w64, t64(D), t64(L), t64(m), method)
+    gz_ref, gD_ref, gw_ref = do.decoder_backward(t64(z), w64, t64(D), t64(L), t64(m), torch.zeros(B, J, 3, dtype=torch.float64),
+                                                 None, None, method, targets=tuple(t64(a) for a in dense), alpha=1.0)
+    assert_close("H vs oracle", H.cpu().numpy(), p_ref.numpy())
+    assert_close("uvd vs oracle", uvd.cpu().numpy(), uvd_ref.numpy())
+    assert_close("gz vs oracle", gz.cpu().numpy(), gz_ref.numpy(), GRAD_RTOL)
+    assert_close("gD vs oracle", gD.cpu().numpy(), gD_ref.numpy(), GRAD_RTOL)
+    if method == "softmax":
+        assert_close("gw vs oracle", ops.reduce_partials(gwp).view(-1, 1).cpu().numpy(), gw_ref.numpy(), GRAD_RTOL)

@@ -397,9 +397,12 @@ __device__ __forceinline__ float load_px(const void* __restrict__ frame, int idx
 // PNG decode arithmetic (which made the raw-frame build SLOWER than the float32 one in r1: 0.59 vs 0.54 ms).
 constexpr int kWinTab = 768;                       // covers cube <= 380 mm; larger cubes use the per-tap arithmetic
 struct WinTab { const float* tab; int base; int n; };
+// tab[n] is a 0.f sentinel: every raw value outside the table clamps onto it, so the lookup is one unconditional
+// shared-memory load (r2: the predicated form made ptxas rebuild the shared-window address per tap - S2R + MOV +
+// VIADD + LEA under the predicate, 64 of the 252 instructions of a 2x2 block).
 __device__ __forceinline__ float tab_lookup(unsigned int raw, const WinTab& t) {
-    const unsigned int i = raw - static_cast<unsigned int>(t.base);
-    return i < static_cast<unsigned int>(t.n) ? t.tab[i] : 0.f;
+    const unsigned int i = min(raw - static_cast<unsigned int>(t.base), static_cast<unsigned int>(t.n));
+    return t.tab[i];
 }
 
 template <typename T, int FMT, bool INTERIOR, bool TAB = false, bool SMEM = false>
@@ -622,7 +625,7 @@ sfr_build_kernel(SfrArgs a) {
     __shared__ int band_list_n;
     __shared__ int band_flags[2];                           // [0] mask count, [1] NaN seen (this CTA)
     constexpr bool kTab = (FMT != FMT_F32) && sizeof(T) == 4;      // raw 16-bit frames: window lookup table
-    __shared__ float wtab[kTab ? kWinTab : 1];
+    __shared__ float wtab[kTab ? kWinTab + 1 : 1];          // + the 0.f sentinel at [n]
     extern __shared__ __align__(128) unsigned char stage_raw[];    // STAGED: kStageBytes of source rows
     __shared__ __align__(8) uint64_t stage_bar;
 
@@ -709,6 +712,7 @@ sfr_build_kernel(SfrArgs a) {
         }
         for (int i = tid; i < wt.n; i += kThreads)
             wtab[i] = Arith<float>::window(decode_px<FMT>(static_cast<unsigned int>(wt.base + i)), g);
+        if (tid == 0) wtab[wt.n] = 0.f;
     }
     if (g.ok) {
         if (tid < kImage) xtap[tid] = linear_tap(tid, g.ncols, g.scale_x);

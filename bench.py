@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--augment", action="store_true",
                     help="build the SFR targets through the augmented branch (datasets.py:216-299, train.py defaults)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-balance", action="store_true",
+                    help="N > 1: keep equal shards in the e2e leg (default: also try bandwidth-proportional shards)")
     ap.add_argument("--no-sparse", action="store_true", help="skip the variants of the step (two-kernel, compact, raw)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager decoder baseline on the GPU")
     ap.add_argument("--no-extras", action="store_true",
@@ -295,6 +297,7 @@ def run_b200(args):
     pending = {"work": False}
     arenas = {}
 
+    reduce_mode = {"n_mean": 0, "op": dist.ReduceOp.AVG if world > 1 else None}     # unequal shards: global n_mean + SUM
     store_heat = {"on": True}      # False: the last stage as model.forward_loss runs it (heat maps never leave the kernel)
 
     def step(frames_, com_, cube_, uvd_, z_, D_, kw=None, key="main"):
@@ -308,15 +311,16 @@ def run_b200(args):
             pending["work"] = False
         total, terms, uvd_out = ops.fused_decoder_loss(z_, w, D_, batch.label_img, batch.mask, heat_t,
                                                        batch.depthmaps, batch.uvd, method="softmax", alpha=alpha,
-                                                       lambda_h=lambda_h, lambda_d=lambda_d, store_heat=store_heat["on"])[:3]
+                                                       lambda_h=lambda_h, lambda_d=lambda_d, store_heat=store_heat["on"],
+                                                       n_mean=reduce_mode["n_mean"])[:3]
         z_.grad = D_.grad = w.grad = None
         total.backward()
         if world > 1:
             # what the DDP bucket carries for this path: dL/dw [J] and the logged loss terms [3]
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
-                dist.all_reduce(w.grad, op=dist.ReduceOp.AVG)
-                dist.all_reduce(terms, op=dist.ReduceOp.AVG)
+                dist.all_reduce(w.grad, op=reduce_mode["op"])
+                dist.all_reduce(terms, op=reduce_mode["op"])
             w.grad.record_stream(comm_stream)
             terms.record_stream(comm_stream)
             pending["work"] = True
@@ -328,6 +332,12 @@ def run_b200(args):
             pending["work"] = False
             dist.barrier()
         torch.cuda.synchronize()
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(round(float(t.item())))
 
     def max_over_ranks(x):
         t = torch.tensor([x], device=dev, dtype=torch.float64)
@@ -597,29 +607,51 @@ def run_b200(args):
         errors['inner_stage'] = repr(exc)
         sys.stderr.write("bench.py: inner_stage failed: %r\n" % (exc,))
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region ----
-    def run_e2e():
+    e2e_pool = {}
+
+    def e2e_inputs(cap):
+        """Pinned host copies of `cap` samples (the rank's B synthetic samples, repeated beyond B) and logits for them."""
+        if e2e_pool.get("cap", 0) >= cap:
+            return e2e_pool
+        e2e_pool.clear()
+        torch.cuda.empty_cache()
+        fmt = raw_fmt if raw_frames is not None else "f32"
+        src = raw_frames if raw_frames is not None else frames
+        host_frames = torch.empty((cap,) + tuple(src.shape[1:]), dtype=src.dtype, pin_memory=True)
+        for lo in range(0, cap, B):
+            n = min(B, cap - lo)
+            host_frames[lo:lo + n].copy_(src[:n])
+        idx = torch.arange(cap) % B
+        e2e_pool.update(cap=cap, fmt=fmt, host_frames=host_frames,
+                        com=com.cpu()[idx].numpy(), cube=cube.cpu()[idx].numpy(), uvd=uvd.cpu()[idx].numpy(),
+                        z=z.detach() if cap == B else z.detach()[idx.to(dev)],
+                        D=D.detach() if cap == B else D.detach()[idx.to(dev)])
+        return e2e_pool
+
+    def run_e2e(Br=None, n_steps=None, n_mean=0):
         """Public feed API: raw uint16 frames + annotations live in pinned host memory; every step the annotations are
         copied and pwr_sfr_fetch pulls the crop windows over PCIe on the copy stream while the previous batch is being
         built and decoded; the loss vector and the decoded joints are read back and waited for every step.  The
-        logits stand in for the conv backbone's outputs, which only ever exist on the device."""
-        import numpy as np
-        fmt = raw_fmt if raw_frames is not None else "f32"
-        src = raw_frames if raw_frames is not None else frames
-        host_frames = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
-        host_frames.copy_(src)
-        host = {"com": com.cpu().numpy(), "cube": cube.cpu().numpy(), "uvd": uvd.cpu().numpy()}
+        logits stand in for the conv backbone's outputs, which only ever exist on the device.
+        `Br`: this rank's share of the global batch (default: the equal share B); with unequal shares `n_mean` =
+        global B*J keeps every loss the global-batch mean and the cross-rank reduction is a SUM."""
+        Br = B if Br is None else int(Br)
+        pool = e2e_inputs(max(Br, B))
+        fmt, host_frames = pool["fmt"], pool["host_frames"][:Br]
+        host = {"com": pool["com"][:Br], "cube": pool["cube"][:Br], "uvd": pool["uvd"][:Br]}
         pf = (40.0, shape.halfu, shape.halfv) if raw_frames is not None else None
-        hf = feed.HostFeed(shape, B, frame_format=fmt, prefilter=pf, device=dev)
-        out_host = torch.empty(4 + B * J * 3, pin_memory=True)
+        hf = feed.HostFeed(shape, Br, frame_format=fmt, prefilter=pf, device=dev, timing=True)
+        out_host = torch.empty(4 + Br * J * 3, pin_memory=True)
         done = torch.cuda.Event()
-        zz, DD = z.detach().requires_grad_(True), D.detach().requires_grad_(True)
+        zz, DD = pool["z"][:Br].detach().requires_grad_(True), pool["D"][:Br].detach().requires_grad_(True)
+        reduce_mode.update(n_mean=int(n_mean), op=dist.ReduceOp.SUM if n_mean else dist.ReduceOp.AVG)
 
         def submit():
             return hf.submit(host_frames, host["com"], host["cube"], host["uvd"])
 
         def consume(t):
             batch = hf.build(t)
-            total, terms, uvd_out = step(batch, None, None, None, zz, DD)
+            total, terms, uvd_out = step(batch, None, None, None, zz, DD, None, "e2e_%d" % Br)
             if world > 1:                                    # the logged terms are being averaged on the side stream
                 torch.cuda.current_stream().wait_stream(comm_stream)
                 pending["work"] = False
@@ -628,47 +660,83 @@ def run_b200(args):
             out_host[4:].copy_(uvd_out.reshape(-1), non_blocking=True)
             done.record()
 
-        n_e2e = args.e2e_steps or min(args.steps, 20)
-        t = submit()
-        for _ in range(3):                                   # warm-up with the pipeline running
-            nxt = submit()
-            consume(t)
-            done.synchronize()
-            t = nxt
-        fetched = hf.fetched_bytes(t)
-        barrier()
-        host_ms = [0.0, 0.0, 0.0]                            # host time in submit / consume / waiting for the results
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            ta = time.perf_counter()
-            nxt = submit()                                   # batch k+1 starts crossing PCIe
-            tb = time.perf_counter()
-            consume(t)                                       # batch k: build + decode + loss + backward + D2H
-            tc = time.perf_counter()
-            done.synchronize()                               # the host holds loss and joints of batch k
-            td = time.perf_counter()
-            host_ms[0] += (tb - ta) * 1e3; host_ms[1] += (tc - tb) * 1e3; host_ms[2] += (td - tc) * 1e3
-            t = nxt
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        barrier()
-        dt = max_over_ranks(dt)
+        try:
+            n_e2e = n_steps or args.e2e_steps or min(args.steps, 20)
+            t = submit()
+            for _ in range(3):                                   # warm-up with the pipeline running
+                nxt = submit()
+                consume(t)
+                done.synchronize()
+                t = nxt
+            fetched = hf.fetched_bytes(t)
+            barrier()
+            host_ms = [0.0, 0.0, 0.0]                            # host time in submit / consume / waiting for the results
+            fetch_ms = 0.0
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                ta = time.perf_counter()
+                nxt = submit()                                   # batch k+1 starts crossing PCIe
+                tb = time.perf_counter()
+                consume(t)                                       # batch k: build + decode + loss + backward + D2H
+                tc = time.perf_counter()
+                done.synchronize()                               # the host holds loss and joints of batch k
+                td = time.perf_counter()
+                host_ms[0] += (tb - ta) * 1e3; host_ms[1] += (tc - tb) * 1e3; host_ms[2] += (td - tc) * 1e3
+                fetch_ms += hf.fetch_ms(t)                       # long finished: batch k was built from it
+                t = nxt
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            dt = max_over_ranks(dt)
+        finally:
+            reduce_mode.update(n_mean=0, op=dist.ReduceOp.AVG if world > 1 else None)
+            arenas.pop("e2e_%d" % Br, None)
         loss_host = float(out_host[0])
         h2d = fetched + hf.h2d_bytes_small
-        res = {"value": B * world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+        total_samples = sum_over_ranks(Br)
+        res = {"value": total_samples * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "h2d_bytes_per_step_all_ranks": sum_over_ranks(h2d),
                "d2h_bytes_per_step": out_host.numel() * 4, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
                "pcie_gbs_per_gpu": h2d / (dt / n_e2e) / 1e9, "window_hw": list(hf.win_hw), "loss_read_back": loss_host,
                "host_ms_per_step": {"submit": host_ms[0] / n_e2e, "consume": host_ms[1] / n_e2e,
                                     "wait_for_results": host_ms[2] / n_e2e},
+               "fetch_ms_per_step": fetch_ms / n_e2e, "batch_this_rank": Br,
                "frames_in_host_memory_bytes": host_frames.numel() * host_frames.element_size(),
                "note": "per rank and step: com + cube + uvd (%d B) copied from pinned host memory and the crop windows of "
                        "the raw %s frames (%d B of the %d B the frames occupy) pulled over PCIe by pwr_sfr_fetch on a "
                        "copy stream, one batch ahead of the compute stream (feed.HostFeed); loss[4] + uvd[B,J,3] read back "
                        "and waited for every step; the logits z, D stay on the device (they are the conv backbone's outputs); "
-                       "wall clock, max over ranks" % (hf.h2d_bytes_small, fmt, fetched,
+                       "wall clock, max over ranks; byte counts are rank 0's" % (hf.h2d_bytes_small, fmt, fetched,
                                                        host_frames.numel() * host_frames.element_size())}
-        del host_frames, hf
+        del hf
         return res
+
+    def run_e2e_balanced(equal):
+        """N > 1: the host links of a multi-GPU box are not equal (GPUs behind a shared upstream port halve each other)
+        and a lock-step job runs at the pace of the slowest one.  Give every rank a share of the SAME global batch
+        proportional to the rate its own fetches sustained (distributed.proportional_shards; three short rounds, each
+        measured under the previous round's shares), then time the feed again.  Same total work per step (N x B
+        samples), global-batch-mean loss through n_mean.  Returns None when it does not beat equal shares."""
+        from pixelwiseregression_b200 import distributed as pdist
+        n_mean = world * B * J
+        Br, fetch = B, equal["fetch_ms_per_step"]
+        history = []
+        for _ in range(3):
+            rates = pdist.gather_rates(Br / max(fetch, 1e-6), dev)
+            shards = pdist.proportional_shards(rates, world * B, 64, B // 2, B + B // 2)
+            history.append(shards)
+            Br = shards[rank]
+            probe = run_e2e(Br, n_steps=4, n_mean=n_mean)
+            fetch = probe["fetch_ms_per_step"]
+        if history[-1] == [B] * world:           # the links are equal (same list on every rank): nothing to gain
+            return None
+        res = run_e2e(Br, n_mean=n_mean)
+        res["sharding"] = {"mode": "bandwidth-proportional", "samples_per_rank": history[-1], "rounds": history,
+                           "global_batch": world * B,
+                           "what": "every rank's share of the global batch is proportional to the PCIe rate its own window "
+                                   "fetches sustained in the previous round (HostFeed.fetch_ms -> "
+                                   "distributed.proportional_shards); loss = global-batch mean (n_mean), gradients SUM-reduced"}
+        return res if res["value"] > equal["value"] else None
 
     def run_e2e_whole_frames(n_steps=3):
         """Round 1's definition, kept for continuity: whole float32 frames AND the logits cross PCIe, serially."""
@@ -709,8 +777,22 @@ def run_b200(args):
     try:
         if not args.no_e2e:
             sampler.section("e2e")
+            if world > 1 and not args.no_e2e_balance:
+                e2e_inputs(B + B // 2)                       # one pinned pool for both legs
             e2e = run_e2e()
+            e2e["sharding"] = {"mode": "equal", "samples_per_rank": [B] * world, "global_batch": world * B}
+            if world > 1 and not args.no_e2e_balance:
+                try:
+                    bal = run_e2e_balanced(e2e)
+                    if bal is not None:
+                        bal["equal_shards"] = {k: e2e[k] for k in ("value", "ms_per_step", "pcie_gbs_per_gpu", "fetch_ms_per_step")}
+                        e2e = bal
+                except Exception as exc:      # keep the equal-shard figure
+                    errors['e2e_balanced'] = repr(exc)
+                    sys.stderr.write("bench.py: e2e_balanced failed: %r\n" % (exc,))
+                    barrier()
             e2e["clocks"] = sampler.end_section("e2e")
+            e2e_pool.clear()
             if not args.no_extras:
                 e2e_r1 = run_e2e_whole_frames()
 

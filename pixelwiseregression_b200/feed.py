@@ -33,16 +33,18 @@ class _Slot:
         self.consumed = torch.cuda.Event()    # compute stream: the builder has read the windows
         self.used = False
         self.meta = None
+        self.t0 = self.t1 = None              # timing=True: events around the window fetch on the copy stream
 
 
 class HostFeed:
     """`shape`: a synth.DatasetShape (intrinsics + frame size); `batch`: samples per submit; `prefilter`:
     (margin, halfu, halfv) of load_from_text or None; `win_hw`: window size, default = large enough for the
     first submitted batch with 12.5 % headroom on the box (a later batch that needs more raises, never
-    truncates silently); `depth`: batches in flight (2 = double buffering)."""
+    truncates silently); `depth`: batches in flight (2 = double buffering); `timing`: time every window fetch
+    with CUDA events on the copy stream (`fetch_ms`) - what `distributed.proportional_shards` is fed with."""
 
     def __init__(self, shape, batch, *, frame_format="f32", prefilter=None, test_only=False, targets="dense",
-                 win_hw=None, depth=2, device=None, augment=False):
+                 win_hw=None, depth=2, device=None, augment=False, timing=False):
         if not torch.cuda.is_available():
             raise _lib.PwrError("HostFeed needs a CUDA device (there is no CPU fallback)")
         self.shape, self.batch = shape, int(batch)
@@ -55,6 +57,7 @@ class HostFeed:
         self.copy_stream = torch.cuda.Stream(self.device, priority=-1)
         self.slots = [_Slot() for _ in range(max(int(depth), 1))]
         self.n = 0
+        self.timing = bool(timing)
         self.h2d_bytes_small = 0       # annotation bytes of the last submit (the window bytes are counted on the device)
 
     # -- helpers ------------------------------------------------------------------------------
@@ -109,9 +112,15 @@ class HostFeed:
                 small += B * 8 * 8
             if slot.fw is not None:
                 slot.fw.fetched_bytes.zero_()
+            if self.timing:
+                if slot.t0 is None:
+                    slot.t0, slot.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                slot.t0.record(self.copy_stream)
             slot.fw = sfr.fetch_windows(frames, slot.dev["com"], slot.dev["cube"], fx=self.shape.fx, fy=self.shape.fy,
                                         frame_format=self.frame_format, prefilter=self.prefilter, augment=aug_dev,
                                         win_hw=self.win_hw, out=slot.fw)
+            if self.timing:
+                slot.t1.record(self.copy_stream)
             slot.ready.record(self.copy_stream)
         slot.used = True
         slot.meta = (ticket, aug_dev)
@@ -132,6 +141,14 @@ class HostFeed:
                               augment=slot.meta[1], arena=slot.arena)
         slot.consumed.record(cur)
         return batch
+
+    def fetch_ms(self, ticket):
+        """Device time of the window fetch of `ticket` on the copy stream (needs timing=True; synchronises on it)."""
+        slot = self.slots[ticket % len(self.slots)]
+        if not self.timing or slot.t1 is None or slot.meta is None or slot.meta[0] != ticket:
+            raise _lib.PwrError("fetch_ms: ticket %d is not in flight, or HostFeed was built without timing=True" % ticket)
+        slot.t1.synchronize()
+        return slot.t0.elapsed_time(slot.t1)
 
     def fetched_bytes(self, ticket):
         """Bytes `pwr_sfr_fetch` pulled from the frames for `ticket` (device -> host read: synchronises), and

@@ -214,3 +214,42 @@ def test_host_feed_test_only_and_augmented_modes():
         torch.cuda.synchronize()
         same(got, ref, "augmented feed, draw %d" % seed)
         hf.fetched_bytes(0 if seed == 1 else 1)            # raises if a region did not fit its window
+
+
+def test_fetch_timing_and_uneven_shards_keep_the_global_mean():
+    """HostFeed(timing=True).fetch_ms feeds distributed.proportional_shards; two feeds of unequal batch with
+    n_mean = global B*J must add up to one feed of the whole batch (what the N > 1 e2e leg of bench.py relies on)."""
+    from pixelwiseregression_b200 import distributed as pd, ops
+    shape = synth.NYU
+    B, J = 12, shape.joints
+    d = synth.make_frames(shape, B, seed=23)
+    raw = torch.from_numpy(raw_of(d["frames"])).pin_memory()
+    pf = (40.0, shape.halfu, shape.halfv)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    z = torch.randn(B, J, 64, 64, generator=g).to(DEV)
+    D = torch.randn(B, J, 64, 64, generator=g).to(DEV)
+    w = (torch.rand(J, 1, generator=g) + 0.5).to(DEV)
+
+    def run(lo, hi, n_mean):
+        hf = feed.HostFeed(shape, hi - lo, frame_format="nyu_gb16", prefilter=pf, timing=True)
+        t = hf.submit(raw[lo:hi], d["com"][lo:hi], d["cube"][lo:hi], d["uvd"][lo:hi])
+        batch = hf.build(t)
+        ms = hf.fetch_ms(t)
+        assert ms > 0.0
+        zz, DD, ww = (x.clone().requires_grad_(True) for x in (z[lo:hi], D[lo:hi], w))
+        total, terms, _ = ops.fused_decoder_loss(zz, ww, DD, batch.label_img, batch.mask, batch.heatmaps, batch.depthmaps,
+                                                 batch.uvd, alpha=0.5, n_mean=n_mean)[:3]
+        total.backward()
+        return total.detach(), terms.detach(), ww.grad, zz.grad, (hi - lo) / ms
+
+    whole = run(0, B, 0)
+    shards = pd.proportional_shards([1.0, 2.0], B, 1, 1, B)
+    assert shards == [4, 8]
+    a, b = run(0, shards[0], B * J), run(shards[0], B, B * J)
+    for i, name in ((0, "loss"), (1, "terms"), (2, "dL/dw")):
+        s = a[i] + b[i]
+        assert torch.allclose(s, whole[i], rtol=2e-5, atol=1e-8), name
+    assert torch.allclose(torch.cat([a[3], b[3]]), whole[3], rtol=1e-5, atol=1e-10)
+    with pytest.raises(_lib.PwrError):
+        hf = feed.HostFeed(shape, B, frame_format="nyu_gb16", prefilter=pf)
+        hf.fetch_ms(hf.submit(raw, d["com"], d["cube"], d["uvd"]))

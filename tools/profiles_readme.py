@@ -43,6 +43,7 @@ L = ["# profiles/ — round %s\n" % tag[1:],
      "| `%s_pcie_probe.json`, `%s_pcie_probe_n8.json`, `%s_topo*.txt` | `tools/pcie_probe.cu`: how a GPU can pull frames / crop windows from pinned host memory (design of the e2e feed); the same probe on 8 GPUs at once; `nvidia-smi topo -m` |" % (tag, tag, tag),
      "| `%s_sanitizer_lean_racecheck.log`, `%s_ab_fused_lean.txt` | racecheck of `decoder_fused_lean_kernel` (the three-CTA one-pass variant, all 4 instantiations); `tools/ab_fused.py`: lean vs two-CTA one-pass kernel, ms and bit-identity |" % (tag, tag),
      "| `%s_ab_sfr_window_table.txt`, `%s_ab_sfr_hoisted_taps.txt`, `%s_ab_sfr_packed_taps.txt` | `tools/ab_sfr.py` A/B of the SFR builder: sentinel window-table lookup (kept: 0.244 -> 0.212 ms compact raw frames); per-thread hoisted column taps at 4 / 5 / 6 CTAs per SM and packed 16-byte tap tables (both measured, rejected: register pressure / no gain) |" % (tag, tag, tag),
+     "| `%s_bench_n8_balanced.json`, `%s_bench_n2_balanced.json` | `bench.py --no-extras` at N = 8 / 2 with the bandwidth-proportional shards of the e2e leg (`e2e.sharding`, `e2e.equal_shards`) |" % (tag, tag),
      "| `%s_sweep_hand17_n1.txt` | `tools/sweep_inference.py`: BASELINE configs[4] inference sweep, batch 256 .. 16384 |" % tag,
      "| `../tools/capture_profiles.sh`, `../tools/sanitize.sh` | the exact commands behind the above |", ""]
 
@@ -139,6 +140,15 @@ for n in (1, 2, 4, 8):
         100 * b["e2e"]["value"] / (n * bench["e2e"]["value"]), b["e2e"]["pcie_gbs_per_gpu"],
         b["train_step"]["fused"]["samples_per_s"], b["train_msra"]["fused"]["samples_per_s"],
         ("%.2f M" % (sw["samples_per_s_calls"] / 1e6)) if sw else "-"))
+bal = load("%s_bench_n8_balanced.json" % tag)
+if bal and bal.get("e2e") and bal["e2e"].get("equal_shards"):
+    e = bal["e2e"]
+    L += ["", "e2e at N = 8 with bandwidth-proportional shards of the global batch (`%s_bench_n8_balanced.json`, end of r2): "
+          "%.0f samples/s against %.0f with equal shards on the same box (+%.0f %%), %.1f ms per step, shares %s of %d; "
+          "%.0f GB/s of windows for the whole box - the host side of the box is the bound, unevenly shared between the GPUs."
+          % (tag, e["value"], e["equal_shards"]["value"], 100 * (e["value"] / e["equal_shards"]["value"] - 1), e["ms_per_step"],
+             e["sharding"]["samples_per_rank"], e["sharding"]["global_batch"],
+             e["h2d_bytes_per_step_all_ranks"] / e["ms_per_step"] / 1e6)]
 ts = bench["train_step"]
 L += ["", "configs[2] at N = 1, batch 128 (ms per step): decoder + loss as the reference writes them (eager) %.2f, drop-in model %.2f, fused "
       "criterion %.2f - the cuDNN hourglass backbone (out of scope, unchanged) is ~98 %% of the step." % (

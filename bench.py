@@ -793,6 +793,9 @@ def run_b200(args):
                     barrier()
             e2e["clocks"] = sampler.end_section("e2e")
             e2e_pool.clear()
+            torch.cuda.synchronize()
+            if hasattr(torch._C, "_host_emptyCache"):        # hand the pinned pool back before the next leg pins its own
+                torch._C._host_emptyCache()
             if not args.no_extras:
                 e2e_r1 = run_e2e_whole_frames()
 

@@ -96,6 +96,7 @@ L += ["## Variants of the step and the kernels of an inner stage (`%s_bench_n1.j
       "| what | samples/s | ms/step | step frac | kernels (ms, frac of measured peak on own bytes) |", "|---|---|---|---|---|"]
 for k, title in (("two_kernel_step", "SURVEY 8d accounting (forward, then backward+loss)"), ("raw_frames_step", "raw uint16 NYU frames (decode + hand rectangle in the kernel)"),
                  ("no_heat_store_step", "last stage without the heat-map store (what `forward_loss` runs)"),
+                 ("dense_tuple_compact_loss", "dense tuple written for the caller, loss evaluated from the taps (`targets='both'`)"),
                  ("sparse_targets", "compact targets (64-byte taps per joint)")):
     v = bench.get(k)
     if v:

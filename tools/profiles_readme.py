@@ -41,7 +41,7 @@ L = ["# profiles/ — round %s\n" % tag[1:],
      "| `%s_sass_excerpt.txt` | per-kernel instruction mix of the shipped `.so` (`tools/sass_excerpt.py`): which kernels contain `UBLKCP` (bulk TMA) / `SYNCS` (mbarrier) |" % tag,
      "| `%s_sanitizer_{racecheck,memcheck,initcheck,smoke}.log` | `compute-sanitizer` over the one-pass kernel (all 12 instantiations), the six-slot backward, fetch + window mode, the raw-frame window table, the bb loader and `smoke()` (`tools/sanitize.sh`) |" % tag,
      "| `%s_pcie_probe.json`, `%s_pcie_probe_n8.json`, `%s_topo*.txt` | `tools/pcie_probe.cu`: how a GPU can pull frames / crop windows from pinned host memory (design of the e2e feed); the same probe on 8 GPUs at once; `nvidia-smi topo -m` |" % (tag, tag, tag),
-     "| `%s_sanitizer_lean_racecheck.log`, `%s_ab_fused_lean.txt` | racecheck of `decoder_fused_lean_kernel` (the three-CTA one-pass variant, all 4 instantiations); `tools/ab_fused.py`: lean vs two-CTA one-pass kernel, ms and bit-identity |" % (tag, tag),
+     "| `%s_sanitizer_lean_racecheck.log`, `%s_sanitizer_window_table_{racecheck,memcheck}.log`, `%s_ab_fused_lean.txt` | racecheck of `decoder_fused_lean_kernel` (the three-CTA one-pass variant, all 4 instantiations); `tools/ab_fused.py`: lean vs two-CTA one-pass kernel, ms and bit-identity; racecheck + memcheck of the SFR builder with the sentinel window table and of the uneven-shard feed test |" % (tag, tag, tag),
      "| `%s_ab_sfr_window_table.txt`, `%s_ab_sfr_hoisted_taps.txt`, `%s_ab_sfr_packed_taps.txt` | `tools/ab_sfr.py` A/B of the SFR builder: sentinel window-table lookup (kept: 0.244 -> 0.212 ms compact raw frames); per-thread hoisted column taps at 4 / 5 / 6 CTAs per SM and packed 16-byte tap tables (both measured, rejected: register pressure / no gain) |" % (tag, tag, tag),
      "| `%s_bench_n8_balanced.json`, `%s_bench_n2_balanced.json` | `bench.py --no-extras` at N = 8 / 2 with the bandwidth-proportional shards of the e2e leg (`e2e.sharding`, `e2e.equal_shards`) |" % (tag, tag),
      "| `%s_sweep_hand17_n1.txt` | `tools/sweep_inference.py`: BASELINE configs[4] inference sweep, batch 256 .. 16384 |" % tag,
@@ -164,7 +164,7 @@ for r in bench["sweep"]["rows"]:
 
 # ---- sanitizer
 L += ["", "## compute-sanitizer\n"]
-for tool in ("racecheck", "memcheck", "initcheck", "smoke", "lean_racecheck"):
+for tool in ("racecheck", "memcheck", "initcheck", "smoke", "lean_racecheck", "window_table_racecheck", "window_table_memcheck"):
     f = os.path.join(P, "%s_sanitizer_%s.log" % (tag, tool))
     if os.path.isfile(f):
         lines = [l.strip() for l in open(f) if "SUMMARY" in l or "passed" in l or "failed" in l]

@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--augment", action="store_true",
                     help="build the SFR targets through the augmented branch (datasets.py:216-299, train.py defaults)")
+    ap.add_argument("--watchdog", type=int, default=480,
+                    help="seconds after the timed region at which rank 0 prints the line with whatever the extras "
+                         "have measured by then and exits (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-balance", action="store_true",
                     help="N > 1: keep equal shards in the e2e leg (default: also try bandwidth-proportional shards)")
@@ -395,6 +398,76 @@ def run_b200(args):
                          "algorithmic_bytes": per_launch_bytes[name], "achieved_gbs": gbs, "frac": gbs / peak}
     dominant = max(kernels, key=lambda k: kernels[k]["avg_ms"])
     step_kernel_ms = sum(k["avg_ms"] for k in kernels.values())
+    # Every extra starts as None and the line is built by a closure: if an extra hangs (a rank-local failure inside a
+    # collective at N > 1), rank 0's watchdog still prints the main line with what was measured so far.
+    e2e = e2e_r1 = two_kernel = sparse = raw_step = no_heat = both = inner = two_stage = graph_step = None
+    train_step = train_msra = sweep = cpu = gpu_eager = None
+    def build_line():
+        dk = kernels[dominant]
+        cfg = workload_config(shape, B, args.frame_format, args.augment, alpha, lambda_h, lambda_d)
+        cfg.update({"l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
+                          % (B * shape.height * shape.width * (4 if args.frame_format == "f32" else 2) / 1e9,
+                             B * J * 4096 * 4 / 1e9),
+                    "algorithmic_bytes_per_sample": step_bytes,
+                    "last_stage": "one pass (pwr_decoder_fwd_bwd_loss): forward + loss + backward visit z, D and "
+                                  "the targets once; the two-kernel route of SURVEY 8d is timed in `two_kernel_step`"})
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
+            "clocks": clocks,
+            "e2e": e2e,
+            "ms_per_step_median": median_ms, "value_median": B * world / (median_ms * 1e-3),
+            "e2e_whole_frames_r1_definition": e2e_r1,
+            "two_kernel_step": two_kernel,
+            "sparse_targets": sparse,
+            "raw_frames_step": raw_step,
+            "no_heat_store_step": no_heat, "dense_tuple_compact_loss": both,
+            "inner_stage": inner,
+            "two_stage_decoder": two_stage,
+            "graph_step": graph_step,
+            "train_step": train_step,
+            "train_msra": train_msra,
+            "sweep": sweep,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,
+                         "nominal_peak": NOMINAL_HBM_GBS, "frac_of_nominal": dk["achieved_gbs"] / NOMINAL_HBM_GBS,
+                         "avg_launch_ms": dk["avg_ms"], "algorithmic_bytes_per_launch": dk["algorithmic_bytes"],
+                         "share_of_step": dk["avg_ms"] / step_kernel_ms if step_kernel_ms else None},
+            "kernels": kernels,
+            "step_roofline_frac": (step_bytes * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
+            "step_roofline_frac_of_nominal": (step_bytes * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / NOMINAL_HBM_GBS,
+            "host_issue_ms_per_step": issue_ms,
+            "between_kernels_ms_per_step": gap_ms,
+            "cpu_baseline": cpu,
+            "gpu_eager_decoder": gpu_eager,
+            "errors": errors or None,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    tr = json.load(f)
+                line["roofline"]["traffic"] = tr.get(dominant, {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        return line
+
+    watchdog = None
+    if rank == 0 and args.watchdog > 0:
+        def fire():
+            try:
+                line_ = build_line()
+                line_["errors"] = dict(errors, watchdog="extras did not finish within %d s after the timed region; "
+                                                        "the line holds what was measured until then" % args.watchdog)
+                print(json.dumps(line_, default=str), file=OUT, flush=True)
+            finally:
+                os._exit(0)
+        watchdog = threading.Timer(args.watchdog, fire)
+        watchdog.daemon = True
+        watchdog.start()
 
     def kernel_table(prof_v, bytes_table):
         kms = {}
@@ -890,56 +963,9 @@ def run_b200(args):
     sampler.stop()
 
     if rank == 0:
-        dk = kernels[dominant]
-        cfg = workload_config(shape, B, args.frame_format, args.augment, alpha, lambda_h, lambda_d)
-        cfg.update({"l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
-                          % (B * shape.height * shape.width * (4 if args.frame_format == "f32" else 2) / 1e9,
-                             B * J * 4096 * 4 / 1e9),
-                    "algorithmic_bytes_per_sample": step_bytes,
-                    "last_stage": "one pass (pwr_decoder_fwd_bwd_loss): forward + loss + backward visit z, D and "
-                                  "the targets once; the two-kernel route of SURVEY 8d is timed in `two_kernel_step`"})
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfg,
-            "clocks": clocks,
-            "e2e": e2e,
-            "ms_per_step_median": median_ms, "value_median": B * world / (median_ms * 1e-3),
-            "e2e_whole_frames_r1_definition": e2e_r1,
-            "two_kernel_step": two_kernel,
-            "sparse_targets": sparse,
-            "raw_frames_step": raw_step,
-            "no_heat_store_step": no_heat, "dense_tuple_compact_loss": both,
-            "inner_stage": inner,
-            "two_stage_decoder": two_stage,
-            "graph_step": graph_step,
-            "train_step": train_step,
-            "train_msra": train_msra,
-            "sweep": sweep,
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": dk["frac"], "traffic": None, "peak_source": peak_src,
-                         "nominal_peak": NOMINAL_HBM_GBS, "frac_of_nominal": dk["achieved_gbs"] / NOMINAL_HBM_GBS,
-                         "avg_launch_ms": dk["avg_ms"], "algorithmic_bytes_per_launch": dk["algorithmic_bytes"],
-                         "share_of_step": dk["avg_ms"] / step_kernel_ms if step_kernel_ms else None},
-            "kernels": kernels,
-            "step_roofline_frac": (step_bytes * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
-            "step_roofline_frac_of_nominal": (step_bytes * B / (elapsed_ms / args.steps * 1e-3) / 1e9) / NOMINAL_HBM_GBS,
-            "host_issue_ms_per_step": issue_ms,
-            "between_kernels_ms_per_step": gap_ms,
-            "cpu_baseline": cpu,
-            "gpu_eager_decoder": gpu_eager,
-            "errors": errors or None,
-        }
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(traffic_file):
-            try:
-                with open(traffic_file) as f:
-                    tr = json.load(f)
-                line["roofline"]["traffic"] = tr.get(dominant, {}).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        if watchdog is not None:
+            watchdog.cancel()
+        line = build_line()
         print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -43,7 +43,7 @@ L = ["# profiles/ — round %s\n" % tag[1:],
      "| `%s_pcie_probe.json`, `%s_pcie_probe_n8.json`, `%s_topo*.txt` | `tools/pcie_probe.cu`: how a GPU can pull frames / crop windows from pinned host memory (design of the e2e feed); the same probe on 8 GPUs at once; `nvidia-smi topo -m` |" % (tag, tag, tag),
      "| `%s_sanitizer_lean_racecheck.log`, `%s_sanitizer_window_table_{racecheck,memcheck}.log`, `%s_ab_fused_lean.txt` | racecheck of `decoder_fused_lean_kernel` (the three-CTA one-pass variant, all 4 instantiations); `tools/ab_fused.py`: lean vs two-CTA one-pass kernel, ms and bit-identity; racecheck + memcheck of the SFR builder with the sentinel window table and of the uneven-shard feed test |" % (tag, tag, tag),
      "| `%s_ab_sfr_window_table.txt`, `%s_ab_sfr_hoisted_taps.txt`, `%s_ab_sfr_packed_taps.txt` | `tools/ab_sfr.py` A/B of the SFR builder: sentinel window-table lookup (kept: 0.244 -> 0.212 ms compact raw frames); per-thread hoisted column taps at 4 / 5 / 6 CTAs per SM and packed 16-byte tap tables (both measured, rejected: register pressure / no gain) |" % (tag, tag, tag),
-     "| `%s_bench_n8_balanced.json`, `%s_bench_n2_balanced.json` | `bench.py --no-extras` at N = 8 / 2 with the bandwidth-proportional shards of the e2e leg (`e2e.sharding`, `e2e.equal_shards`) |" % (tag, tag),
+     "| `%s_bench_n8_balanced.json`, `%s_bench_n4_balanced.json`, `%s_bench_n2_balanced.json` | `bench.py --no-extras` at N = 8 / 4 / 2 with the bandwidth-proportional shards of the e2e leg (`e2e.sharding`, `e2e.equal_shards`; at N = 2 and 4 the links of those boxes were equal and the equal shards stood) |" % (tag, tag, tag),
      "| `%s_sweep_hand17_n1.txt` | `tools/sweep_inference.py`: BASELINE configs[4] inference sweep, batch 256 .. 16384 |" % tag,
      "| `../tools/capture_profiles.sh`, `../tools/sanitize.sh` | the exact commands behind the above |", ""]
 

@@ -400,7 +400,7 @@ def run_b200(args):
     step_kernel_ms = sum(k["avg_ms"] for k in kernels.values())
     # Every extra starts as None and the line is built by a closure: if an extra hangs (a rank-local failure inside a
     # collective at N > 1), rank 0's watchdog still prints the main line with what was measured so far.
-    e2e = e2e_r1 = two_kernel = sparse = raw_step = no_heat = both = inner = two_stage = graph_step = None
+    e2e = e2e_r1 = two_kernel = sparse = raw_step = raw_sparse = no_heat = both = inner = two_stage = graph_step = None
     train_step = train_msra = sweep = cpu = gpu_eager = None
     def build_line():
         dk = kernels[dominant]
@@ -422,7 +422,7 @@ def run_b200(args):
             "e2e_whole_frames_r1_definition": e2e_r1,
             "two_kernel_step": two_kernel,
             "sparse_targets": sparse,
-            "raw_frames_step": raw_step,
+            "raw_frames_step": raw_step, "raw_frames_sparse_targets": raw_sparse,
             "no_heat_store_step": no_heat, "dense_tuple_compact_loss": both,
             "inner_stage": inner,
             "two_stage_decoder": two_stage,
@@ -522,7 +522,7 @@ def run_b200(args):
         return {"avg_ms": ms, "algorithmic_bytes_per_sample": bytes_per_sample, "achieved_gbs": gbs, "frac": gbs / peak,
                 "what": what}
 
-    two_kernel = sparse = raw_step = no_heat = both = None
+    two_kernel = sparse = raw_step = raw_sparse = no_heat = both = None
     try:
         if not args.no_sparse:
             # (1) SURVEY 8d's own accounting: forward kernel, then backward+loss kernel (the logits are read twice)
@@ -577,6 +577,14 @@ def run_b200(args):
                     roofline.step_one_pass_bytes(J),
                     "same step on raw uint16 %s frames resident in HBM, decoded inside the SFR kernel with the "
                     "load_from_text hand rectangle (SURVEY 8f-1)" % raw_fmt, "raw")
+                # (3b) both reductions of traffic at once: raw 16-bit frames in, compact targets out
+                raw_sparse = timed_variant(
+                    raw_frames, dict(raw_kw, targets="sparse"), True,
+                    {"pwr_sfr_build": roofline.sfr_build_sparse_bytes(J),
+                     "pwr_decoder_fwd_bwd_loss": roofline.decoder_fused_bytes(J, sparse=True)},
+                    roofline.step_one_pass_bytes(J, sparse=True),
+                    "raw uint16 %s frames (decode + hand rectangle in the SFR kernel) AND compact targets" % raw_fmt,
+                    "raw_sparse")
 
     except Exception as exc:      # an extra must never cost the main JSON line
         errors['variants'] = repr(exc)

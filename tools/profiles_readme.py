@@ -97,7 +97,8 @@ L += ["## Variants of the step and the kernels of an inner stage (`%s_bench_n1.j
 for k, title in (("two_kernel_step", "SURVEY 8d accounting (forward, then backward+loss)"), ("raw_frames_step", "raw uint16 NYU frames (decode + hand rectangle in the kernel)"),
                  ("no_heat_store_step", "last stage without the heat-map store (what `forward_loss` runs)"),
                  ("dense_tuple_compact_loss", "dense tuple written for the caller, loss evaluated from the taps (`targets='both'`)"),
-                 ("sparse_targets", "compact targets (64-byte taps per joint)")):
+                 ("sparse_targets", "compact targets (64-byte taps per joint)"),
+                 ("raw_frames_sparse_targets", "raw uint16 frames AND compact targets")):
     v = bench.get(k)
     if v:
         L.append("| `%s`: %s | %.2f M | %.3f | %.3f | %s |" % (k, title, v["value"] / 1e6, v["ms_per_step"], v["step_roofline_frac"],

@@ -84,10 +84,19 @@ def workload_name(shape, batch):
 
 
 def workload_config(shape, batch, frame_format, augment, alpha, lambda_h, lambda_d):
-    """The keys both arms print, so that the driver's `same_config` check compares like with like."""
-    return {"workload": workload_name(shape, batch), "batch_per_gpu": batch, "joints": shape.joints,
+    """The workload both arms are quoted on: they print this dict unchanged, so the driver's `same_config` check
+    compares like with like (arm-specific remarks live in `config_note`, outside it)."""
+    from pixelwiseregression_b200 import roofline
+    J = shape.joints
+    return {"workload": workload_name(shape, batch), "batch_per_gpu": batch, "joints": J,
             "frame_format": frame_format, "augment": bool(augment), "alpha": alpha, "lambda_h": lambda_h,
-            "lambda_d": lambda_d}
+            "lambda_d": lambda_d,
+            "l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
+                  % (batch * shape.height * shape.width * (4 if frame_format == "f32" else 2) / 1e9,
+                     batch * J * 4096 * 4 / 1e9),
+            "algorithmic_bytes_per_sample": roofline.step_one_pass_bytes(J),
+            "last_stage": "one pass (pwr_decoder_fwd_bwd_loss): forward + loss + backward visit z, D and "
+                          "the targets once; the two-kernel route of SURVEY 8d is timed in `two_kernel_step`"}
 
 
 def measured_peak():
@@ -192,14 +201,14 @@ def run_reference(args):
     res = {"sample": cpu_baseline.describe(shape, n, cores)}
     value = n * args.steps / dt
     cfg = workload_config(shape, args.batch, "f32", False, args.alpha, 1.0, 0.01)
-    cfg["note"] = ("each step is a bounded sample of %d samples of that workload on the host CPU; the port (fork pool over "
+    cfg_note = ("each step is a bounded sample of %d samples of that workload on the host CPU; the port (fork pool over "
                    "all cores, OpenCV resize / blur) is FASTER than the stock reference path, whose process_single_data "
                    "takes 38-63 ms per sample per DataLoader worker (SURVEY section 6; measured in the build container)" % n)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "config_note": cfg_note,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": res["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -405,12 +414,6 @@ def run_b200(args):
     def build_line():
         dk = kernels[dominant]
         cfg = workload_config(shape, B, args.frame_format, args.augment, alpha, lambda_h, lambda_d)
-        cfg.update({"l2": "inputs larger than L2 (frames %.2f GB, logits 2 x %.2f GB per GPU); no flush needed"
-                          % (B * shape.height * shape.width * (4 if args.frame_format == "f32" else 2) / 1e9,
-                             B * J * 4096 * 4 / 1e9),
-                    "algorithmic_bytes_per_sample": step_bytes,
-                    "last_stage": "one pass (pwr_decoder_fwd_bwd_loss): forward + loss + backward visit z, D and "
-                                  "the targets once; the two-kernel route of SURVEY 8d is timed in `two_kernel_step`"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,

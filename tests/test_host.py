@@ -94,3 +94,18 @@ def test_host_feed_and_fetch_refuse_to_run_without_cuda():
         sfr.fetch_windows(torch.zeros(1, 480, 640), torch.zeros(1, 3), torch.zeros(1), fx=1.0, fy=1.0)
     with pytest.raises(PwrError, match="kernel_size=7"):
         sfr.build_sfr(torch.zeros(1, 480, 640), np.zeros((1, 3)), 150.0, np.zeros((1, 14, 3)), fx=1.0, fy=1.0, kernel_size=9)
+
+
+def test_both_bench_arms_describe_the_same_workload():
+    """bench.py's two arms print `config` from one function with the same arguments, so the driver's same_config
+    check compares like with like (arm-specific remarks live outside it)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from pixelwiseregression_b200 import roofline, synth
+    a = bench.workload_config(synth.NYU, 4096, "f32", False, 1.0, 1.0, 0.01)
+    b = bench.workload_config(synth.NYU, 4096, "f32", False, 1.0, 1.0, 0.01)
+    assert a == b and a["algorithmic_bytes_per_sample"] == roofline.step_one_pass_bytes(14) == 2261404
+    assert "larger than L2" in a["l2"] and a["batch_per_gpu"] == 4096 and a["joints"] == 14
